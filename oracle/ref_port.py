@@ -348,11 +348,11 @@ class ModelOneB(_Base):
         super().__init__()
         input_size = torch.Size(input_size)
         n = input_size.numel()
-        self.manifold = PoincareBall(latent_curvature)
+        self.latent_manifold = PoincareBall(latent_curvature)
         self.prior_scale, self.beta, self.kl_loss_method = prior_scale, beta, kl_loss_method
         self.last_activation, self.loss_recon_method = last_activation, loss_recon_method
         self.encoder = nn.Sequential(*([] if len(input_size) == 1 else [nn.Flatten()]), nn.Linear(n, hidden_layer_dim), nn.GELU())
-        self.mu = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), ExpMap0(self.manifold))
+        self.mu = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), ExpMap0(self.latent_manifold))
         self.scale = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), nn.Softplus())
         tail = [] if len(input_size) == 1 else [nn.Unflatten(1, input_size)]
         if last_activation == "sigmoid":
@@ -360,9 +360,13 @@ class ModelOneB(_Base):
         elif last_activation == "softplus":
             tail.append(nn.Softplus())
         self.decoder = nn.Sequential(
-            Distance2PoincareHyperplanes(latent_dim, hidden_layer_dim, ball=self.manifold),
+            Distance2PoincareHyperplanes(latent_dim, hidden_layer_dim, ball=self.latent_manifold),
             nn.GELU(), nn.Linear(hidden_layer_dim, n), *tail,
         )
+
+    @property
+    def manifold(self):
+        return self.latent_manifold
 
     def forward(self, x, eps=None):
         h = self.encoder(x)
