@@ -1,0 +1,424 @@
+// K4 / K5 / fused latent head: WrappedNormal reparameterised sample, log-density, Monte-Carlo KL.
+// reference: hyperbolic_vae/distributions/wrapped_normal.py:66-89, manifolds.py:25-35 (logdetexp),
+//            models/vae_hyperbolic.py:126-127,191-216 (posterior built twice + prior per step).
+//
+// Each kernel is one pass: a row (length D) sits in the registers of G lanes, all norms / inner
+// products are warp-shuffle reductions, nothing is staged in HBM between sample and KL.
+// Algorithmic bytes per row (fp32): sample fwd 16D, bwd 24D; log_prob fwd 12D+4, bwd 24D+4;
+// fused head fwd 16D+4 (eps injected), bwd 20D+4.
+#include "hvae_common.cuh"
+
+namespace hvae {
+
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2 pi))
+
+// ---- expmap with lambda given (shared with row_ops' formula; repeated here to keep TU-local inlining) ---
+template <int G, int EPL>
+struct SampleCtx {
+    RowSlice<G, EPL> u, w, zpre;
+    float mu2, m, lam, un_raw, un, th, t, pn;
+    bool m_clamped, hit;
+    MAddCtx ma;
+};
+
+// z = project(mu (+) tanh(sc lam ||u||/2)/sc * u/||u||),  u = (sigma*eps)/lam   (lam = lambda_mu; lambda_0 = 2 cancels)
+template <int G, int EPL>
+__device__ __forceinline__ void sample_row(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& sig,
+                                           const RowSlice<G, EPL>& eps, RowSlice<G, EPL>& z, SampleCtx<G, EPL>& k,
+                                           const Ball& ball) {
+    k.mu2 = sqnorm<G, EPL>(mu);
+    const float m = 1.0f - ball.c * k.mu2;
+    k.m_clamped = m < kMinNorm;
+    k.m = fmaxf(m, kMinNorm);
+    k.lam = 2.0f / k.m;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) k.u.v[i] = (sig.v[i] * eps.v[i]) / k.lam;
+    k.un_raw = sqrtf(sqnorm<G, EPL>(k.u));
+    k.un = fmaxf(k.un_raw, kMinNorm);
+    k.th = ball.sc * ((k.lam / 2.0f) * k.un);
+    k.t = tanh_c(k.th);
+    const float q = ball.rsc * k.t;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) k.w.v[i] = q * (k.u.v[i] / k.un);
+    k.ma = mobius_add_raw<G, EPL>(mu, k.w, k.zpre, ball);
+    z = k.zpre;
+    k.hit = project_inplace<G, EPL>(z, ball, k.pn);
+}
+
+// g: dL/dz (post-projection). Adds into gmu, writes gsig.
+template <int G, int EPL>
+__device__ __forceinline__ void sample_row_bwd(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& eps,
+                                               const SampleCtx<G, EPL>& k, RowSlice<G, EPL> g,
+                                               RowSlice<G, EPL>& gmu_acc, RowSlice<G, EPL>& gsig_acc, const Ball& ball) {
+    project_bwd<G, EPL>(g, k.zpre, k.pn, k.hit, ball);
+    RowSlice<G, EPL> gx, gw;
+    mobius_add_raw_bwd<G, EPL>(mu, k.w, k.ma, g, gx, gw, ball);
+    const float sech2 = (1.0f - k.t * k.t) * tanh_mask(k.th);
+    const float q = ball.rsc * k.t / k.un;
+    const float dq_dun = (sech2 * (k.lam * 0.5f) - q) / k.un;
+    const float dq_dlam = sech2 * 0.5f;
+    const float gwu = dot<G, EPL>(gw, k.u);
+    const float coef = (k.un_raw >= kMinNorm) ? dq_dun * gwu / k.un_raw : 0.0f;
+    RowSlice<G, EPL> gu;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) gu.v[i] = q * gw.v[i] + coef * k.u.v[i];
+    // u = v/lam: gv = gu/lam ; glam += -(gu.u)/lam
+    const float guu = dot<G, EPL>(gu, k.u);
+    const float glam = dq_dlam * gwu - guu / k.lam;
+    const float gmu2 = k.m_clamped ? 0.0f : glam * (2.0f / (k.m * k.m)) * ball.c;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        gmu_acc.v[i] += gx.v[i] + 2.0f * gmu2 * mu.v[i];
+        gsig_acc.v[i] += (gu.v[i] / k.lam) * eps.v[i];
+    }
+}
+
+// ---- log-density of WrappedNormal(mu, sigma) at z -----------------------------------------------------
+template <int G, int EPL>
+struct LogProbCtx {
+    RowSlice<G, EPL> xn, s;  // xn = -mu, s = (-mu)(+)z
+    float r, sn, phi, a, d;
+    MAddCtx ma;
+};
+
+template <int G, int EPL, bool kScalarSigma>
+__device__ __forceinline__ float logprob_row(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& sig, float sigma0,
+                                             const RowSlice<G, EPL>& z, LogProbCtx<G, EPL>& k, const Ball& ball, int D,
+                                             int lg) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) k.xn.v[i] = -mu.v[i];
+    k.ma = mobius_add_raw<G, EPL>(k.xn, z, k.s, ball);
+    k.r = sqrtf(sqnorm<G, EPL>(k.s));
+    k.sn = fmaxf(k.r, kMinNorm);
+    k.a = ball.sc * k.sn;
+    k.phi = 2.0f * artanh_c(k.a) / k.a;  // u = phi * s  (lambda_mu cancels: logmap /lam, transp *lam/2, *lambda_0)
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int idx = lg + i * G;
+        if (idx < D) {
+            const float sg = kScalarSigma ? sigma0 : sig.v[i];
+            const float ui = k.phi * k.s.v[i];
+            acc += -(ui * ui) / (2.0f * (sg * sg)) - logf(sg) - kHalfLog2Pi;
+        }
+    }
+    acc = group_sum<G>(acc);
+    k.d = 2.0f * (ball.rsc * artanh_c(ball.sc * k.r));
+    // logdetexp = (D-1) (log sinh(sc d) - log sc - log d) = (D-1) log(sinh(sc d)/(sc d))
+    return acc - (float)(D - 1) * log_sinhc(ball.sc * k.d);
+}
+
+// g: upstream scalar. Accumulates gmu, gsig, gz.
+template <int G, int EPL, bool kScalarSigma>
+__device__ __forceinline__ void logprob_row_bwd(const RowSlice<G, EPL>& sig, float sigma0, const RowSlice<G, EPL>& z,
+                                                const LogProbCtx<G, EPL>& k, float g, RowSlice<G, EPL>& gmu_acc,
+                                                RowSlice<G, EPL>& gsig_acc, RowSlice<G, EPL>& gz_acc, const Ball& ball,
+                                                int D, int lg) {
+    RowSlice<G, EPL> gu;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int idx = lg + i * G;
+        const float sg = kScalarSigma ? sigma0 : sig.v[i];
+        const float ui = k.phi * k.s.v[i];
+        const bool on = idx < D;
+        gu.v[i] = on ? -g * ui / (sg * sg) : 0.0f;
+        if (!kScalarSigma && on) gsig_acc.v[i] += g * ((ui * ui) / (sg * sg * sg) - 1.0f / sg);
+    }
+    const float dphi = (2.0f * artanh_grad(k.a) - k.phi) / k.sn;
+    const float gus = dot<G, EPL>(gu, k.s);
+    float coef = (k.r >= kMinNorm) ? dphi * gus / k.r : 0.0f;
+    // -(D-1) d/dr log_sinhc(sc d(r)),  dd/dr = 2 artanh'(sc r)
+    if (k.r > 0.0f) {
+        const float dL = (float)(D - 1) * dlog_sinhc(ball.sc * k.d) * ball.sc * (2.0f * artanh_grad(ball.sc * k.r));
+        coef -= g * dL / k.r;
+    }
+    RowSlice<G, EPL> gs, gx, gy;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) gs.v[i] = k.phi * gu.v[i] + coef * k.s.v[i];
+    mobius_add_raw_bwd<G, EPL>(k.xn, z, k.ma, gs, gx, gy, ball);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        gmu_acc.v[i] -= gx.v[i];
+        gz_acc.v[i] += gy.v[i];
+    }
+}
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+template <int G, int EPL>
+__global__ void __launch_bounds__(kRowThreads) k_wrapped_sample_fwd(const float* __restrict__ mu,
+                                                                     const float* __restrict__ sigma,
+                                                                     const float* __restrict__ eps, float* __restrict__ z,
+                                                                     int64_t S, int64_t B, int D, Ball ball) {
+    HVAE_ROW_PROLOGUE(G)
+    const int64_t rows = S * B;
+    for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
+        const int64_t row = r0 + sub;
+        const bool valid = row < rows;
+        const int64_t b = valid ? row % B : 0;
+        RowSlice<G, EPL> m, sg, e, zr;
+        m.load(mu, b, D, lg, valid);
+        sg.load(sigma, b, D, lg, valid);
+        e.load(eps, row, D, lg, valid);
+        SampleCtx<G, EPL> k;
+        sample_row<G, EPL>(m, sg, e, zr, k, ball);
+        zr.store(z, row, D, lg, valid);
+    }
+}
+
+// one lane group per b; loops over the sample dim so that gmu/gsigma are complete sums
+template <int G, int EPL>
+__global__ void __launch_bounds__(kRowThreads) k_wrapped_sample_bwd(const float* __restrict__ mu,
+                                                                     const float* __restrict__ sigma,
+                                                                     const float* __restrict__ eps,
+                                                                     const float* __restrict__ gz, float* __restrict__ gmu,
+                                                                     float* __restrict__ gsigma, int64_t S, int64_t B, int D,
+                                                                     Ball ball) {
+    HVAE_ROW_PROLOGUE(G)
+    for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
+        const int64_t b = r0 + sub;
+        const bool valid = b < B;
+        RowSlice<G, EPL> m, sg, gm, gs;
+        m.load(mu, b, D, lg, valid);
+        sg.load(sigma, b, D, lg, valid);
+        gm.zero();
+        gs.zero();
+        for (int64_t s = 0; s < S; ++s) {
+            RowSlice<G, EPL> e, g, zr;
+            e.load(eps, s * B + b, D, lg, valid);
+            g.load(gz, s * B + b, D, lg, valid);
+            SampleCtx<G, EPL> k;
+            sample_row<G, EPL>(m, sg, e, zr, k, ball);
+            sample_row_bwd<G, EPL>(m, e, k, g, gm, gs, ball);
+        }
+        gm.store(gmu, b, D, lg, valid);
+        gs.store(gsigma, b, D, lg, valid);
+    }
+}
+
+template <int G, int EPL, bool kPrior>
+__global__ void __launch_bounds__(kRowThreads) k_wrapped_logprob_fwd(const float* __restrict__ mu,
+                                                                      const float* __restrict__ sigma, float sigma0,
+                                                                      const float* __restrict__ z, float* __restrict__ logp,
+                                                                      int64_t S, int64_t B, int D, Ball ball) {
+    HVAE_ROW_PROLOGUE(G)
+    const int64_t rows = S * B;
+    for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
+        const int64_t row = r0 + sub;
+        const bool valid = row < rows;
+        const int64_t b = valid ? row % B : 0;
+        RowSlice<G, EPL> m, sg, zr;
+        if (kPrior) {
+            m.zero();
+            sg.zero();
+        } else {
+            m.load(mu, b, D, lg, valid);
+            sg.load(sigma, b, D, lg, valid);
+            if (!valid) {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
+            }
+        }
+        zr.load(z, row, D, lg, valid);
+        LogProbCtx<G, EPL> k;
+        const float lp = logprob_row<G, EPL, kPrior>(m, sg, sigma0, zr, k, ball, D, lg);
+        if (valid && lg == 0) logp[row] = lp;
+    }
+}
+
+template <int G, int EPL, bool kPrior>
+__global__ void __launch_bounds__(kRowThreads) k_wrapped_logprob_bwd(const float* __restrict__ mu,
+                                                                      const float* __restrict__ sigma, float sigma0,
+                                                                      const float* __restrict__ z,
+                                                                      const float* __restrict__ glogp, float* __restrict__ gmu,
+                                                                      float* __restrict__ gsigma, float* __restrict__ gz,
+                                                                      int64_t S, int64_t B, int D, Ball ball) {
+    HVAE_ROW_PROLOGUE(G)
+    for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
+        const int64_t b = r0 + sub;
+        const bool valid = b < B;
+        RowSlice<G, EPL> m, sg, gm, gs;
+        if (kPrior) {
+            m.zero();
+            sg.zero();
+        } else {
+            m.load(mu, b, D, lg, valid);
+            sg.load(sigma, b, D, lg, valid);
+            if (!valid) {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
+            }
+        }
+        gm.zero();
+        gs.zero();
+        for (int64_t s = 0; s < S; ++s) {
+            const int64_t row = s * B + b;
+            RowSlice<G, EPL> zr, gzr;
+            zr.load(z, row, D, lg, valid);
+            gzr.zero();
+            const float g = valid ? __ldg(glogp + row) : 0.0f;
+            LogProbCtx<G, EPL> k;
+            logprob_row<G, EPL, kPrior>(m, sg, sigma0, zr, k, ball, D, lg);
+            logprob_row_bwd<G, EPL, kPrior>(sg, sigma0, zr, k, g, gm, gs, gzr, ball, D, lg);
+            if (gz) gzr.store(gz, row, D, lg, valid);
+        }
+        if (!kPrior) {
+            if (gmu) gm.store(gmu, b, D, lg, valid);
+            if (gsigma) gs.store(gsigma, b, D, lg, valid);
+        }
+    }
+}
+
+// ---- fused latent head: z = rsample, kl = log q(z) - log p(z) ------------------------------------------
+template <int G, int EPL>
+__global__ void __launch_bounds__(kRowThreads) k_latent_head_fwd(const float* __restrict__ mu, const float* __restrict__ sigma,
+                                                                  const float* __restrict__ eps, float prior_scale,
+                                                                  float* __restrict__ z, float* __restrict__ kl, int64_t B,
+                                                                  int D, Ball ball) {
+    HVAE_ROW_PROLOGUE(G)
+    for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
+        const int64_t b = r0 + sub;
+        const bool valid = b < B;
+        RowSlice<G, EPL> m, sg, e, zr, zero;
+        m.load(mu, b, D, lg, valid);
+        sg.load(sigma, b, D, lg, valid);
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
+        }
+        e.load(eps, b, D, lg, valid);
+        zero.zero();
+        SampleCtx<G, EPL> k;
+        sample_row<G, EPL>(m, sg, e, zr, k, ball);
+        zr.store(z, b, D, lg, valid);
+        LogProbCtx<G, EPL> kq, kp;
+        const float lq = logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
+        const float lp = logprob_row<G, EPL, true>(zero, zero, prior_scale, zr, kp, ball, D, lg);
+        if (valid && lg == 0) kl[b] = lq - lp;
+    }
+}
+
+template <int G, int EPL>
+__global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __restrict__ mu, const float* __restrict__ sigma,
+                                                                  const float* __restrict__ eps, float prior_scale,
+                                                                  const float* __restrict__ gz, const float* __restrict__ gkl,
+                                                                  float* __restrict__ gmu, float* __restrict__ gsigma,
+                                                                  int64_t B, int D, Ball ball) {
+    HVAE_ROW_PROLOGUE(G)
+    for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
+        const int64_t b = r0 + sub;
+        const bool valid = b < B;
+        RowSlice<G, EPL> m, sg, e, zr, zero, gm, gs, gzt, dummy;
+        m.load(mu, b, D, lg, valid);
+        sg.load(sigma, b, D, lg, valid);
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
+        }
+        e.load(eps, b, D, lg, valid);
+        zero.zero();
+        gm.zero();
+        gs.zero();
+        dummy.zero();
+        if (gz) gzt.load(gz, b, D, lg, valid); else gzt.zero();
+        const float g = (gkl && valid) ? __ldg(gkl + b) : 0.0f;
+        SampleCtx<G, EPL> k;
+        sample_row<G, EPL>(m, sg, e, zr, k, ball);
+        {
+            LogProbCtx<G, EPL> kq;
+            logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
+            logprob_row_bwd<G, EPL, false>(sg, 0.0f, zr, kq, g, gm, gs, gzt, ball, D, lg);
+        }
+        {
+            LogProbCtx<G, EPL> kp;
+            logprob_row<G, EPL, true>(zero, zero, prior_scale, zr, kp, ball, D, lg);
+            logprob_row_bwd<G, EPL, true>(zero, prior_scale, zr, kp, -g, dummy, dummy, gzt, ball, D, lg);
+        }
+        sample_row_bwd<G, EPL>(m, e, k, gzt, gm, gs, ball);
+        gm.store(gmu, b, D, lg, valid);
+        gs.store(gsigma, b, D, lg, valid);
+    }
+}
+
+}  // namespace hvae
+
+using namespace hvae;
+
+#define HVAE_CHECK_SBD(S, B, D)                                                   \
+    if ((S) < 0 || (B) < 0 || (D) <= 0 || (D) > kMaxRowDim) return HVAE_ESHAPE;    \
+    if ((S) == 0 || (B) == 0) return HVAE_OK;
+
+#define HVAE_DISPATCH_T(KERN, TARG, D, rows, s, ...)                                                                 \
+    do {                                                                                                             \
+        if ((D) <= 2)        KERN<1, 2, TARG><<<row_grid((rows), 1), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 4)   KERN<1, 4, TARG><<<row_grid((rows), 1), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 8)   KERN<2, 4, TARG><<<row_grid((rows), 2), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 16)  KERN<4, 4, TARG><<<row_grid((rows), 4), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 32)  KERN<8, 4, TARG><<<row_grid((rows), 8), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 64)  KERN<16, 4, TARG><<<row_grid((rows), 16), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
+        else if ((D) <= 128) KERN<32, 4, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
+        else if ((D) <= 256) KERN<32, 8, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
+        else if ((D) <= 512) KERN<32, 16, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);          \
+        else                 KERN<32, 32, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);          \
+    } while (0)
+
+extern "C" int hvae_wrapped_sample_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, int64_t S,
+                                           int64_t B, int64_t D, float c, void* stream) {
+    HVAE_CHECK_SBD(S, B, D)
+    if (!mu || !sigma || !eps || !z) return HVAE_EARG;
+    HVAE_ROW_DISPATCH(k_wrapped_sample_fwd, D, S * B, (cudaStream_t)stream, mu, sigma, eps, z, S, B, (int)D, make_ball(c));
+    return check_launch();
+}
+
+extern "C" int hvae_wrapped_sample_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
+                                           float* gmu, float* gsigma, int64_t S, int64_t B, int64_t D, float c,
+                                           void* stream) {
+    HVAE_CHECK_SBD(S, B, D)
+    if (!mu || !sigma || !eps || !gz || !gmu || !gsigma) return HVAE_EARG;
+    HVAE_ROW_DISPATCH(k_wrapped_sample_bwd, D, B, (cudaStream_t)stream, mu, sigma, eps, gz, gmu, gsigma, S, B, (int)D,
+                      make_ball(c));
+    return check_launch();
+}
+
+extern "C" int hvae_wrapped_logprob_fwd_f32(const float* mu, const float* sigma, float sigma0, const float* z, float* logp,
+                                            int64_t S, int64_t B, int64_t D, float c, void* stream) {
+    HVAE_CHECK_SBD(S, B, D)
+    if (!z || !logp || ((mu == nullptr) != (sigma == nullptr))) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Ball ball = make_ball(c);
+    if (mu) HVAE_DISPATCH_T(k_wrapped_logprob_fwd, false, D, S * B, s, mu, sigma, sigma0, z, logp, S, B, (int)D, ball);
+    else    HVAE_DISPATCH_T(k_wrapped_logprob_fwd, true, D, S * B, s, mu, sigma, sigma0, z, logp, S, B, (int)D, ball);
+    return check_launch();
+}
+
+extern "C" int hvae_wrapped_logprob_bwd_f32(const float* mu, const float* sigma, float sigma0, const float* z,
+                                            const float* glogp, float* gmu, float* gsigma, float* gz, int64_t S, int64_t B,
+                                            int64_t D, float c, void* stream) {
+    HVAE_CHECK_SBD(S, B, D)
+    if (!z || !glogp || ((mu == nullptr) != (sigma == nullptr))) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Ball ball = make_ball(c);
+    if (mu) HVAE_DISPATCH_T(k_wrapped_logprob_bwd, false, D, B, s, mu, sigma, sigma0, z, glogp, gmu, gsigma, gz, S, B, (int)D, ball);
+    else    HVAE_DISPATCH_T(k_wrapped_logprob_bwd, true, D, B, s, mu, sigma, sigma0, z, glogp, gmu, gsigma, gz, S, B, (int)D, ball);
+    return check_launch();
+}
+
+extern "C" int hvae_latent_head_fwd_f32(const float* mu, const float* sigma, const float* eps, float prior_scale, float* z,
+                                        float* kl, int64_t B, int64_t D, float c, void* stream) {
+    HVAE_CHECK_SBD(1, B, D)
+    if (!mu || !sigma || !eps || !z || !kl) return HVAE_EARG;
+    HVAE_ROW_DISPATCH(k_latent_head_fwd, D, B, (cudaStream_t)stream, mu, sigma, eps, prior_scale, z, kl, B, (int)D,
+                      make_ball(c));
+    return check_launch();
+}
+
+extern "C" int hvae_latent_head_bwd_f32(const float* mu, const float* sigma, const float* eps, float prior_scale,
+                                        const float* gz, const float* gkl, float* gmu, float* gsigma, int64_t B, int64_t D,
+                                        float c, void* stream) {
+    HVAE_CHECK_SBD(1, B, D)
+    if (!mu || !sigma || !eps || !gmu || !gsigma) return HVAE_EARG;
+    HVAE_ROW_DISPATCH(k_latent_head_bwd, D, B, (cudaStream_t)stream, mu, sigma, eps, prior_scale, gz, gkl, gmu, gsigma, B,
+                      (int)D, make_ball(c));
+    return check_launch();
+}

@@ -1,0 +1,391 @@
+"""torch custom ops (`torch.ops.hvae.*`) over the C ABI, each with an ANALYTIC backward op — autograd
+never differentiates through primitives on this path (BASELINE.json north_star (4)).
+
+All ops take contiguous float32 CUDA tensors flattened to rows; the public helpers below do the
+reshaping.  `c` is float(manifold.c) — the fp32 softplus round-trip value, not the ctor argument.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi as C
+
+_op = torch.library.custom_op
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows(t: Tensor) -> Tensor:
+    return _c(t).view(-1, t.shape[-1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# unary row maps: expmap0 / logmap0
+# ---------------------------------------------------------------------------------------------------
+def _unary(name):
+    fwd_sym, bwd_sym = "hvae_%s_fwd_f32" % name, "hvae_%s_bwd_f32" % name
+
+    @_op("hvae::%s_fwd" % name, mutates_args=())
+    def fwd(x: Tensor, c: float) -> Tensor:
+        C.require_cuda(x)
+        y = torch.empty_like(x)
+        C.call(fwd_sym, C.ptr(x), C.ptr(y), x.shape[0], x.shape[1], c, C.stream())
+        return y
+
+    @fwd.register_fake
+    def _(x, c):
+        return torch.empty_like(x)
+
+    @_op("hvae::%s_bwd" % name, mutates_args=())
+    def bwd(x: Tensor, g: Tensor, c: float) -> Tensor:
+        C.require_cuda(x, g)
+        gx = torch.empty_like(x)
+        C.call(bwd_sym, C.ptr(x), C.ptr(g), C.ptr(gx), x.shape[0], x.shape[1], c, C.stream())
+        return gx
+
+    @bwd.register_fake
+    def _(x, g, c):
+        return torch.empty_like(x)
+
+    def setup(ctx, inputs, output):
+        ctx.save_for_backward(inputs[0])
+        ctx.c = inputs[1]
+
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return bwd(x, _c(g), ctx.c), None
+
+    fwd.register_autograd(backward, setup_context=setup)
+    return fwd, bwd
+
+
+expmap0_fwd, expmap0_bwd = _unary("expmap0")
+logmap0_fwd, logmap0_bwd = _unary("logmap0")
+
+
+def expmap0(u: Tensor, c: float) -> Tensor:
+    return expmap0_fwd(_rows(u), c).view(u.shape)
+
+
+def logmap0(y: Tensor, c: float) -> Tensor:
+    return logmap0_fwd(_rows(y), c).view(y.shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+# binary row maps: mobius_add / expmap / logmap / dist
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::mobius_add_fwd", mutates_args=())
+def mobius_add_fwd(x: Tensor, y: Tensor, c: float, project: bool) -> Tensor:
+    C.require_cuda(x, y)
+    out = torch.empty_like(x)
+    C.call("hvae_mobius_add_fwd_f32", C.ptr(x), C.ptr(y), C.ptr(out), x.shape[0], x.shape[1], c, int(project), C.stream())
+    return out
+
+
+@mobius_add_fwd.register_fake
+def _(x, y, c, project):
+    return torch.empty_like(x)
+
+
+@_op("hvae::mobius_add_bwd", mutates_args=())
+def mobius_add_bwd(x: Tensor, y: Tensor, g: Tensor, c: float, project: bool) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(x, y, g)
+    gx, gy = torch.empty_like(x), torch.empty_like(y)
+    C.call("hvae_mobius_add_bwd_f32", C.ptr(x), C.ptr(y), C.ptr(g), C.ptr(gx), C.ptr(gy), x.shape[0], x.shape[1], c,
+           int(project), C.stream())
+    return gx, gy
+
+
+@mobius_add_bwd.register_fake
+def _(x, y, g, c, project):
+    return torch.empty_like(x), torch.empty_like(y)
+
+
+def _madd_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.c, ctx.project = inputs[2], inputs[3]
+
+
+def _madd_backward(ctx, g):
+    x, y = ctx.saved_tensors
+    gx, gy = mobius_add_bwd(x, y, _c(g), ctx.c, ctx.project)
+    return gx, gy, None, None
+
+
+mobius_add_fwd.register_autograd(_madd_backward, setup_context=_madd_setup)
+
+
+def _broadcast_rows(a: Tensor, b: Tensor):
+    if a.shape != b.shape:
+        a, b = torch.broadcast_tensors(a, b)
+    return _rows(a), _rows(b), a.shape
+
+
+def mobius_add(x: Tensor, y: Tensor, c: float, project: bool = True) -> Tensor:
+    xr, yr, shape = _broadcast_rows(x, y)
+    return mobius_add_fwd(xr, yr, c, project).view(shape)
+
+
+def _binary(name, out_is_scalar=False):
+    fwd_sym, bwd_sym = "hvae_%s_fwd_f32" % name, "hvae_%s_bwd_f32" % name
+
+    @_op("hvae::%s_fwd" % name, mutates_args=())
+    def fwd(x: Tensor, y: Tensor, c: float) -> Tensor:
+        C.require_cuda(x, y)
+        out = x.new_empty(x.shape[0]) if out_is_scalar else torch.empty_like(x)
+        C.call(fwd_sym, C.ptr(x), C.ptr(y), C.ptr(out), x.shape[0], x.shape[1], c, C.stream())
+        return out
+
+    @fwd.register_fake
+    def _(x, y, c):
+        return x.new_empty(x.shape[0]) if out_is_scalar else torch.empty_like(x)
+
+    @_op("hvae::%s_bwd" % name, mutates_args=())
+    def bwd(x: Tensor, y: Tensor, g: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+        C.require_cuda(x, y, g)
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        C.call(bwd_sym, C.ptr(x), C.ptr(y), C.ptr(g), C.ptr(gx), C.ptr(gy), x.shape[0], x.shape[1], c, C.stream())
+        return gx, gy
+
+    @bwd.register_fake
+    def _(x, y, g, c):
+        return torch.empty_like(x), torch.empty_like(y)
+
+    def setup(ctx, inputs, output):
+        ctx.save_for_backward(inputs[0], inputs[1])
+        ctx.c = inputs[2]
+
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        gx, gy = bwd(x, y, _c(g), ctx.c)
+        return gx, gy, None
+
+    fwd.register_autograd(backward, setup_context=setup)
+    return fwd, bwd
+
+
+expmap_fwd, expmap_bwd = _binary("expmap")
+logmap_fwd, logmap_bwd = _binary("logmap")
+dist_fwd, dist_bwd = _binary("dist", out_is_scalar=True)
+
+
+def expmap(x: Tensor, u: Tensor, c: float) -> Tensor:
+    xr, ur, shape = _broadcast_rows(x, u)
+    return expmap_fwd(xr, ur, c).view(shape)
+
+
+def logmap(x: Tensor, y: Tensor, c: float) -> Tensor:
+    xr, yr, shape = _broadcast_rows(x, y)
+    return logmap_fwd(xr, yr, c).view(shape)
+
+
+def dist(x: Tensor, y: Tensor, c: float, keepdim: bool = False) -> Tensor:
+    xr, yr, shape = _broadcast_rows(x, y)
+    d = dist_fwd(xr, yr, c).view(shape[:-1])
+    return d.unsqueeze(-1) if keepdim else d
+
+
+# ---------------------------------------------------------------------------------------------------
+# WrappedNormal: sample / log_prob / fused latent head
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::wrapped_sample_fwd", mutates_args=())
+def wrapped_sample_fwd(mu: Tensor, sigma: Tensor, eps: Tensor, c: float) -> Tensor:
+    """mu, sigma: (B,D); eps: (S,B,D) -> z (S,B,D)"""
+    C.require_cuda(mu, sigma, eps)
+    S, B, D = eps.shape
+    z = torch.empty_like(eps)
+    C.call("hvae_wrapped_sample_fwd_f32", C.ptr(mu), C.ptr(sigma), C.ptr(eps), C.ptr(z), S, B, D, c, C.stream())
+    return z
+
+
+@wrapped_sample_fwd.register_fake
+def _(mu, sigma, eps, c):
+    return torch.empty_like(eps)
+
+
+@_op("hvae::wrapped_sample_bwd", mutates_args=())
+def wrapped_sample_bwd(mu: Tensor, sigma: Tensor, eps: Tensor, gz: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(mu, sigma, eps, gz)
+    S, B, D = eps.shape
+    gmu, gsig = torch.empty_like(mu), torch.empty_like(sigma)
+    C.call("hvae_wrapped_sample_bwd_f32", C.ptr(mu), C.ptr(sigma), C.ptr(eps), C.ptr(gz), C.ptr(gmu), C.ptr(gsig), S, B, D,
+           c, C.stream())
+    return gmu, gsig
+
+
+@wrapped_sample_bwd.register_fake
+def _(mu, sigma, eps, gz, c):
+    return torch.empty_like(mu), torch.empty_like(sigma)
+
+
+def _ws_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], inputs[2])
+    ctx.c = inputs[3]
+
+
+def _ws_backward(ctx, gz):
+    mu, sigma, eps = ctx.saved_tensors
+    gmu, gsig = wrapped_sample_bwd(mu, sigma, eps, _c(gz), ctx.c)
+    return gmu, gsig, None, None
+
+
+wrapped_sample_fwd.register_autograd(_ws_backward, setup_context=_ws_setup)
+
+
+@_op("hvae::wrapped_logprob_fwd", mutates_args=())
+def wrapped_logprob_fwd(mu: Tensor, sigma: Tensor, z: Tensor, c: float) -> Tensor:
+    """mu, sigma: (B,D); z: (S,B,D) -> logp (S,B)"""
+    C.require_cuda(mu, sigma, z)
+    S, B, D = z.shape
+    out = z.new_empty(S, B)
+    C.call("hvae_wrapped_logprob_fwd_f32", C.ptr(mu), C.ptr(sigma), 0.0, C.ptr(z), C.ptr(out), S, B, D, c, C.stream())
+    return out
+
+
+@wrapped_logprob_fwd.register_fake
+def _(mu, sigma, z, c):
+    return z.new_empty(z.shape[0], z.shape[1])
+
+
+@_op("hvae::wrapped_logprob_bwd", mutates_args=())
+def wrapped_logprob_bwd(mu: Tensor, sigma: Tensor, z: Tensor, g: Tensor, c: float) -> Tuple[Tensor, Tensor, Tensor]:
+    C.require_cuda(mu, sigma, z, g)
+    S, B, D = z.shape
+    gmu, gsig, gz = torch.empty_like(mu), torch.empty_like(sigma), torch.empty_like(z)
+    C.call("hvae_wrapped_logprob_bwd_f32", C.ptr(mu), C.ptr(sigma), 0.0, C.ptr(z), C.ptr(g), C.ptr(gmu), C.ptr(gsig),
+           C.ptr(gz), S, B, D, c, C.stream())
+    return gmu, gsig, gz
+
+
+@wrapped_logprob_bwd.register_fake
+def _(mu, sigma, z, g, c):
+    return torch.empty_like(mu), torch.empty_like(sigma), torch.empty_like(z)
+
+
+def _wl_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], inputs[2])
+    ctx.c = inputs[3]
+
+
+def _wl_backward(ctx, g):
+    mu, sigma, z = ctx.saved_tensors
+    gmu, gsig, gz = wrapped_logprob_bwd(mu, sigma, z, _c(g), ctx.c)
+    return gmu, gsig, gz, None
+
+
+wrapped_logprob_fwd.register_autograd(_wl_backward, setup_context=_wl_setup)
+
+
+@_op("hvae::wrapped_logprob_prior_fwd", mutates_args=())
+def wrapped_logprob_prior_fwd(z: Tensor, sigma0: float, c: float) -> Tensor:
+    """log-density of WrappedNormal(origin, sigma0 * 1) at z (S,B,D) -> (S,B)"""
+    C.require_cuda(z)
+    S, B, D = z.shape
+    out = z.new_empty(S, B)
+    C.call("hvae_wrapped_logprob_fwd_f32", None, None, sigma0, C.ptr(z), C.ptr(out), S, B, D, c, C.stream())
+    return out
+
+
+@wrapped_logprob_prior_fwd.register_fake
+def _(z, sigma0, c):
+    return z.new_empty(z.shape[0], z.shape[1])
+
+
+@_op("hvae::wrapped_logprob_prior_bwd", mutates_args=())
+def wrapped_logprob_prior_bwd(z: Tensor, g: Tensor, sigma0: float, c: float) -> Tensor:
+    C.require_cuda(z, g)
+    S, B, D = z.shape
+    gz = torch.empty_like(z)
+    C.call("hvae_wrapped_logprob_bwd_f32", None, None, sigma0, C.ptr(z), C.ptr(g), None, None, C.ptr(gz), S, B, D, c,
+           C.stream())
+    return gz
+
+
+@wrapped_logprob_prior_bwd.register_fake
+def _(z, g, sigma0, c):
+    return torch.empty_like(z)
+
+
+def _wlp_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.sigma0, ctx.c = inputs[1], inputs[2]
+
+
+def _wlp_backward(ctx, g):
+    (z,) = ctx.saved_tensors
+    return wrapped_logprob_prior_bwd(z, _c(g), ctx.sigma0, ctx.c), None, None
+
+
+wrapped_logprob_prior_fwd.register_autograd(_wlp_backward, setup_context=_wlp_setup)
+
+
+@_op("hvae::latent_head_fwd", mutates_args=())
+def latent_head_fwd(mu: Tensor, sigma: Tensor, eps: Tensor, prior_scale: float, c: float) -> Tuple[Tensor, Tensor]:
+    """Fused K4+K5: z = rsample(mu, sigma; eps) (B,D), kl = log q(z|x) - log p(z) (B,)"""
+    C.require_cuda(mu, sigma, eps)
+    B, D = mu.shape
+    z, kl = torch.empty_like(mu), mu.new_empty(B)
+    C.call("hvae_latent_head_fwd_f32", C.ptr(mu), C.ptr(sigma), C.ptr(eps), prior_scale, C.ptr(z), C.ptr(kl), B, D, c,
+           C.stream())
+    return z, kl
+
+
+@latent_head_fwd.register_fake
+def _(mu, sigma, eps, prior_scale, c):
+    return torch.empty_like(mu), mu.new_empty(mu.shape[0])
+
+
+@_op("hvae::latent_head_bwd", mutates_args=())
+def latent_head_bwd(mu: Tensor, sigma: Tensor, eps: Tensor, gz: Optional[Tensor], gkl: Optional[Tensor],
+                    prior_scale: float, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(mu, sigma, eps, gz, gkl)
+    B, D = mu.shape
+    gmu, gsig = torch.empty_like(mu), torch.empty_like(sigma)
+    C.call("hvae_latent_head_bwd_f32", C.ptr(mu), C.ptr(sigma), C.ptr(eps), prior_scale, C.ptr(gz), C.ptr(gkl), C.ptr(gmu),
+           C.ptr(gsig), B, D, c, C.stream())
+    return gmu, gsig
+
+
+@latent_head_bwd.register_fake
+def _(mu, sigma, eps, gz, gkl, prior_scale, c):
+    return torch.empty_like(mu), torch.empty_like(sigma)
+
+
+def _lh_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], inputs[2])
+    ctx.prior_scale, ctx.c = inputs[3], inputs[4]
+
+
+def _lh_backward(ctx, gz, gkl):
+    mu, sigma, eps = ctx.saved_tensors
+    gz = None if gz is None else _c(gz)
+    gkl = None if gkl is None else _c(gkl)
+    gmu, gsig = latent_head_bwd(mu, sigma, eps, gz, gkl, ctx.prior_scale, ctx.c)
+    return gmu, gsig, None, None, None
+
+
+latent_head_fwd.register_autograd(_lh_backward, setup_context=_lh_setup)
+
+
+def latent_head(mu: Tensor, sigma: Tensor, eps: Tensor, prior_scale: float, c: float) -> Tuple[Tensor, Tensor]:
+    return latent_head_fwd(_c(mu), _c(sigma), _c(eps), float(prior_scale), c)
+
+
+# ---------------------------------------------------------------------------------------------------
+# flags shared with include/hvae_b200.h
+# ---------------------------------------------------------------------------------------------------
+GYRO_SIGNED, GYRO_SQUARED, GYRO_SCALED, GYRO_PVAE = 1, 2, 4, 8
+
+
+def log_sinhc(x: Tensor) -> Tensor:
+    """log(sinh(x)/x), stable at small x (tensor expression; only used by the free-function logdetexp)."""
+    x2 = x * x
+    small = x2 * (1.0 / 6.0 + x2 * (-1.0 / 180.0 + x2 * (1.0 / 2835.0)))
+    xl = x.clamp_min(0.5)
+    large = xl + torch.log1p(-torch.exp(-2.0 * xl)) - 0.6931471805599453 - torch.log(xl)
+    return torch.where(x < 0.5, small, large)

@@ -1,0 +1,152 @@
+/* hvae_b200 — C ABI of the B200-native Poincare-ball VAE hot path.
+ *
+ * The reference (grisaitis/hyperbolic-vae) is pure Python: it has no FFI/plugin registry, so the
+ * drop-in boundary it exposes is its Python class API.  This header is the C-ABI
+ * layer UNDER that API: every entry point replaces the eager PyTorch/geoopt graph of one reference
+ * call site (cited per function as file:line into /root/reference/hyperbolic_vae/).  The Python
+ * package `hvae` binds these symbols with ctypes and wraps them as torch custom ops with analytic
+ * backward (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - All tensors: row-major contiguous float32 device pointers owned by the caller.  The library
+ *    allocates nothing and keeps no state besides cached function attributes.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous, stream-ordered, never
+ *    synchronize the device or the host, and are re-entrant.
+ *  - Return 0 on success, a negative HVAE_E* code otherwise; nothing throws across the ABI.
+ *  - sm_100a only.  There is no CPU fallback and no other-arch fallback by design.
+ *  - c is the curvature MAGNITUDE as read from the manifold: float(manifold.c)
+ *    (= softplus(isp_c) in fp32, not the constructor argument; SURVEY.md §7 "hard parts").
+ */
+#ifndef HVAE_B200_H
+#define HVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVAE_VERSION 100
+
+#define HVAE_OK 0
+#define HVAE_ESHAPE (-1)  /* unsupported or inconsistent shape */
+#define HVAE_EALIGN (-2)  /* pointer alignment */
+#define HVAE_EARCH (-3)   /* device is not sm_100 */
+#define HVAE_ELAUNCH (-4) /* CUDA launch failure */
+#define HVAE_EARG (-5)    /* null pointer / bad flag / workspace too small */
+
+/* flags for the gyroplane (hyperplane-distance) op */
+#define HVAE_GYRO_SIGNED 1u   /* keep the sign of <diff,a> (else abs)                         */
+#define HVAE_GYRO_SQUARED 2u  /* d^2 (times sign(d) if signed)       layers.py:203-207        */
+#define HVAE_GYRO_SCALED 4u   /* multiply by ||a||  (geoopt `scaled`, pvae `norm`)            */
+#define HVAE_GYRO_PVAE 8u     /* normdist2plane clamps + projected (-p)(+)x  manifolds.py:41-65 */
+
+int hvae_version(void);
+const char* hvae_strerror(int code);
+/* 0 if the current device is compute capability 10.x, else HVAE_EARCH */
+int hvae_device_check(void);
+
+/* ---- K3: expmap0 / logmap0  (layers.py:124-130; models/vae_hyperbolic.py:120,187; vae_one_b.py:218) -- */
+int hvae_expmap0_fwd_f32(const float* u, float* y, int64_t rows, int64_t D, float c, void* stream);
+int hvae_expmap0_bwd_f32(const float* u, const float* gy, float* gu, int64_t rows, int64_t D, float c, void* stream);
+int hvae_logmap0_fwd_f32(const float* y, float* u, int64_t rows, int64_t D, float c, void* stream);
+int hvae_logmap0_bwd_f32(const float* y, const float* gu, float* gy, int64_t rows, int64_t D, float c, void* stream);
+
+/* ---- mobius_add (geoopt PoincareBall.mobius_add; manifolds.py:54) ---------------------------------- */
+int hvae_mobius_add_fwd_f32(const float* x, const float* y, float* out, int64_t rows, int64_t D, float c,
+                            int project, void* stream);
+int hvae_mobius_add_bwd_f32(const float* x, const float* y, const float* gout, float* gx, float* gy,
+                            int64_t rows, int64_t D, float c, int project, void* stream);
+
+/* ---- generic two-point row ops: expmap(x,u), logmap(x,y), dist(x,y), transp(x,y,v) ------------------ */
+int hvae_expmap_fwd_f32(const float* x, const float* u, float* out, int64_t rows, int64_t D, float c, void* stream);
+int hvae_expmap_bwd_f32(const float* x, const float* u, const float* gout, float* gx, float* gu,
+                        int64_t rows, int64_t D, float c, void* stream);
+int hvae_logmap_fwd_f32(const float* x, const float* y, float* out, int64_t rows, int64_t D, float c, void* stream);
+int hvae_logmap_bwd_f32(const float* x, const float* y, const float* gout, float* gx, float* gy,
+                        int64_t rows, int64_t D, float c, void* stream);
+int hvae_dist_fwd_f32(const float* x, const float* y, float* d, int64_t rows, int64_t D, float c, void* stream);
+int hvae_dist_bwd_f32(const float* x, const float* y, const float* gd, float* gx, float* gy,
+                      int64_t rows, int64_t D, float c, void* stream);
+
+/* ---- K4: WrappedNormal.rsample  (distributions/wrapped_normal.py:66-74) --------------------------------
+ * mu, sigma: (B,D); eps, z: (S,B,D).  z = project(mu (+) tanh(sqrt(c) lambda_mu ||u||/2) u/(sqrt(c)||u||)),
+ * u = sigma*eps / lambda_0 * lambda_0/lambda_mu.  bwd reduces over S into gmu/gsigma (B,D). */
+int hvae_wrapped_sample_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z,
+                                int64_t S, int64_t B, int64_t D, float c, void* stream);
+int hvae_wrapped_sample_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
+                                float* gmu, float* gsigma, int64_t S, int64_t B, int64_t D, float c, void* stream);
+
+/* ---- K5: WrappedNormal.log_prob  (distributions/wrapped_normal.py:76-89; manifolds.py:25-35) -------------
+ * mu, sigma: (B,D); z: (S,B,D); logp: (S,B).  If mu == NULL the location is the origin and sigma is the
+ * scalar `sigma0` (the prior WrappedNormal(0, prior_scale*1): vae_hyperbolic.py:194-199). */
+int hvae_wrapped_logprob_fwd_f32(const float* mu, const float* sigma, float sigma0, const float* z, float* logp,
+                                 int64_t S, int64_t B, int64_t D, float c, void* stream);
+int hvae_wrapped_logprob_bwd_f32(const float* mu, const float* sigma, float sigma0, const float* z,
+                                 const float* glogp, float* gmu, float* gsigma, float* gz,
+                                 int64_t S, int64_t B, int64_t D, float c, void* stream);
+
+/* ---- K4+K5 fused latent head: z = rsample(mu,sigma;eps), kl = log q(z|x) - log p(z) --------------------
+ * (models/vae_hyperbolic.py:126-127,191-216; vae_hyperbolic_gyroplane_decoder.py:95-144).  S = 1.
+ * kl: (B,).  bwd takes the upstream gradients of z (B,D; may be NULL) and kl (B,; may be NULL). */
+int hvae_latent_head_fwd_f32(const float* mu, const float* sigma, const float* eps, float prior_scale,
+                             float* z, float* kl, int64_t B, int64_t D, float c, void* stream);
+int hvae_latent_head_bwd_f32(const float* mu, const float* sigma, const float* eps, float prior_scale,
+                             const float* gz, const float* gkl, float* gmu, float* gsigma,
+                             int64_t B, int64_t D, float c, void* stream);
+
+#ifdef HVAE_PENDING /* declared ahead of implementation; enabled as each kernel lands */
+/* ---- K2: gyroplane / hyperplane distance  (layers.py:193-210 & geoopt Distance2StereographicHyperplanes;
+ *      layers.py:96-121 -> manifolds.py:41-65 with HVAE_GYRO_PVAE) ---------------------------------------
+ * x: (B,D); p, a: (P,D) (a may alias p); bias: (P,) or NULL; out: (B,P).
+ * out[b,j] = asinh(2 sqrt(c) <diff,a_j> / ((1 - c||diff||^2) ||a_j||)) / sqrt(c), diff = (-p_j) (+) x_b. */
+int hvae_gyroplane_fwd_f32(const float* x, const float* p, const float* a, const float* bias, float* out,
+                           int64_t B, int64_t D, int64_t P, float c, uint32_t flags, void* stream);
+size_t hvae_gyroplane_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P);
+/* gp/ga: (P,D) (ga may be NULL when a aliases p: its gradient is added into gp); gbias: (P,) or NULL */
+int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout,
+                           float* gx, float* gp, float* ga, float* gbias,
+                           int64_t B, int64_t D, int64_t P, float c, uint32_t flags,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K1b: Riemannian layer weight prep  (layers.py:58-67) ------------------------------------------------
+ * W: (P,F) `_weight`; beta: (P,) `_bias` (over_param=False) -> bpt = expmap0(W*beta) (P,F),
+ * M = W * clamp_min(1 - c||bpt||^2, 1e-15) (P,F).  If bias_pt_in != NULL (over_param=True) it is used as bpt. */
+int hvae_weight_prep_fwd_f32(const float* W, const float* beta, const float* bias_pt_in, float* bpt, float* M,
+                             int64_t P, int64_t F, float c, void* stream);
+int hvae_weight_prep_bwd_f32(const float* W, const float* beta, const float* bias_pt_in,
+                             const float* gM, const float* gbpt, float* gW, float* gbeta, float* gbias_pt,
+                             int64_t P, int64_t F, float c, void* stream);
+
+/* ---- K1: Mobius matvec  (layers.py:145-147 -> geoopt mobius_matvec + project) ---------------------------
+ * x: (B,F); M: (P,F); y: (B,P).  mx (B,P) is written when mx_out != NULL (saved for backward). */
+int hvae_mobius_matvec_fwd_f32(const float* x, const float* M, float* y, float* mx_out,
+                               int64_t B, int64_t F, int64_t P, float c, void* stream);
+size_t hvae_mobius_matvec_bwd_workspace_bytes(int64_t B, int64_t F, int64_t P);
+int hvae_mobius_matvec_bwd_f32(const float* x, const float* M, const float* mx, const float* gy,
+                               float* gx, float* gM, int64_t B, int64_t F, int64_t P, float c,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K6/K7: HyperbolicRadius  (distributions/old_pvae_riemannian_normal.py:31,51 -> pvae, App. A.2) ------
+ * sigma: (B,) per-row scale (already clamped to [0.1,7] by the caller as RiemannianNormal does). */
+int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, float* dlogZ_dsigma, int64_t B, int64_t dim,
+                                 float c, void* stream);
+/* r: (S,B) samples by rejection from a tangent hull, Philox4x32-10 stream (seed, offset) */
+int hvae_hradius_sample_f32(const float* sigma, float* r, int64_t S, int64_t B, int64_t dim, float c,
+                            uint64_t seed, uint64_t offset, void* stream);
+/* implicit reparameterisation: dr/dsigma = -(dF/dsigma)/(dF/dr) at the given (r, sigma); cdf optional */
+int hvae_hradius_rgrad_f32(const float* sigma, const float* r, float* dr_dsigma, float* cdf,
+                           int64_t S, int64_t B, int64_t dim, float c, void* stream);
+/* expmap_polar: z = mu (+) tanh(sqrt(c) r/2) alpha/(sqrt(c)||alpha||)   (pvae manifolds; App. A.2) */
+int hvae_expmap_polar_fwd_f32(const float* mu, const float* alpha, const float* r, float* z,
+                              int64_t S, int64_t B, int64_t D, float c, void* stream);
+int hvae_expmap_polar_bwd_f32(const float* mu, const float* alpha, const float* r, const float* gz,
+                              float* gmu, float* gr, int64_t S, int64_t B, int64_t D, float c, void* stream);
+
+#endif /* HVAE_PENDING */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVAE_B200_H */
