@@ -1,0 +1,507 @@
+// K2: gyroplane (signed hyperplane distance) layer, forward and analytic backward — SIMT path for
+// latent dims D <= 64 (the decoder-side shapes of configs 1-4: D = 2..64, P = 16..1024).
+//
+// reference: hyperbolic_vae/layers.py:193-210 (Distance2PoincareHyperplanes) and geoopt's
+// Distance2StereographicHyperplanes -> math.dist2plane (App. A.1);  layers.py:96-121 (GeodesicLayer)
+// -> manifolds.py:41-65 (normdist2plane) with HVAE_GYRO_PVAE.
+//
+// The reference broadcasts to (B, D, P) intermediates (~12 of them kept for autograd).  Here the
+// Mobius subtraction is re-expressed through inner products:
+//   A = 1 - 2c<p,x> + c|x|^2,  Bc = 1 - c|p|^2,  den = 1 - 2c<p,x> + c^2|p|^2|x|^2
+//   <diff,a> = (-A<p,a> + Bc<x,a>)/den,   |diff|^2 = (A^2|p|^2 - 2 A Bc <p,x> + Bc^2|x|^2)/den^2
+// so one pass over D per (row, plane) pair gives <p,x> (and <a,x>), and the rest is a scalar epilogue.
+// Memory is O(B*P) for the output only.  Algorithmic bytes: fwd 4(BD + 2PD + BP), bwd 4(BP + 2BD + 4PD).
+// At D <= 64 the kernel is bound by the B*P output write / epilogue math, not by the FMA count.
+#include "hvae_common.cuh"
+
+namespace hvae {
+
+struct GyroParams {
+    float c, sc, rsc, maxnorm;
+    uint32_t flags;
+};
+
+struct GyroPairCtx {
+    float A, Bc, den, N1, N2, da, dn2, an, w, denom, y, out0, out1, rho_n;  // rho_n: |diff| when projected
+    bool den_ok, dn2_ok, w_ok, projected;
+};
+
+// scalar epilogue shared by forward and backward (and, later, by the tensor-core path)
+__device__ __forceinline__ float gyro_pair_fwd(float px, float xa, float x2, float p2, float pa, float an_raw,
+                                               const GyroParams& P, GyroPairCtx& k) {
+    const float c = P.c;
+    const bool pvae = P.flags & HVAE_GYRO_PVAE;
+    k.A = 1.0f - 2.0f * c * px + c * x2;
+    k.Bc = 1.0f - c * p2;
+    const float den0 = 1.0f - 2.0f * c * px + c * c * p2 * x2;
+    k.den_ok = den0 >= kMinNorm;
+    k.den = fmaxf(den0, kMinNorm);
+    k.N1 = -k.A * pa + k.Bc * xa;
+    k.N2 = fmaxf(k.A * k.A * p2 - 2.0f * k.A * k.Bc * px + k.Bc * k.Bc * x2, 0.0f);
+    const float rden = 1.0f / k.den;
+    k.da = k.N1 * rden;
+    float dn2r = k.N2 * rden * rden;
+    k.projected = false;
+    if (pvae) {
+        const float n = fmaxf(sqrtf(dn2r), kMinNorm);
+        if (n > P.maxnorm) {  // (-p)(+)x was projected back into the ball
+            k.projected = true;
+            k.rho_n = n;
+            k.da = k.da / n * P.maxnorm;
+            dn2r = P.maxnorm * P.maxnorm;
+        }
+    }
+    k.dn2_ok = dn2r >= kMinNorm;
+    k.dn2 = fmaxf(dn2r, kMinNorm);
+    const float s = (P.flags & HVAE_GYRO_SIGNED) ? k.da : fabsf(k.da);
+    k.an = pvae ? fmaxf(an_raw, kMinNorm) : an_raw;
+    k.w = (1.0f - c * k.dn2) * k.an;
+    if (pvae) {
+        k.w_ok = k.w >= kMinNorm;
+        k.denom = fmaxf(k.w, kMinNorm);
+    } else {
+        k.w_ok = true;
+        k.denom = (k.w >= 0.0f ? 1.0f : -1.0f) * (fabsf(k.w) + kMinNorm);  // clamp_abs, sign(0) = +1
+    }
+    k.y = 2.0f * P.sc * s / k.denom;
+    k.out0 = asinhf(k.y) * P.rsc;
+    k.out1 = (P.flags & HVAE_GYRO_SCALED) ? k.out0 * k.an : k.out0;
+    float o = k.out1;
+    if (P.flags & HVAE_GYRO_SQUARED) {
+        const float sg = (o > 0.0f) ? 1.0f : ((o < 0.0f) ? -1.0f : 0.0f);
+        o = (P.flags & HVAE_GYRO_SIGNED) ? o * o * sg : o * o;
+    }
+    return o;
+}
+
+struct GyroPairGrad {
+    float dpx, dxa, dx2, dp2, dpa, dan;  // dan: gradient wrt the RAW ||a||
+};
+
+__device__ __forceinline__ GyroPairGrad gyro_pair_bwd(float g, float px, float xa, float x2, float p2, float pa,
+                                                      float an_raw, const GyroParams& P, const GyroPairCtx& k) {
+    GyroPairGrad r;
+    const float c = P.c;
+    const bool pvae = P.flags & HVAE_GYRO_PVAE;
+    float g1 = g;
+    if (P.flags & HVAE_GYRO_SQUARED) g1 = (P.flags & HVAE_GYRO_SIGNED) ? g * 2.0f * fabsf(k.out1) : g * 2.0f * k.out1;
+    float gan = 0.0f;  // wrt the (possibly clamped) an
+    float g0 = g1;
+    if (P.flags & HVAE_GYRO_SCALED) {
+        gan += g1 * k.out0;
+        g0 = g1 * k.an;
+    }
+    const float dy = g0 * P.rsc * rsqrtf(1.0f + k.y * k.y);
+    const float ds = dy * 2.0f * P.sc / k.denom;
+    const float ddenom = -dy * k.y / k.denom;
+    const float dw = k.w_ok ? ddenom : 0.0f;
+    const float ddn2 = dw * (-c * k.an);
+    gan += dw * (1.0f - c * k.dn2);
+    float dda = ds;
+    if (!(P.flags & HVAE_GYRO_SIGNED)) dda = (k.da > 0.0f) ? ds : ((k.da < 0.0f) ? -ds : 0.0f);
+    float dN1, dN2, dden;
+    if (k.projected) {
+        // da = maxnorm * N1 / sqrt(N2); |diff|^2 == maxnorm^2 carries no gradient
+        const float rs = rsqrtf(k.N2);
+        dN1 = dda * P.maxnorm * rs;
+        dN2 = -dda * P.maxnorm * k.N1 * 0.5f * rs * rs * rs;
+        dden = 0.0f;
+    } else {
+        const float ddn2r = k.dn2_ok ? ddn2 : 0.0f;
+        const float rden = 1.0f / k.den;
+        dN1 = dda * rden;
+        dN2 = ddn2r * rden * rden;
+        dden = -dda * k.N1 * rden * rden - 2.0f * ddn2r * k.N2 * rden * rden * rden;
+    }
+    const float dden0 = k.den_ok ? dden : 0.0f;
+    const float dA = -pa * dN1 + (2.0f * k.A * p2 - 2.0f * k.Bc * px) * dN2;
+    const float dBc = xa * dN1 + (-2.0f * k.A * px + 2.0f * k.Bc * x2) * dN2;
+    r.dpa = -k.A * dN1;
+    r.dxa = k.Bc * dN1;
+    r.dp2 = k.A * k.A * dN2 - c * dBc + c * c * x2 * dden0;
+    r.dx2 = k.Bc * k.Bc * dN2 + c * dA + c * c * p2 * dden0;
+    r.dpx = -2.0f * k.A * k.Bc * dN2 - 2.0f * c * dA - 2.0f * c * dden0;
+    r.dan = (pvae && an_raw < kMinNorm) ? 0.0f : gan;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tiling: a CTA of 128 threads owns TB rows x TJ planes; thread = one plane, 8 rows at a time.
+// smem: xs[TB][D4] (row-major, broadcast reads), ps[D4][TJ] / as[D4][TJ] (plane-minor, conflict-free).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kGyroThreads = 128;
+constexpr int kGyroTB = 64;   // rows per CTA
+constexpr int kGyroRB = 8;    // rows per register block
+
+template <int D4, bool kAliased>
+__global__ void __launch_bounds__(kGyroThreads)
+k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
+           const float* __restrict__ bias, float* __restrict__ out, int B, int D, int P_, GyroParams prm) {
+    constexpr int TJ = kGyroThreads;
+    extern __shared__ float smem[];
+    float* xs = smem;                       // [TB][D4]
+    float* xs2 = xs + kGyroTB * D4;         // [TB]
+    float* ps = xs2 + kGyroTB;              // [D4][TJ]
+    float* as = ps + D4 * TJ;               // [D4][TJ] (unused when aliased)
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * TJ;
+    const int b0 = blockIdx.y * kGyroTB;
+    const int j = j0 + tid;
+    // stage planes (plane-minor) and rows
+    for (int i = tid; i < TJ * D4; i += kGyroThreads) {
+        const int jj = i / D4, d = i - jj * D4;
+        const bool ok = (j0 + jj) < P_ && d < D;
+        ps[d * TJ + jj] = ok ? __ldg(p + (int64_t)(j0 + jj) * D + d) : 0.0f;
+        if (!kAliased) as[d * TJ + jj] = ok ? __ldg(a + (int64_t)(j0 + jj) * D + d) : 0.0f;
+    }
+    for (int i = tid; i < kGyroTB * D4; i += kGyroThreads) {
+        const int bb = i / D4, d = i - bb * D4;
+        xs[i] = ((b0 + bb) < B && d < D) ? __ldg(x + (int64_t)(b0 + bb) * D + d) : 0.0f;
+    }
+    __syncthreads();
+    if (tid < kGyroTB) {
+        float s = 0.0f;
+#pragma unroll 4
+        for (int d = 0; d < D4; ++d) s = fmaf(xs[tid * D4 + d], xs[tid * D4 + d], s);
+        xs2[tid] = s;
+    }
+    float p2 = 0.0f, pa = 0.0f, a2 = 0.0f;
+#pragma unroll 4
+    for (int d = 0; d < D4; ++d) {
+        const float pv = ps[d * TJ + tid];
+        const float av = kAliased ? pv : as[d * TJ + tid];
+        p2 = fmaf(pv, pv, p2);
+        pa = fmaf(pv, av, pa);
+        a2 = fmaf(av, av, a2);
+    }
+    const float an_raw = sqrtf(a2);
+    const float bj = (bias != nullptr && j < P_) ? __ldg(bias + j) : 0.0f;
+    __syncthreads();
+    for (int r0 = 0; r0 < kGyroTB; r0 += kGyroRB) {
+        if (b0 + r0 >= B) break;
+        float px[kGyroRB], xa[kGyroRB];
+#pragma unroll
+        for (int r = 0; r < kGyroRB; ++r) px[r] = xa[r] = 0.0f;
+#pragma unroll 2
+        for (int d = 0; d < D4; d += 4) {
+            const float p0 = ps[(d + 0) * TJ + tid], p1 = ps[(d + 1) * TJ + tid];
+            const float p2_ = ps[(d + 2) * TJ + tid], p3 = ps[(d + 3) * TJ + tid];
+            float a0 = p0, a1 = p1, a2_ = p2_, a3 = p3;
+            if (!kAliased) {
+                a0 = as[(d + 0) * TJ + tid]; a1 = as[(d + 1) * TJ + tid];
+                a2_ = as[(d + 2) * TJ + tid]; a3 = as[(d + 3) * TJ + tid];
+            }
+#pragma unroll
+            for (int r = 0; r < kGyroRB; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + (r0 + r) * D4 + d);
+                px[r] = fmaf(p0, xv.x, fmaf(p1, xv.y, fmaf(p2_, xv.z, fmaf(p3, xv.w, px[r]))));
+                if (!kAliased) xa[r] = fmaf(a0, xv.x, fmaf(a1, xv.y, fmaf(a2_, xv.z, fmaf(a3, xv.w, xa[r]))));
+            }
+        }
+        if (j < P_) {
+#pragma unroll
+            for (int r = 0; r < kGyroRB; ++r) {
+                const int b = b0 + r0 + r;
+                if (b < B) {
+                    GyroPairCtx k;
+                    const float o = gyro_pair_fwd(px[r], kAliased ? px[r] : xa[r], xs2[r0 + r], p2, pa, an_raw, prm, k);
+                    out[(int64_t)b * P_ + j] = o + bj;
+                }
+            }
+        }
+    }
+}
+
+// gx: thread = one row, planes streamed from smem (broadcast); upstream-grad tile staged through smem.
+constexpr int kGyroBxThreads = 128;  // rows per CTA
+constexpr int kGyroBxTJ = 32;        // planes per smem stage
+
+template <int D4, bool kAliased>
+__global__ void __launch_bounds__(kGyroBxThreads)
+k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
+             const float* __restrict__ gout, float* __restrict__ gx, int B, int D, int P_, GyroParams prm) {
+    constexpr int TJ = kGyroBxTJ;
+    __shared__ float ps[TJ][D4];
+    __shared__ float as[kAliased ? 1 : TJ][D4];
+    __shared__ float pst[TJ][4];                      // p2, pa, an_raw
+    __shared__ float gs[kGyroBxThreads][TJ + 1];      // upstream grad tile [row][plane]
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * kGyroBxThreads;
+    const int b = b0 + tid;
+    float xr[D4], acc[D4];
+    float x2 = 0.0f, sdx2 = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D4; ++d) {
+        xr[d] = (b < B && d < D) ? __ldg(x + (int64_t)b * D + d) : 0.0f;
+        x2 = fmaf(xr[d], xr[d], x2);
+        acc[d] = 0.0f;
+    }
+    for (int j0 = 0; j0 < P_; j0 += TJ) {
+        __syncthreads();
+        for (int i = tid; i < TJ * D4; i += kGyroBxThreads) {
+            const int jj = i / D4, d = i - jj * D4;
+            const bool ok = (j0 + jj) < P_ && d < D;
+            ps[jj][d] = ok ? __ldg(p + (int64_t)(j0 + jj) * D + d) : 0.0f;
+            if (!kAliased) as[jj][d] = ok ? __ldg(a + (int64_t)(j0 + jj) * D + d) : 0.0f;
+        }
+        for (int i = tid; i < kGyroBxThreads * TJ; i += kGyroBxThreads) {
+            const int rr = i / TJ, jj = i - rr * TJ;
+            gs[rr][jj] = ((b0 + rr) < B && (j0 + jj) < P_) ? __ldg(gout + (int64_t)(b0 + rr) * P_ + j0 + jj) : 0.0f;
+        }
+        __syncthreads();
+        if (tid < TJ) {
+            float p2 = 0.0f, pa = 0.0f, a2 = 0.0f;
+            for (int d = 0; d < D4; ++d) {
+                const float pv = ps[tid][d];
+                const float av = kAliased ? pv : as[tid][d];
+                p2 = fmaf(pv, pv, p2);
+                pa = fmaf(pv, av, pa);
+                a2 = fmaf(av, av, a2);
+            }
+            pst[tid][0] = p2; pst[tid][1] = pa; pst[tid][2] = sqrtf(a2);
+        }
+        __syncthreads();
+        const int jn = min(TJ, P_ - j0);
+        for (int jj = 0; jj < jn; ++jj) {
+            float px = 0.0f, xa = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D4; d += 4) {
+                const float4 pv = *reinterpret_cast<const float4*>(&ps[jj][d]);
+                px = fmaf(pv.x, xr[d], fmaf(pv.y, xr[d + 1], fmaf(pv.z, xr[d + 2], fmaf(pv.w, xr[d + 3], px))));
+                if (!kAliased) {
+                    const float4 av = *reinterpret_cast<const float4*>(&as[jj][d]);
+                    xa = fmaf(av.x, xr[d], fmaf(av.y, xr[d + 1], fmaf(av.z, xr[d + 2], fmaf(av.w, xr[d + 3], xa))));
+                }
+            }
+            if (kAliased) xa = px;
+            const float p2 = pst[jj][0], pa = pst[jj][1], an_raw = pst[jj][2];
+            GyroPairCtx k;
+            gyro_pair_fwd(px, xa, x2, p2, pa, an_raw, prm, k);
+            const GyroPairGrad gr = gyro_pair_bwd(gs[tid][jj], px, xa, x2, p2, pa, an_raw, prm, k);
+            sdx2 += gr.dx2;
+            const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
+#pragma unroll
+            for (int d = 0; d < D4; d += 4) {
+                const float4 pv = *reinterpret_cast<const float4*>(&ps[jj][d]);
+                acc[d] = fmaf(cp, pv.x, acc[d]); acc[d + 1] = fmaf(cp, pv.y, acc[d + 1]);
+                acc[d + 2] = fmaf(cp, pv.z, acc[d + 2]); acc[d + 3] = fmaf(cp, pv.w, acc[d + 3]);
+                if (!kAliased) {
+                    const float4 av = *reinterpret_cast<const float4*>(&as[jj][d]);
+                    acc[d] = fmaf(gr.dxa, av.x, acc[d]); acc[d + 1] = fmaf(gr.dxa, av.y, acc[d + 1]);
+                    acc[d + 2] = fmaf(gr.dxa, av.z, acc[d + 2]); acc[d + 3] = fmaf(gr.dxa, av.w, acc[d + 3]);
+                }
+            }
+        }
+    }
+    if (b < B) {
+#pragma unroll
+        for (int d = 0; d < D4; ++d)
+            if (d < D) gx[(int64_t)b * D + d] = acc[d] + 2.0f * sdx2 * xr[d];
+    }
+}
+
+// gp / ga / gbias: thread = one plane; a CTA covers TJ planes x a slab of rows; partial sums go to the
+// workspace [slab][P][D] (+[slab][P] for bias) and a second kernel reduces over slabs (deterministic).
+constexpr int kGyroBpThreads = 128;
+constexpr int kGyroBpTB = 32;  // rows per smem stage
+
+template <int D4, bool kAliased>
+__global__ void __launch_bounds__(kGyroBpThreads)
+k_gyro_bwd_p(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
+             const float* __restrict__ gout, float* __restrict__ wp, float* __restrict__ wa, float* __restrict__ wb,
+             int B, int D, int P_, int rows_per_slab, GyroParams prm) {
+    constexpr int TJ = kGyroBpThreads;
+    __shared__ float xs[kGyroBpTB][D4];
+    __shared__ float xs2[kGyroBpTB];
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x * TJ + tid;
+    const int slab = blockIdx.y;
+    const int bs = slab * rows_per_slab;
+    const int be = min(B, bs + rows_per_slab);
+    float pr[D4], ar[kAliased ? 1 : D4], accp[D4], acca[kAliased ? 1 : D4];
+    float p2 = 0.0f, pa = 0.0f, a2 = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D4; ++d) {
+        pr[d] = (j < P_ && d < D) ? __ldg(p + (int64_t)j * D + d) : 0.0f;
+        const float av = kAliased ? pr[d] : ((j < P_ && d < D) ? __ldg(a + (int64_t)j * D + d) : 0.0f);
+        if (!kAliased) { ar[d] = av; acca[d] = 0.0f; }
+        p2 = fmaf(pr[d], pr[d], p2);
+        pa = fmaf(pr[d], av, pa);
+        a2 = fmaf(av, av, a2);
+        accp[d] = 0.0f;
+    }
+    const float an_raw = sqrtf(a2);
+    float sdp2 = 0.0f, sdpa = 0.0f, sdan = 0.0f, sg = 0.0f;
+    for (int b0 = bs; b0 < be; b0 += kGyroBpTB) {
+        __syncthreads();
+        for (int i = tid; i < kGyroBpTB * D4; i += kGyroBpThreads) {
+            const int bb = i / D4, d = i - bb * D4;
+            xs[bb][d] = ((b0 + bb) < be && d < D) ? __ldg(x + (int64_t)(b0 + bb) * D + d) : 0.0f;
+        }
+        __syncthreads();
+        if (tid < kGyroBpTB) {
+            float s = 0.0f;
+            for (int d = 0; d < D4; ++d) s = fmaf(xs[tid][d], xs[tid][d], s);
+            xs2[tid] = s;
+        }
+        __syncthreads();
+        const int bn = min(kGyroBpTB, be - b0);
+        if (j < P_) {
+            for (int bb = 0; bb < bn; ++bb) {
+                float px = 0.0f, xa = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D4; d += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][d]);
+                    px = fmaf(pr[d], xv.x, fmaf(pr[d + 1], xv.y, fmaf(pr[d + 2], xv.z, fmaf(pr[d + 3], xv.w, px))));
+                    if (!kAliased)
+                        xa = fmaf(ar[d], xv.x, fmaf(ar[d + 1], xv.y, fmaf(ar[d + 2], xv.z, fmaf(ar[d + 3], xv.w, xa))));
+                }
+                if (kAliased) xa = px;
+                const float g = __ldg(gout + (int64_t)(b0 + bb) * P_ + j);  // coalesced across the CTA's planes
+                GyroPairCtx k;
+                gyro_pair_fwd(px, xa, xs2[bb], p2, pa, an_raw, prm, k);
+                const GyroPairGrad gr = gyro_pair_bwd(g, px, xa, xs2[bb], p2, pa, an_raw, prm, k);
+                sdp2 += gr.dp2; sdpa += gr.dpa; sdan += gr.dan; sg += g;
+                const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
+#pragma unroll
+                for (int d = 0; d < D4; d += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][d]);
+                    accp[d] = fmaf(cp, xv.x, accp[d]); accp[d + 1] = fmaf(cp, xv.y, accp[d + 1]);
+                    accp[d + 2] = fmaf(cp, xv.z, accp[d + 2]); accp[d + 3] = fmaf(cp, xv.w, accp[d + 3]);
+                    if (!kAliased) {
+                        acca[d] = fmaf(gr.dxa, xv.x, acca[d]); acca[d + 1] = fmaf(gr.dxa, xv.y, acca[d + 1]);
+                        acca[d + 2] = fmaf(gr.dxa, xv.z, acca[d + 2]); acca[d + 3] = fmaf(gr.dxa, xv.w, acca[d + 3]);
+                    }
+                }
+            }
+        }
+    }
+    if (j < P_) {
+        const float inv_an = an_raw > 0.0f ? 1.0f / an_raw : 0.0f;
+        float* wpj = wp + ((int64_t)slab * P_ + j) * D;
+        float* waj = kAliased ? nullptr : wa + ((int64_t)slab * P_ + j) * D;
+#pragma unroll
+        for (int d = 0; d < D4; ++d) {
+            if (d < D) {
+                if (kAliased) {
+                    // a == p: pa = p2 and an = |p| all flow into the single parameter
+                    wpj[d] = accp[d] + (2.0f * sdp2 + 2.0f * sdpa + sdan * inv_an) * pr[d];
+                } else {
+                    wpj[d] = accp[d] + 2.0f * sdp2 * pr[d] + sdpa * ar[d];
+                    waj[d] = acca[d] + sdpa * pr[d] + sdan * inv_an * ar[d];
+                }
+            }
+        }
+        wb[(int64_t)slab * P_ + j] = sg;
+    }
+}
+
+__global__ void k_gyro_reduce_slabs(const float* __restrict__ w, float* __restrict__ out, int64_t n, int slabs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.0f;
+    for (int k = 0; k < slabs; ++k) s += w[(int64_t)k * n + i];
+    out[i] = s;
+}
+
+inline int gyro_slabs(int64_t B, int64_t P) {
+    const int64_t jb = (P + kGyroBpThreads - 1) / kGyroBpThreads;
+    int64_t want = (2 * kNumSMs + jb - 1) / jb;            // ~2 CTAs per SM in flight
+    const int64_t maxs = (B + kGyroBpTB - 1) / kGyroBpTB;   // at least one stage of rows per slab
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+inline GyroParams make_gyro_params(float c, uint32_t flags) {
+    const Ball b = make_ball(c);
+    GyroParams p;
+    p.c = b.c; p.sc = b.sc; p.rsc = b.rsc; p.maxnorm = b.maxnorm; p.flags = flags;
+    return p;
+}
+
+template <int D4>
+int gyro_fwd_launch(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B, int64_t D,
+                    int64_t P, const GyroParams& prm, cudaStream_t s) {
+    const bool aliased = (a == p);
+    dim3 grid((unsigned)((P + kGyroThreads - 1) / kGyroThreads), (unsigned)((B + kGyroTB - 1) / kGyroTB));
+    const size_t smem = sizeof(float) * ((size_t)kGyroTB * D4 + kGyroTB + (size_t)D4 * kGyroThreads * (aliased ? 1 : 2));
+    if (aliased) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gyro_fwd<D4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_gyro_fwd<D4, true><<<grid, kGyroThreads, smem, s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, prm);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gyro_fwd<D4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_gyro_fwd<D4, false><<<grid, kGyroThreads, smem, s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, prm);
+    }
+    return check_launch();
+}
+
+template <int D4>
+int gyro_bwd_launch(const float* x, const float* p, const float* a, const float* gout, float* gx, float* gp, float* ga,
+                    float* gbias, int64_t B, int64_t D, int64_t P, const GyroParams& prm, float* ws, cudaStream_t s) {
+    const bool aliased = (a == p);
+    const int slabs = gyro_slabs(B, P);
+    const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBpTB - 1) / kGyroBpTB * kGyroBpTB);
+    float* wp = ws;
+    float* wa = wp + (int64_t)slabs * P * D;
+    float* wb = wa + (aliased ? 0 : (int64_t)slabs * P * D);
+    if (gx) {
+        dim3 grid((unsigned)((B + kGyroBxThreads - 1) / kGyroBxThreads));
+        if (aliased) k_gyro_bwd_x<D4, true><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, gx, (int)B, (int)D, (int)P, prm);
+        else         k_gyro_bwd_x<D4, false><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, gx, (int)B, (int)D, (int)P, prm);
+    }
+    if (gp || ga || gbias) {
+        dim3 grid((unsigned)((P + kGyroBpThreads - 1) / kGyroBpThreads), (unsigned)slabs);
+        if (aliased) k_gyro_bwd_p<D4, true><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, gout, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab, prm);
+        else         k_gyro_bwd_p<D4, false><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, gout, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab, prm);
+        const int64_t n = P * D;
+        if (gp) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wp, gp, n, slabs);
+        if (ga && !aliased) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wa, ga, n, slabs);
+        if (gbias) k_gyro_reduce_slabs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(wb, gbias, P, slabs);
+    }
+    return check_launch();
+}
+
+}  // namespace hvae
+
+using namespace hvae;
+
+constexpr int64_t kGyroMaxD = 64;
+
+extern "C" int hvae_gyroplane_fwd_f32(const float* x, const float* p, const float* a, const float* bias, float* out,
+                                      int64_t B, int64_t D, int64_t P, float c, uint32_t flags, void* stream) {
+    if (B < 0 || P < 0 || D <= 0 || D > kGyroMaxD) return HVAE_ESHAPE;
+    if (B == 0 || P == 0) return HVAE_OK;
+    if (!x || !p || !a || !out) return HVAE_EARG;
+    const GyroParams prm = make_gyro_params(c, flags);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D <= 4) return gyro_fwd_launch<4>(x, p, a, bias, out, B, D, P, prm, s);
+    if (D <= 8) return gyro_fwd_launch<8>(x, p, a, bias, out, B, D, P, prm, s);
+    if (D <= 16) return gyro_fwd_launch<16>(x, p, a, bias, out, B, D, P, prm, s);
+    if (D <= 32) return gyro_fwd_launch<32>(x, p, a, bias, out, B, D, P, prm, s);
+    return gyro_fwd_launch<64>(x, p, a, bias, out, B, D, P, prm, s);
+}
+
+extern "C" size_t hvae_gyroplane_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P) {
+    if (B <= 0 || P <= 0 || D <= 0) return 0;
+    const int slabs = gyro_slabs(B, P);
+    return sizeof(float) * ((size_t)slabs * P * D * 2 + (size_t)slabs * P);
+}
+
+extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout, float* gx,
+                                      float* gp, float* ga, float* gbias, int64_t B, int64_t D, int64_t P, float c,
+                                      uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+    if (B < 0 || P < 0 || D <= 0 || D > kGyroMaxD) return HVAE_ESHAPE;
+    if (B == 0 || P == 0) return HVAE_OK;
+    if (!x || !p || !a || !gout) return HVAE_EARG;
+    if (a != p && gp && !ga) return HVAE_EARG;
+    if (!workspace || workspace_bytes < hvae_gyroplane_bwd_workspace_bytes(B, D, P)) return HVAE_EARG;
+    const GyroParams prm = make_gyro_params(c, flags);
+    cudaStream_t s = (cudaStream_t)stream;
+    float* ws = (float*)workspace;
+    if (D <= 4) return gyro_bwd_launch<4>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 8) return gyro_bwd_launch<8>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 16) return gyro_bwd_launch<16>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 32) return gyro_bwd_launch<32>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    return gyro_bwd_launch<64>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+}

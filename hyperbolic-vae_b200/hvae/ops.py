@@ -389,3 +389,240 @@ def log_sinhc(x: Tensor) -> Tensor:
     xl = x.clamp_min(0.5)
     large = xl + torch.log1p(-torch.exp(-2.0 * xl)) - 0.6931471805599453 - torch.log(xl)
     return torch.where(x < 0.5, small, large)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 gyroplane
+# ---------------------------------------------------------------------------------------------------
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    """Grow-only per-device scratch owned by torch's allocator (the C library allocates nothing)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+@_op("hvae::gyroplane_fwd", mutates_args=())
+def gyroplane_fwd(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], c: float, flags: int) -> Tensor:
+    """x (B,D); p (P,D); a (P,D) or None (= p); bias (P,) or None -> (B,P)"""
+    C.require_cuda(x, p, a, bias)
+    B, D = x.shape
+    P = p.shape[0]
+    out = x.new_empty(B, P)
+    C.call("hvae_gyroplane_fwd_f32", C.ptr(x), C.ptr(p), C.ptr(p if a is None else a), C.ptr(bias), C.ptr(out), B, D, P, c,
+           flags, C.stream())
+    return out
+
+
+@gyroplane_fwd.register_fake
+def _(x, p, a, bias, c, flags):
+    return x.new_empty(x.shape[0], p.shape[0])
+
+
+@_op("hvae::gyroplane_bwd", mutates_args=())
+def gyroplane_bwd(x: Tensor, p: Tensor, a: Optional[Tensor], g: Tensor, c: float, flags: int,
+                  need_bias: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    C.require_cuda(x, p, a, g)
+    B, D = x.shape
+    P = p.shape[0]
+    gx, gp = torch.empty_like(x), torch.empty_like(p)
+    ga = torch.empty_like(a) if a is not None else x.new_empty(0)
+    gb = x.new_empty(P) if need_bias else x.new_empty(0)
+    nbytes = C.lib().hvae_gyroplane_bwd_workspace_bytes(B, D, P)
+    ws = _workspace(nbytes, x.device)
+    C.call("hvae_gyroplane_bwd_f32", C.ptr(x), C.ptr(p), C.ptr(p if a is None else a), C.ptr(g), C.ptr(gx), C.ptr(gp),
+           C.ptr(ga) if a is not None else None, C.ptr(gb) if need_bias else None, B, D, P, c, flags, C.ptr(ws),
+           ws.numel(), C.stream())
+    C.launch_count += 2 + (1 if a is not None else 0) + (1 if need_bias else 0)
+    return gx, gp, ga, gb
+
+
+@gyroplane_bwd.register_fake
+def _(x, p, a, g, c, flags, need_bias):
+    return (torch.empty_like(x), torch.empty_like(p), torch.empty_like(a) if a is not None else x.new_empty(0),
+            x.new_empty(p.shape[0]) if need_bias else x.new_empty(0))
+
+
+def _gy_setup(ctx, inputs, output):
+    x, p, a, bias, c, flags = inputs
+    ctx.save_for_backward(x, p, a if a is not None else p)
+    ctx.has_a, ctx.has_bias, ctx.c, ctx.flags = a is not None, bias is not None, c, flags
+
+
+def _gy_backward(ctx, g):
+    x, p, a = ctx.saved_tensors
+    gx, gp, ga, gb = gyroplane_bwd(x, p, a if ctx.has_a else None, _c(g), ctx.c, ctx.flags, ctx.has_bias)
+    return gx, gp, (ga if ctx.has_a else None), (gb if ctx.has_bias else None), None, None
+
+
+gyroplane_fwd.register_autograd(_gy_backward, setup_context=_gy_setup)
+
+
+def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], c: float, flags: int) -> Tensor:
+    """Signed hyperplane distances of every row of x (..., D) to every plane -> (..., P)."""
+    lead = x.shape[:-1]
+    xr = _rows(x)
+    a_arg = None if (a is None or a is p) else _c(a)
+    out = gyroplane_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
+    return out.view(*lead, p.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1b weight prep + K1 Mobius matvec
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::weight_prep_fwd", mutates_args=())
+def weight_prep_fwd(W: Tensor, beta: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    """W (P,F) `_weight`, beta (P,) `_bias` -> (bias point expmap0(W*beta) (P,F), transported weight (P,F))"""
+    C.require_cuda(W, beta)
+    P, F = W.shape
+    bpt, M = torch.empty_like(W), torch.empty_like(W)
+    C.call("hvae_weight_prep_fwd_f32", C.ptr(W), C.ptr(beta), None, C.ptr(bpt), C.ptr(M), P, F, c, C.stream())
+    return bpt, M
+
+
+@weight_prep_fwd.register_fake
+def _(W, beta, c):
+    return torch.empty_like(W), torch.empty_like(W)
+
+
+@_op("hvae::weight_prep_bwd", mutates_args=())
+def weight_prep_bwd(W: Tensor, beta: Tensor, gM: Optional[Tensor], gbpt: Optional[Tensor], c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(W, beta, gM, gbpt)
+    P, F = W.shape
+    gW, gbeta = torch.empty_like(W), torch.empty_like(beta)
+    C.call("hvae_weight_prep_bwd_f32", C.ptr(W), C.ptr(beta), None, C.ptr(gM), C.ptr(gbpt), C.ptr(gW), C.ptr(gbeta), None,
+           P, F, c, C.stream())
+    return gW, gbeta
+
+
+@weight_prep_bwd.register_fake
+def _(W, beta, gM, gbpt, c):
+    return torch.empty_like(W), torch.empty_like(beta)
+
+
+def _wp_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.c = inputs[2]
+
+
+def _wp_backward(ctx, gbpt, gM):
+    W, beta = ctx.saved_tensors
+    gW, gbeta = weight_prep_bwd(W, beta, None if gM is None else _c(gM), None if gbpt is None else _c(gbpt), ctx.c)
+    return gW, gbeta, None
+
+
+weight_prep_fwd.register_autograd(_wp_backward, setup_context=_wp_setup)
+
+
+def weight_prep(W: Tensor, beta: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    """beta is the (P,1) `_bias` parameter of RiemannianLayer (over_param=False)."""
+    return weight_prep_fwd(_c(W), _c(beta).view(-1), c)
+
+
+@_op("hvae::weight_prep_op_fwd", mutates_args=())
+def weight_prep_op_fwd(W: Tensor, bias_pt: Tensor, c: float) -> Tensor:
+    """over_param=True: M = W * clamp_min(1 - c|bias_pt|^2)"""
+    C.require_cuda(W, bias_pt)
+    P, F = W.shape
+    M = torch.empty_like(W)
+    C.call("hvae_weight_prep_fwd_f32", C.ptr(W), None, C.ptr(bias_pt), None, C.ptr(M), P, F, c, C.stream())
+    return M
+
+
+@weight_prep_op_fwd.register_fake
+def _(W, bias_pt, c):
+    return torch.empty_like(W)
+
+
+@_op("hvae::weight_prep_op_bwd", mutates_args=())
+def weight_prep_op_bwd(W: Tensor, bias_pt: Tensor, gM: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(W, bias_pt, gM)
+    P, F = W.shape
+    gW, gb = torch.empty_like(W), torch.empty_like(bias_pt)
+    C.call("hvae_weight_prep_bwd_f32", C.ptr(W), None, C.ptr(bias_pt), C.ptr(gM), None, C.ptr(gW), None, C.ptr(gb), P, F, c,
+           C.stream())
+    return gW, gb
+
+
+@weight_prep_op_bwd.register_fake
+def _(W, bias_pt, gM, c):
+    return torch.empty_like(W), torch.empty_like(bias_pt)
+
+
+def _wpo_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.c = inputs[2]
+
+
+def _wpo_backward(ctx, gM):
+    W, b = ctx.saved_tensors
+    gW, gb = weight_prep_op_bwd(W, b, _c(gM), ctx.c)
+    return gW, gb, None
+
+
+weight_prep_op_fwd.register_autograd(_wpo_backward, setup_context=_wpo_setup)
+
+
+def weight_prep_overparam(W: Tensor, bias_pt: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    return bias_pt, weight_prep_op_fwd(_c(W), _c(bias_pt), c)
+
+
+@_op("hvae::mobius_matvec_fwd", mutates_args=())
+def mobius_matvec_fwd(x: Tensor, M: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    """x (B,F), M (P,F) -> (y (B,P) projected Mobius matvec, mx (B,P) saved for backward)"""
+    C.require_cuda(x, M)
+    B, F = x.shape
+    P = M.shape[0]
+    y, mx = x.new_empty(B, P), x.new_empty(B, P)
+    C.call("hvae_mobius_matvec_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), C.ptr(mx), B, F, P, c, C.stream())
+    return y, mx
+
+
+@mobius_matvec_fwd.register_fake
+def _(x, M, c):
+    return x.new_empty(x.shape[0], M.shape[0]), x.new_empty(x.shape[0], M.shape[0])
+
+
+@_op("hvae::mobius_matvec_bwd", mutates_args=())
+def mobius_matvec_bwd(x: Tensor, M: Tensor, mx: Tensor, gy: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(x, M, mx, gy)
+    B, F = x.shape
+    P = M.shape[0]
+    gx, gM = torch.empty_like(x), torch.empty_like(M)
+    nbytes = C.lib().hvae_mobius_matvec_bwd_workspace_bytes(B, F, P)
+    ws = _workspace(nbytes, x.device)
+    C.call("hvae_mobius_matvec_bwd_f32", C.ptr(x), C.ptr(M), C.ptr(mx), C.ptr(gy), C.ptr(gx), C.ptr(gM), B, F, P, c,
+           C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += 2
+    return gx, gM
+
+
+@mobius_matvec_bwd.register_fake
+def _(x, M, mx, gy, c):
+    return torch.empty_like(x), torch.empty_like(M)
+
+
+def _mm_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], output[1])
+    ctx.c = inputs[2]
+
+
+def _mm_backward(ctx, gy, _gmx):
+    x, M, mx = ctx.saved_tensors
+    gx, gM = mobius_matvec_bwd(x, M, mx, _c(gy), ctx.c)
+    return gx, gM, None
+
+
+mobius_matvec_fwd.register_autograd(_mm_backward, setup_context=_mm_setup)
+
+
+def mobius_matvec(x: Tensor, M: Tensor, c: float) -> Tensor:
+    """project(M (x)_c x) for every row of x (..., F) -> (..., P)"""
+    lead = x.shape[:-1]
+    y, _ = mobius_matvec_fwd(_rows(x), _c(M), c)
+    return y.view(*lead, M.shape[0])

@@ -96,7 +96,6 @@ int hvae_latent_head_bwd_f32(const float* mu, const float* sigma, const float* e
                              const float* gz, const float* gkl, float* gmu, float* gsigma,
                              int64_t B, int64_t D, float c, void* stream);
 
-#ifdef HVAE_PENDING /* declared ahead of implementation; enabled as each kernel lands */
 /* ---- K2: gyroplane / hyperplane distance  (layers.py:193-210 & geoopt Distance2StereographicHyperplanes;
  *      layers.py:96-121 -> manifolds.py:41-65 with HVAE_GYRO_PVAE) ---------------------------------------
  * x: (B,D); p, a: (P,D) (a may alias p); bias: (P,) or NULL; out: (B,P).
@@ -128,6 +127,7 @@ int hvae_mobius_matvec_bwd_f32(const float* x, const float* M, const float* mx, 
                                float* gx, float* gM, int64_t B, int64_t F, int64_t P, float c,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+#ifdef HVAE_PENDING /* declared ahead of implementation; enabled as each kernel lands */
 /* ---- K6/K7: HyperbolicRadius  (distributions/old_pvae_riemannian_normal.py:31,51 -> pvae, App. A.2) ------
  * sigma: (B,) per-row scale (already clamped to [0.1,7] by the caller as RiemannianNormal does). */
 int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, float* dlogZ_dsigma, int64_t B, int64_t dim,

@@ -16,8 +16,26 @@ from __future__ import annotations
 
 import torch
 
+import contextlib
+
 MIN_NORM = 1e-15
 BALL_EPS = {torch.float32: 4e-3, torch.float64: 1e-5}
+
+# "float64 arithmetic, float32 semantics": when the float64 evaluation is used as the tie-breaker truth
+# for a float32 result, the dtype-dependent CONSTANTS must stay those of the float32 function
+# (projection eps 4e-3, artanh clamp float32(1-1e-7) = 0.99999988), otherwise it is a different function.
+_FP32_SEMANTICS = False
+_ARTANH_CLAMP_F32 = float(torch.tensor(1 - 1e-7, dtype=torch.float32))
+
+
+@contextlib.contextmanager
+def fp32_semantics(on: bool = True):
+    global _FP32_SEMANTICS
+    old, _FP32_SEMANTICS = _FP32_SEMANTICS, on
+    try:
+        yield
+    finally:
+        _FP32_SEMANTICS = old
 
 
 # ---- scalar helpers -------------------------------------------------------------------------
@@ -26,7 +44,10 @@ def tanh(x: torch.Tensor) -> torch.Tensor:
 
 
 def artanh(x: torch.Tensor) -> torch.Tensor:
-    x = x.clamp(-1 + 1e-7, 1 - 1e-7)
+    if _FP32_SEMANTICS:
+        x = x.clamp(-_ARTANH_CLAMP_F32, _ARTANH_CLAMP_F32)
+    else:
+        x = x.clamp(-1 + 1e-7, 1 - 1e-7)
     return (torch.log(1 + x) - torch.log(1 - x)) * 0.5
 
 
@@ -83,7 +104,9 @@ def arsin_k(x: torch.Tensor, k) -> torch.Tensor:
 def project(x: torch.Tensor, *, k, dim: int = -1, eps: float = -1.0) -> torch.Tensor:
     k = _as_k(k, x)
     if eps < 0:
-        eps = 4e-3 if x.dtype == torch.float32 else 1e-5
+        eps = 4e-3 if (x.dtype == torch.float32 or _FP32_SEMANTICS) else 1e-5
+    if _FP32_SEMANTICS:
+        eps = 1.0 - float(torch.tensor(1 - eps, dtype=torch.float32))  # the fp32 path divides float32(0.996)
     maxnorm = (1 - eps) / (sabs(k) ** 0.5)
     maxnorm = torch.where(k.lt(0), maxnorm, k.new_full((), 1e15))
     norm = x.norm(dim=dim, keepdim=True, p=2).clamp_min(MIN_NORM)

@@ -1,0 +1,179 @@
+"""GPU parity: K2 gyroplane (both clamp variants, bias/squared/scaled flags), K1b weight prep, K1 Mobius
+matvec — forward, input grads and parameter grads — against the golden fixtures (reference files run
+verbatim) and the float32/float64 oracle on seeded inputs incl. the edge rows the survey lists
+(x -> p, |x| at the projection radius, plane through ~0, off-ball Mobius input, zero rows, zero weight rows)."""
+import pytest
+import torch
+
+from util_parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _oball(c, dtype=torch.float32):
+    from oracle.geoopt_min import PoincareBall
+
+    b = PoincareBall(c=c)
+    if dtype == torch.float64:
+        b.isp_c.data = b.isp_c.data.double()
+    return b
+
+
+def _oracle_layer_run(make_layer, params, x, gout, dtype):
+    """Build the oracle layer in `dtype`, load params, run fwd+bwd. Returns out, gx, {param: grad}."""
+    from oracle.geoopt_min.manifolds.stereographic import math as gmath
+
+    layer = make_layer(dtype)
+    with torch.no_grad():
+        for k, v in params.items():
+            getattr(layer, k).data = v.detach().clone().to(dtype)
+    xx = x.detach().clone().to(dtype).requires_grad_(True)
+    with gmath.fp32_semantics(dtype == torch.float64):
+        out = layer(xx)
+        out.backward(gout.detach().clone().to(dtype))
+    return out.detach(), xx.grad, {k: getattr(layer, k).grad for k in params}
+
+
+def _cuda_layer_run(layer, params, x, gout):
+    layer = layer.cuda()
+    with torch.no_grad():
+        for k, v in params.items():
+            getattr(layer, k).data.copy_(v)
+    xx = x.detach().clone().cuda().requires_grad_(True)
+    out = layer(xx)
+    out.backward(gout.cuda())
+    return out.detach(), xx.grad, {k: getattr(layer, k).grad for k in params}
+
+
+def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5):
+    assert_parity(cuda[0], o32[0], o64[0], what=tag + " out", rtol=rtol, atol=atol, row_relative=False)
+    assert_parity(cuda[1], o32[1], o64[1], what=tag + " gx", rtol=rtol, atol=atol, slack_mult=2.0)
+    for k in cuda[2]:
+        # parameter grads are sums over the batch: judge on the tensor's scale
+        assert_parity(cuda[2][k], o32[2][k], o64[2][k], what=tag + " g" + k, rtol=pg_tol, atol=atol, norm_relative=True,
+                      slack_mult=2.0)
+
+
+def _gyro_layers(kind, D, P, c):
+    import hvae
+    from hvae import layers as HL
+    from oracle import ref_port as R
+    from oracle.geoopt_min.layers.stereographic import Distance2StereographicHyperplanes as OGeo
+
+    ball = hvae.PoincareBall(c)
+    if kind == "bias":
+        return HL.Distance2PoincareHyperplanes(D, P, ball=ball), (lambda dt: R.Distance2PoincareHyperplanes(D, P, ball=_oball(c, dt))), ["points", "bias"]
+    if kind == "geoopt":
+        return HL.Distance2StereographicHyperplanes(D, P, ball=ball), (lambda dt: OGeo(D, P, ball=_oball(c, dt))), ["points"]
+    if kind == "squared":
+        return (HL.Distance2StereographicHyperplanes(D, P, signed=True, squared=True, ball=ball),
+                (lambda dt: OGeo(D, P, signed=True, squared=True, ball=_oball(c, dt))), ["points"])
+    if kind == "unsigned":
+        return (HL.Distance2StereographicHyperplanes(D, P, signed=False, ball=ball),
+                (lambda dt: OGeo(D, P, signed=False, ball=_oball(c, dt))), ["points"])
+    if kind == "geodesic":
+        return HL.GeodesicLayer(D, P, ball), (lambda dt: R.GeodesicLayer(D, P, _oball(c, dt))), ["_weight", "_bias"]
+    if kind == "geodesic_wn":
+        return (HL.GeodesicLayer(D, P, ball, weight_norm=True), (lambda dt: R.GeodesicLayer(D, P, _oball(c, dt), weight_norm=True)),
+                ["_weight", "_bias"])
+    raise KeyError(kind)
+
+
+def test_golden_gyroplane_and_geodesic(golden_ops):
+    for rec in golden_ops:
+        c, D = rec["c_ctor"], rec["D"]
+        for key, kind, pnames in (("gyroplane_bias", "bias", {"points": "points", "bias": "bias"}),
+                                  ("gyroplane_geoopt", "geoopt", {"points": "points"}),
+                                  ("gyroplane_squared", "squared", {"points": "points"}),
+                                  ("geodesic", "geodesic", {"_weight": "_weight", "_bias": "_bias"})):
+            g = rec[key]
+            P = g[list(pnames)[0]].shape[0]
+            layer, make_o, names = _gyro_layers(kind, D, P, c)
+            params = {k: g[k] for k in names}
+            cu = _cuda_layer_run(layer, params, g["x"], g["gout"])
+            o64 = _oracle_layer_run(make_o, params, g["x"], g["gout"], torch.float64)
+            gold = (g["out"], g["gx"], {k: g["g" + k] for k in names})
+            _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64)
+
+
+@pytest.mark.parametrize("kind", ["bias", "geoopt", "squared", "unsigned", "geodesic", "geodesic_wn"])
+@pytest.mark.parametrize("D,P,B", [(2, 16, 128), (2, 512, 77), (5, 100, 300), (10, 600, 130), (33, 50, 65), (64, 128, 257), (3, 1, 1)])
+def test_gyroplane_seeded(kind, D, P, B):
+    c = 1.0 if D != 5 else 0.5
+    torch.manual_seed(D * 1000 + P)
+    layer, make_o, names = _gyro_layers(kind, D, P, c)
+    ob = _oball(c)
+    x = ob.expmap0(torch.randn(B, D) * 0.8 / D ** 0.5).detach()
+    params = {k: getattr(layer, k).detach().clone() for k in names}
+    if "points" in params and B > 4 and P > 3:
+        x[2] = params["points"][1] * (1 + 1e-4)          # x -> p
+        x[3] = ob.expmap0(torch.randn(D) * 50.0)          # |x| at the projection radius
+        params["points"][min(3, P - 1)] *= 1e-9           # plane through ~origin
+    gout = torch.randn(B, P)
+    cu = _cuda_layer_run(layer, params, x, gout)
+    o32 = _oracle_layer_run(make_o, params, x, gout, torch.float32)
+    o64 = _oracle_layer_run(make_o, params, x, gout, torch.float64)
+    _check("%s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64)
+
+
+def _mobius_layers(F, P, c):
+    import hvae
+    from hvae import layers as HL
+    from oracle import ref_port as R
+
+    return HL.MobiusLayer(F, P, hvae.PoincareBall(c)), (lambda dt: R.MobiusLayer(F, P, _oball(c, dt)))
+
+
+def test_golden_mobius_layer(golden_ops):
+    for rec in golden_ops:
+        c, D = rec["c_ctor"], rec["D"]
+        for key in ("mobius_layer", "mobius_layer_zero_w"):
+            g = rec[key]
+            F = g["_weight"].shape[1]
+            layer, make_o = _mobius_layers(F, D, c)
+            params = {"_weight": g["_weight"], "_bias": g["_bias"]}
+            cu = _cuda_layer_run(layer, params, g["x"], g["gout"])
+            o64 = _oracle_layer_run(make_o, params, g["x"], g["gout"], torch.float64)
+            gold = (g["out"], g["gx"], {"_weight": g["g_weight"], "_bias": g["g_bias"]})
+            _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64, rtol=3e-5)
+
+
+@pytest.mark.parametrize("F,P,B", [(48, 2, 33), (512, 2, 128), (600, 10, 257), (512, 64, 100), (130, 40, 64), (1000, 5, 9), (64, 100, 50)])
+@pytest.mark.parametrize("scale", [3.0, 0.02])
+def test_mobius_layer_seeded(F, P, B, scale):
+    c = 1.0 if P != 10 else 1.4
+    torch.manual_seed(F + P)
+    layer, make_o = _mobius_layers(F, P, c)
+    params = {"_weight": layer._weight.detach().clone(), "_bias": layer._bias.detach().clone()}
+    x = torch.randn(B, F) * scale  # scale 3: Euclidean features far outside the ball (artanh clamp binds)
+    x[0].zero_()
+    if P > 1:
+        params["_weight"][1].zero_()
+    gout = torch.randn(B, P)
+    cu = _cuda_layer_run(layer, params, x, gout)
+    o32 = _oracle_layer_run(make_o, params, x, gout, torch.float32)
+    o64 = _oracle_layer_run(make_o, params, x, gout, torch.float64)
+    _check("mobius F=%d P=%d B=%d s=%g" % (F, P, B, scale), cu, o32, o64, rtol=3e-5)
+
+
+def test_weight_property_matches_reference(golden_ops):
+    import hvae
+    from hvae import layers as HL
+
+    rec = golden_ops[8]
+    g = rec["mobius_layer"]
+    layer = HL.MobiusLayer(g["_weight"].shape[1], rec["D"], hvae.PoincareBall(rec["c_ctor"])).cuda()
+    with torch.no_grad():
+        layer._weight.copy_(g["_weight"]); layer._bias.copy_(g["_bias"])
+    torch.testing.assert_close(layer.weight.cpu(), g["weight"], rtol=1e-5, atol=1e-7)
+
+
+def test_state_dict_keys_match_reference_layout():
+    import hvae
+    from hvae import layers as HL
+
+    ball = hvae.PoincareBall(1.0)
+    assert set(HL.MobiusLayer(8, 2, ball).state_dict()) == {"_weight", "_bias", "manifold.isp_c"}
+    assert set(HL.Distance2PoincareHyperplanes(2, 5, ball=ball).state_dict()) == {"points", "bias", "ball.isp_c"}
+    assert HL.MobiusLayer(8, 2, ball)._bias.shape == (2, 1)
+    assert HL.GyroplaneLayer is HL.GeodesicLayer
