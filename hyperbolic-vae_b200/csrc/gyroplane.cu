@@ -27,17 +27,31 @@ struct GyroPairCtx {
 };
 
 // scalar epilogue shared by forward and backward (and, later, by the tensor-core path)
+// Difference form (SIMT path): with e = |x-p|^2, q = <p,p-x>, qa = <a,p-x> accumulated from elementwise
+// differences (exact when x -> p), A = Bc + c e and
+//   N1 = -A<p,a> + Bc<x,a> = -Bc qa - c e <p,a>,   N2 = e (Bc^2 + 2 Bc c q + c^2 e |p|^2)
+// so the x -> p cancellation that the plain inner-product form suffers (abs error eps*|p|^2) is gone.
+struct GyroDiff {
+    float e, q, qa;
+};
+
 __device__ __forceinline__ float gyro_pair_fwd(float px, float xa, float x2, float p2, float pa, float an_raw,
-                                               const GyroParams& P, GyroPairCtx& k) {
+                                               const GyroParams& P, GyroPairCtx& k, const GyroDiff* df = nullptr) {
     const float c = P.c;
     const bool pvae = P.flags & HVAE_GYRO_PVAE;
-    k.A = 1.0f - 2.0f * c * px + c * x2;
     k.Bc = 1.0f - c * p2;
     const float den0 = 1.0f - 2.0f * c * px + c * c * p2 * x2;
     k.den_ok = den0 >= kMinNorm;
     k.den = fmaxf(den0, kMinNorm);
-    k.N1 = -k.A * pa + k.Bc * xa;
-    k.N2 = fmaxf(k.A * k.A * p2 - 2.0f * k.A * k.Bc * px + k.Bc * k.Bc * x2, 0.0f);
+    if (df) {
+        k.A = k.Bc + c * df->e;
+        k.N1 = -k.Bc * df->qa - c * df->e * pa;
+        k.N2 = fmaxf(df->e * (k.Bc * k.Bc + 2.0f * k.Bc * c * df->q + c * c * df->e * p2), 0.0f);
+    } else {
+        k.A = 1.0f - 2.0f * c * px + c * x2;
+        k.N1 = -k.A * pa + k.Bc * xa;
+        k.N2 = fmaxf(k.A * k.A * p2 - 2.0f * k.A * k.Bc * px + k.Bc * k.Bc * x2, 0.0f);
+    }
     const float rden = 1.0f / k.den;
     k.da = k.N1 * rden;
     float dn2r = k.N2 * rden * rden;
@@ -179,9 +193,9 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
     __syncthreads();
     for (int r0 = 0; r0 < kGyroTB; r0 += kGyroRB) {
         if (b0 + r0 >= B) break;
-        float px[kGyroRB], xa[kGyroRB];
+        float ee[kGyroRB], qq[kGyroRB], qa[kGyroRB];
 #pragma unroll
-        for (int r = 0; r < kGyroRB; ++r) px[r] = xa[r] = 0.0f;
+        for (int r = 0; r < kGyroRB; ++r) ee[r] = qq[r] = qa[r] = 0.0f;
 #pragma unroll 2
         for (int d = 0; d < D4; d += 4) {
             const float p0 = ps[(d + 0) * TJ + tid], p1 = ps[(d + 1) * TJ + tid];
@@ -194,8 +208,10 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
 #pragma unroll
             for (int r = 0; r < kGyroRB; ++r) {
                 const float4 xv = *reinterpret_cast<const float4*>(xs + (r0 + r) * D4 + d);
-                px[r] = fmaf(p0, xv.x, fmaf(p1, xv.y, fmaf(p2_, xv.z, fmaf(p3, xv.w, px[r]))));
-                if (!kAliased) xa[r] = fmaf(a0, xv.x, fmaf(a1, xv.y, fmaf(a2_, xv.z, fmaf(a3, xv.w, xa[r]))));
+                const float t0 = p0 - xv.x, t1 = p1 - xv.y, t2 = p2_ - xv.z, t3 = p3 - xv.w;
+                ee[r] = fmaf(t0, t0, fmaf(t1, t1, fmaf(t2, t2, fmaf(t3, t3, ee[r]))));
+                qq[r] = fmaf(p0, t0, fmaf(p1, t1, fmaf(p2_, t2, fmaf(p3, t3, qq[r]))));
+                if (!kAliased) qa[r] = fmaf(a0, t0, fmaf(a1, t1, fmaf(a2_, t2, fmaf(a3, t3, qa[r]))));
             }
         }
         if (j < P_) {
@@ -204,7 +220,11 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
                 const int b = b0 + r0 + r;
                 if (b < B) {
                     GyroPairCtx k;
-                    const float o = gyro_pair_fwd(px[r], kAliased ? px[r] : xa[r], xs2[r0 + r], p2, pa, an_raw, prm, k);
+                    GyroDiff df;
+                    df.e = ee[r]; df.q = qq[r]; df.qa = kAliased ? qq[r] : qa[r];
+                    const float px = p2 - qq[r];
+                    const float xa = kAliased ? px : pa - qa[r];
+                    const float o = gyro_pair_fwd(px, xa, xs2[r0 + r], p2, pa, an_raw, prm, k, &df);
                     out[(int64_t)b * P_ + j] = o + bj;
                 }
             }
@@ -263,20 +283,25 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
         __syncthreads();
         const int jn = min(TJ, P_ - j0);
         for (int jj = 0; jj < jn; ++jj) {
-            float px = 0.0f, xa = 0.0f;
+            GyroDiff df;
+            df.e = df.q = df.qa = 0.0f;
 #pragma unroll
             for (int d = 0; d < D4; d += 4) {
                 const float4 pv = *reinterpret_cast<const float4*>(&ps[jj][d]);
-                px = fmaf(pv.x, xr[d], fmaf(pv.y, xr[d + 1], fmaf(pv.z, xr[d + 2], fmaf(pv.w, xr[d + 3], px))));
+                const float t0 = pv.x - xr[d], t1 = pv.y - xr[d + 1], t2 = pv.z - xr[d + 2], t3 = pv.w - xr[d + 3];
+                df.e = fmaf(t0, t0, fmaf(t1, t1, fmaf(t2, t2, fmaf(t3, t3, df.e))));
+                df.q = fmaf(pv.x, t0, fmaf(pv.y, t1, fmaf(pv.z, t2, fmaf(pv.w, t3, df.q))));
                 if (!kAliased) {
                     const float4 av = *reinterpret_cast<const float4*>(&as[jj][d]);
-                    xa = fmaf(av.x, xr[d], fmaf(av.y, xr[d + 1], fmaf(av.z, xr[d + 2], fmaf(av.w, xr[d + 3], xa))));
+                    df.qa = fmaf(av.x, t0, fmaf(av.y, t1, fmaf(av.z, t2, fmaf(av.w, t3, df.qa))));
                 }
             }
-            if (kAliased) xa = px;
+            if (kAliased) df.qa = df.q;
             const float p2 = pst[jj][0], pa = pst[jj][1], an_raw = pst[jj][2];
+            const float px = p2 - df.q;
+            const float xa = kAliased ? px : pa - df.qa;
             GyroPairCtx k;
-            gyro_pair_fwd(px, xa, x2, p2, pa, an_raw, prm, k);
+            gyro_pair_fwd(px, xa, x2, p2, pa, an_raw, prm, k, &df);
             const GyroPairGrad gr = gyro_pair_bwd(gs[tid][jj], px, xa, x2, p2, pa, an_raw, prm, k);
             sdx2 += gr.dx2;
             const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
@@ -348,18 +373,23 @@ k_gyro_bwd_p(const float* __restrict__ x, const float* __restrict__ p, const flo
         const int bn = min(kGyroBpTB, be - b0);
         if (j < P_) {
             for (int bb = 0; bb < bn; ++bb) {
-                float px = 0.0f, xa = 0.0f;
+                GyroDiff df;
+                df.e = df.q = df.qa = 0.0f;
 #pragma unroll
                 for (int d = 0; d < D4; d += 4) {
                     const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][d]);
-                    px = fmaf(pr[d], xv.x, fmaf(pr[d + 1], xv.y, fmaf(pr[d + 2], xv.z, fmaf(pr[d + 3], xv.w, px))));
+                    const float t0 = pr[d] - xv.x, t1 = pr[d + 1] - xv.y, t2 = pr[d + 2] - xv.z, t3 = pr[d + 3] - xv.w;
+                    df.e = fmaf(t0, t0, fmaf(t1, t1, fmaf(t2, t2, fmaf(t3, t3, df.e))));
+                    df.q = fmaf(pr[d], t0, fmaf(pr[d + 1], t1, fmaf(pr[d + 2], t2, fmaf(pr[d + 3], t3, df.q))));
                     if (!kAliased)
-                        xa = fmaf(ar[d], xv.x, fmaf(ar[d + 1], xv.y, fmaf(ar[d + 2], xv.z, fmaf(ar[d + 3], xv.w, xa))));
+                        df.qa = fmaf(ar[d], t0, fmaf(ar[d + 1], t1, fmaf(ar[d + 2], t2, fmaf(ar[d + 3], t3, df.qa))));
                 }
-                if (kAliased) xa = px;
+                if (kAliased) df.qa = df.q;
+                const float px = p2 - df.q;
+                const float xa = kAliased ? px : pa - df.qa;
                 const float g = __ldg(gout + (int64_t)(b0 + bb) * P_ + j);  // coalesced across the CTA's planes
                 GyroPairCtx k;
-                gyro_pair_fwd(px, xa, xs2[bb], p2, pa, an_raw, prm, k);
+                gyro_pair_fwd(px, xa, xs2[bb], p2, pa, an_raw, prm, k, &df);
                 const GyroPairGrad gr = gyro_pair_bwd(g, px, xa, xs2[bb], p2, pa, an_raw, prm, k);
                 sdp2 += gr.dp2; sdpa += gr.dpa; sdan += gr.dan; sg += g;
                 const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
