@@ -5,7 +5,7 @@ verbatim) and the float32/float64 oracle on seeded inputs incl. the edge rows th
 import pytest
 import torch
 
-from util_parity import assert_parity
+from util_parity import assert_parity, kappa, pair_kappa, rtol_grad, rtol_val
 
 pytestmark = pytest.mark.gpu
 
@@ -14,8 +14,8 @@ def _oball(c, dtype=torch.float32):
     from oracle.geoopt_min import PoincareBall
 
     b = PoincareBall(c=c)
-    if dtype == torch.float64:
-        b.isp_c.data = b.isp_c.data.double()
+    if dtype == torch.float64:  # same curvature VALUE as the fp32 ball, held in double
+        b.isp_c.data = torch.log(torch.expm1(torch.tensor(float(b.c), dtype=torch.float64)))
     return b
 
 
@@ -45,9 +45,19 @@ def _cuda_layer_run(layer, params, x, gout):
     return out.detach(), xx.grad, {k: getattr(layer, k).grad for k in params}
 
 
-def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5):
-    assert_parity(cuda[0], o32[0], o64[0], what=tag + " out", rtol=rtol, atol=atol, row_relative=False)
-    assert_parity(cuda[1], o32[1], o64[1], what=tag + " gx", rtol=rtol, atol=atol, slack_mult=2.0)
+def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5, pk=None, squared=False):
+    """pk: (B,P) pair condition factors 1/(1-c|diff|^2).  out = asinh(.../(1-c|diff|^2))/sqrt(c): an fp32
+    error eps in (1-c|diff|^2) moves the output by eps*pk (absolute) and the gradients by eps*pk (relative)."""
+    if pk is not None:
+        # (squared outputs: d(out^2) = 2|out| d(out))
+        amp = 1.0 + 2.0 * torch.Tensor(o64[0].detach()).double().abs().sqrt() if squared else 1.0
+        atol_out = atol + 1.2e-6 * pk * amp
+        rg = 1e-5 + 2e-6 * pk.amax(dim=1, keepdim=True)
+        pg_tol = max(pg_tol, min(float(4e-6 * pk.max()), 5e-2))
+    else:
+        atol_out, rg = atol, rtol
+    assert_parity(cuda[0], o32[0], o64[0], what=tag + " out", rtol=rtol, atol=atol_out, row_relative=False, slack_mult=2.0)
+    assert_parity(cuda[1], o32[1], o64[1], what=tag + " gx", rtol=rg, atol=atol, slack_mult=2.0)
     for k in cuda[2]:
         # parameter grads are sums over the batch: judge on the tensor's scale
         assert_parity(cuda[2][k], o32[2][k], o64[2][k], what=tag + " g" + k, rtol=pg_tol, atol=atol, norm_relative=True,
@@ -93,7 +103,10 @@ def test_golden_gyroplane_and_geodesic(golden_ops):
             cu = _cuda_layer_run(layer, params, g["x"], g["gout"])
             o64 = _oracle_layer_run(make_o, params, g["x"], g["gout"], torch.float64)
             gold = (g["out"], g["gx"], {k: g["g" + k] for k in names})
-            _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64)
+            pk = None
+            if kind != "geodesic":
+                pk = pair_kappa(rec["c"], g["x"], g["points"])
+            _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64, pk=pk, squared=(kind == "squared"))
 
 
 @pytest.mark.parametrize("kind", ["bias", "geoopt", "squared", "unsigned", "geodesic", "geodesic_wn"])
@@ -113,7 +126,16 @@ def test_gyroplane_seeded(kind, D, P, B):
     cu = _cuda_layer_run(layer, params, x, gout)
     o32 = _oracle_layer_run(make_o, params, x, gout, torch.float32)
     o64 = _oracle_layer_run(make_o, params, x, gout, torch.float64)
-    _check("%s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64)
+    pk = None
+    if "points" in params:
+        pk = pair_kappa(float(_oball(c).c), x, params["points"])
+    else:  # geodesic: p = transported weight
+        from oracle import ref_port as R
+        lay = R.GeodesicLayer(D, P, _oball(c))
+        with torch.no_grad():
+            lay._weight.copy_(params["_weight"]); lay._bias.copy_(params["_bias"])
+            pk = pair_kappa(float(_oball(c).c), x, lay.weight)
+    _check("%s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64, pk=pk, squared=(kind == "squared"))
 
 
 def _mobius_layers(F, P, c):

@@ -1,0 +1,81 @@
+"""GPU parity of the whole train step (forward + loss + backward) for the reference's model graphs:
+golden fixtures (reference files executed verbatim, seeded noise recorded) + float64 oracle tie-breaker.
+Identical weights (the reference's state_dict is loaded as-is), identical inputs, identical injected noise."""
+import pytest
+import torch
+
+from util_parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["A", "A_c0.5_D5", "B", "B_c1.4_D8", "B_linear_bernoulli", "C", "OneB", "OneB_log_prob"]
+
+
+def _build(mod, name, **kw):
+    if name == "A":
+        return mod.ModelA(torch.Size([1, 10, 10]), 2, 1.0, 1.0, 1.0, **kw)
+    if name == "A_c0.5_D5":
+        return mod.ModelA(torch.Size([1, 10, 10]), 5, 0.5, 2.0, 2.0, **kw)
+    if name == "B":
+        return mod.ModelB((1, 16, 16), 2, 1.0, "mobius", "geoopt_gyroplane", 1.0, "mse", **kw)
+    if name == "B_c1.4_D8":
+        return mod.ModelB((1, 16, 16), 8, 1.4, "mobius", "geoopt_gyroplane", 2.0, "mse", **kw)
+    if name == "B_linear_bernoulli":
+        return mod.ModelB((1, 16, 16), 2, 1.0, "linear", "geoopt_gyroplane", 1.0, "bernoulli", **kw)
+    if name == "C":
+        return mod.ModelC(torch.Size([300]), 5, 1.0, 32, 0.5, **kw)
+    if name == "OneB":
+        return mod.ModelOneB(torch.Size([300]), 32, 2, 1.0, 2.0, 0.5, "logmap0_analytic")
+    if name == "OneB_log_prob":
+        return mod.ModelOneB(torch.Size([300]), 32, 3, 0.5, 1.0, 1.0, "log_prob")
+    raise KeyError(name)
+
+
+def _load(model, sd):
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if "isp_c" not in k], missing
+    assert not unexpected, unexpected
+
+
+def _oracle64(name, g):
+    from oracle import ref_port as R
+    from oracle.geoopt_min.manifolds.stereographic import math as gmath
+    from oracle.geoopt_min.manifolds.stereographic.manifold import PoincareBall as OBall
+
+    m = _build(R, name)
+    _load(m, g["state_dict"])
+    c32 = {id(b): float(b.c) for b in m.modules() if isinstance(b, OBall)}
+    m = m.double()
+    for b in m.modules():
+        if isinstance(b, OBall):  # keep the fp32 curvature VALUE
+            b.isp_c.data = torch.log(torch.expm1(torch.tensor(c32[id(b)], dtype=torch.float64)))
+    with gmath.fp32_semantics():
+        losses = m.loss(g["x"].double(), eps=g["eps"].double())
+        losses["loss_total"].backward()
+    return losses, {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", NAMES)
+def test_model_step_matches_reference(golden_models, name, fused):
+    from hvae import models as HM
+
+    if name.startswith("OneB") and not fused:
+        pytest.skip("ModelOneB has a single (unfused) path")
+    g = golden_models[name]
+    kw = {} if name.startswith("OneB") else {"fused": fused}
+    model = _build(HM, name, **kw)
+    _load(model, g["state_dict"])
+    model = model.cuda()
+    eps = g["eps"].cuda()
+    losses = model.loss(g["x"].cuda(), eps=eps)
+    losses["loss_total"].backward()
+    l64, g64 = _oracle64(name, g)
+    for k, v in g["losses"].items():
+        assert_parity(losses[k].reshape(1), v.reshape(1), l64[k].reshape(1), what="%s %s" % (name, k), rtol=1e-5, atol=1e-6,
+                      row_relative=False, slack_mult=2.0)
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads) == set(g["grads"]), set(grads) ^ set(g["grads"])
+    for k, v in g["grads"].items():
+        assert_parity(grads[k], v, g64[k], what="%s grad %s" % (name, k), rtol=2e-5, atol=1e-7, norm_relative=True,
+                      slack_mult=2.0)

@@ -44,3 +44,37 @@ def assert_parity(cuda, o32, o64, rtol=RTOL, atol=ATOL, what="", norm_relative=F
             % (what, int(bad.sum()), bad.numel(), idx, cuda[idx], o64[idx],
                ("%.9g" % o32[idx]) if o32 is not None else "-", err[idx], bound[idx] if torch.is_tensor(bound) and bound.dim() else float(bound))
         )
+
+
+def kappa(c, *points):
+    """Per-row condition factor max_i 1/(1 - c|p_i|^2) >= 1 (capped at the fp32 projection radius, 125).
+    Every Poincare map divides by (1 - c|.|^2): values carry a relative fp32 error ~ eps*kappa and
+    derivatives of two-point maps ~ eps*kappa^2 (both points near the boundary), in ANY evaluation order
+    (the reference's included)."""
+    k = None
+    for p in points:
+        p = torch.Tensor(p.detach()).double().cpu()
+        p = p.reshape(-1, p.shape[-1])
+        ki = 1.0 / (1.0 - c * p.pow(2).sum(-1, keepdim=True)).clamp_min(4e-3)
+        k = ki if k is None else torch.maximum(k, ki)
+    return k.clamp_min(1.0)
+
+
+def rtol_val(kap, base=RTOL):
+    return base * kap
+
+
+def rtol_grad(kap, base=RTOL):
+    return torch.maximum(torch.full_like(kap, base), 2e-6 * kap * kap)
+
+
+def pair_kappa(c, x, p):
+    """(B,P) condition factor of the gyroplane pair: 1/(1 - c|(-p)(+)x|^2), float64."""
+    x = torch.Tensor(x.detach()).double().cpu()[:, None, :]
+    p = torch.Tensor(p.detach()).double().cpu()[None, :, :]
+    x2, p2, px = (x * x).sum(-1), (p * p).sum(-1), (x * p).sum(-1)
+    A = 1 - 2 * c * px + c * x2
+    Bc = 1 - c * p2
+    den = (1 - 2 * c * px + c * c * p2 * x2).clamp_min(1e-15)
+    dn2 = (A * A * p2 - 2 * A * Bc * px + Bc * Bc * x2) / (den * den)
+    return 1.0 / (1.0 - c * dn2).abs().clamp_min(1e-7)
