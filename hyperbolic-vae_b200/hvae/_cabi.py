@@ -26,7 +26,6 @@ def declared_functions(header_path=HEADER_PATH):
     """Parse `ret name(args);` prototypes out of the public header -> {name: (ret, [argtypes])}."""
     src = open(header_path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    src = re.sub(r"#ifdef HVAE_PENDING.*?#endif", "", src, flags=re.S)
     protos = {}
     for m in re.finditer(r"^\s*(int|size_t|const char\*)\s+(hvae_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S | re.M):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()

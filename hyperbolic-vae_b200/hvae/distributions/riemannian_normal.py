@@ -1,0 +1,131 @@
+"""Drop-in for `hyperbolic_vae.distributions.old_pvae_riemannian_normal.RiemannianNormal` and the pvae
+classes under it (HyperbolicRadius, HypersphericalUniform) — reference: hyperbolic_vae/distributions/
+old_pvae_riemannian_normal.py:12-52; pvae semantics per SURVEY.md App. A.2.
+
+  rsample:  alpha ~ U(S^{D-1}), r ~ rho(.; sigma) (K6: in-kernel rejection sampling, Philox),
+            z = expmap_polar(mu, alpha, r); dr/dsigma by implicit reparameterisation (K6').
+  log_prob: -dist(mu, z)^2 / (2 sigma^2) - log|S^{D-1}| - logZ(sigma)   (K7: float64 signed series).
+
+The sampler cannot be bit-identical to pvae's (its ARS consumes a data-dependent number of torch.rand
+calls); parity is exact formulas on injected (alpha, r) + a KS test of the sampled radii against cdf_r.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import Tensor
+
+from .. import ops
+from ..manifolds import PoincareBall
+
+
+class HypersphericalUniform(torch.distributions.Distribution):
+    """Uniform on S^{dim} (dim = D-1)."""
+
+    support = torch.distributions.constraints.real
+    has_rsample = False
+    arg_constraints = {}
+
+    def __init__(self, dim, device="cuda", validate_args=None):
+        super().__init__(torch.Size([dim]), validate_args=False)
+        self._dim, self._device = dim, device
+
+    @property
+    def dim(self):
+        return self._dim
+
+    def sample(self, shape=torch.Size()):
+        v = torch.randn(*torch.Size(shape), self._dim + 1, device=self._device)
+        return v / v.norm(dim=-1, keepdim=True)
+
+    def _log_normalizer(self) -> float:
+        return math.log(2) + (self._dim + 1) / 2 * math.log(math.pi) - math.lgamma((self._dim + 1) / 2)
+
+    def entropy(self):
+        return torch.tensor(self._log_normalizer())
+
+    def log_prob(self, x):
+        return torch.full(x.shape[:-1], -self._log_normalizer(), device=x.device)
+
+
+class HyperbolicRadius(torch.distributions.Distribution):
+    """pvae HyperbolicRadius(dim, c, scale): scale (..., 1) per-row sigma."""
+
+    support = torch.distributions.constraints.positive
+    has_rsample = True
+    arg_constraints = {}
+
+    def __init__(self, dim, c, scale: Tensor, ars=True, validate_args=None):
+        self.dim = int(dim)
+        self.c_value = float(c) if not torch.is_tensor(c) else float(c)
+        self.scale = scale
+        self.device = scale.device
+        self.log_normalizer = ops.hradius_lognorm(scale, self.dim, self.c_value)
+        super().__init__(self.scale.size(), validate_args=False)
+
+    def sample(self, sample_shape=torch.Size(), seed=None, offset=None) -> Tensor:
+        S = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
+        r = ops.hradius_sample(self.scale, S, self.dim, self.c_value, seed=seed, offset=offset)
+        return r.view(S, *self.scale.shape)
+
+    def rsample(self, sample_shape=torch.Size(), r: Tensor = None) -> Tensor:
+        """r: optional injected radii of shape (S, *scale.shape)."""
+        if r is None:
+            r = self.sample(sample_shape)
+        S = r.shape[0]
+        out, _ = ops.hradius_reparam(ops._c(r.detach()).view(S, -1), ops._c(self.scale).view(-1), self.dim, self.c_value)
+        return out.view(r.shape)
+
+    def cdf(self, value: Tensor) -> Tensor:
+        S = value.shape[0]
+        return ops.hradius_cdf(value.reshape(S, -1), self.scale, self.dim, self.c_value).view(value.shape)
+
+    def log_prob(self, value: Tensor) -> Tensor:
+        sc = math.sqrt(self.c_value)
+        x = sc * value
+        logsinh = x + torch.log1p(-torch.exp(-2 * x)) - math.log(2)
+        return (-value.pow(2) / (2 * self.scale.pow(2)) + (self.dim - 1) * logsinh
+                - (self.dim - 1) / 2 * math.log(self.c_value) - self.log_normalizer)
+
+
+class RiemannianNormal(torch.distributions.Distribution):
+    arg_constraints = {}
+    support = torch.distributions.constraints.real
+    has_rsample = True
+    validate_loc = False  # the reference asserts no-NaN and on-manifold on every construction (host syncs)
+
+    @property
+    def mean(self):
+        return self.loc
+
+    def __init__(self, loc: Tensor, scale: Tensor, manifold: PoincareBall, validate_args=None):
+        if validate_args or RiemannianNormal.validate_loc:
+            assert not (torch.isnan(loc).any() or torch.isnan(scale).any())
+            manifold.assert_check_point_on_manifold(loc)
+        self.manifold = manifold
+        self.loc = loc
+        self.scale = scale.clamp(min=0.1, max=7.0)
+        D = loc.shape[-1]
+        self.radius = HyperbolicRadius(D, manifold.c_value, self.scale)
+        self.direction = HypersphericalUniform(D - 1, device=loc.device)
+        super().__init__(loc.shape[:-1], loc.shape[-1:], validate_args=False)
+
+    def sample(self, shape=torch.Size()):
+        with torch.no_grad():
+            return self.rsample(shape)
+
+    def rsample(self, sample_shape=torch.Size(), alpha: Tensor = None, r: Tensor = None) -> Tensor:
+        sample_shape = torch.Size(sample_shape)
+        if alpha is None:
+            alpha = self.direction.sample(torch.Size([*sample_shape, *self.loc.shape[:-1]]))
+        radius = self.radius.rsample(sample_shape, r=r)
+        if len(sample_shape) == 0:
+            return ops.expmap_polar(self.loc, alpha.reshape(self.loc.shape), radius.reshape(*self.loc.shape[:-1], 1),
+                                    self.manifold.c_value)
+        return ops.expmap_polar(self.loc, alpha, radius, self.manifold.c_value)
+
+    def log_prob(self, value: Tensor) -> Tensor:
+        loc = self.loc.expand(value.shape)
+        radius_sq = self.manifold.dist(loc, value, keepdim=True).pow(2)
+        return -radius_sq / 2 / self.scale.pow(2) - self.direction._log_normalizer() - self.radius.log_normalizer

@@ -221,8 +221,10 @@ class ModelOneB(nn.Module, _LatentMixin):
             t1 = (mu0 / self.prior_scale).pow(2)
             return (0.5 * (var_ratio + t1 - 1 - var_ratio.log())).mean()
         if self.kl_loss_method == "log_prob":
+            # NB (vae_one_b.py:193-213): z is (B,D) here, so WrappedNormal.log_prob broadcasts to ALL PAIRS
+            # (z_i under q_j) -> (B,B,1); the prior is built with a (B,D) scale so it broadcasts the same way.
             q = WrappedNormal(mu, scale, m)
-            p = WrappedNormal.origin_prior(mu.shape[-1], self.prior_scale, m, device=mu.device)
+            p = WrappedNormal(m.origin(mu.shape[-1], device=mu.device), torch.ones_like(scale) * self.prior_scale, m)
             lq, lp = q.log_prob(z), p.log_prob(z)
             return (lq.exp() * (lq - lp)).mean()
         if self.kl_loss_method == "logmap0_log_prob":
@@ -246,3 +248,52 @@ class ModelOneB(nn.Module, _LatentMixin):
             raise ValueError(f"Unrecognized loss_recon_method: {self.loss_recon_method}")
         kl = self.loss_kl(mu, scale, z)
         return dict(loss_reconstruction=recon, loss_kl=kl, loss_total=recon + self.beta * kl)
+
+
+class PvaeMnist(nn.Module):
+    """Config 2 — the pvae MNIST graph the reference transcribes in scripts/_9_pvae_replicate.py:5-29,124-158
+    with the objective of training/old_pvae_train.py:53-58 (App. A.2):
+      enc: Linear(784,h) ReLU -> mu = expmap0(MobiusLayer(h,D)(e)), sigma = softplus(Linear(h,1)) + 1e-5
+      posterior / prior: RiemannianNormal (HyperbolicRadius rejection sampler), K = 1
+      dec: GeodesicLayer(D,h) ReLU -> Linear(h,784) logits; Bernoulli likelihood (BCE with logits)
+      loss = -E log p(x|z) + beta (log q(z|x) - log p(z)), summed over the batch."""
+
+    def __init__(self, latent_dim=10, hidden_dim=600, c=1.0, prior_std=1.0, beta=1.0, data_size=(1, 28, 28)):
+        super().__init__()
+        from .distributions.riemannian_normal import RiemannianNormal  # noqa: F401
+
+        self.data_size = torch.Size(data_size)
+        n = self.data_size.numel()
+        self.manifold = PoincareBall(c)
+        self.beta, self.prior_std, self.latent_dim = beta, prior_std, latent_dim
+        self.enc = nn.Sequential(nn.Linear(n, hidden_dim), nn.ReLU())
+        self.fc21 = MobiusLayer(hidden_dim, latent_dim, self.manifold)
+        self.fc22 = nn.Linear(hidden_dim, 1)
+        self.dec0 = GeodesicLayer(latent_dim, hidden_dim, self.manifold)
+        self.fc31 = nn.Linear(hidden_dim, n)
+        self._pz_mu = nn.Parameter(torch.zeros(1, latent_dim), requires_grad=False)
+        self._pz_logvar = nn.Parameter(torch.zeros(1, 1), requires_grad=False)
+
+    def encode(self, x):
+        e = self.enc(x.view(x.shape[0], -1))
+        mu = self.manifold.expmap0(self.fc21(e))
+        return mu, F.softplus(self.fc22(e)) + 1e-5
+
+    def decode(self, z):
+        return self.fc31(F.relu(self.dec0(z)))
+
+    def loss(self, x, alpha=None, r=None):
+        from .distributions.riemannian_normal import RiemannianNormal
+
+        B = x.shape[0]
+        mu, sigma = self.encode(x)
+        q = RiemannianNormal(mu, sigma, self.manifold)
+        zs = q.rsample(torch.Size([1]), alpha=alpha, r=r)  # (1,B,D)
+        logits = self.decode(zs)
+        lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
+        pz_scale = F.softplus(self._pz_logvar) / math.log(2) * self.prior_std
+        p = RiemannianNormal(self._pz_mu, pz_scale, self.manifold)
+        kld = q.log_prob(zs).sum(-1) - p.log_prob(zs).sum(-1)
+        recon = -lpx_z.mean(0).sum()
+        kl = kld.mean(0).sum()
+        return dict(loss_total=recon + self.beta * kl, recon_loss=recon, kl_loss=kl)

@@ -626,3 +626,151 @@ def mobius_matvec(x: Tensor, M: Tensor, c: float) -> Tensor:
     lead = x.shape[:-1]
     y, _ = mobius_matvec_fwd(_rows(x), _c(M), c)
     return y.view(*lead, M.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# K6 / K7 HyperbolicRadius + expmap_polar
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::hradius_lognorm_fwd", mutates_args=())
+def hradius_lognorm_fwd(sigma: Tensor, dim: int, c: float) -> Tuple[Tensor, Tensor]:
+    """sigma (B,) -> (logZ (B,), dlogZ/dsigma (B,)); float64 series inside, float32 out (pvae semantics)."""
+    C.require_cuda(sigma)
+    logz, dlogz = torch.empty_like(sigma), torch.empty_like(sigma)
+    C.call("hvae_hradius_lognorm_fwd_f32", C.ptr(sigma), C.ptr(logz), C.ptr(dlogz), sigma.numel(), dim, c, C.stream())
+    return logz, dlogz
+
+
+@hradius_lognorm_fwd.register_fake
+def _(sigma, dim, c):
+    return torch.empty_like(sigma), torch.empty_like(sigma)
+
+
+def _hl_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _hl_backward(ctx, g, _g2):
+    (dlogz,) = ctx.saved_tensors
+    return g * dlogz, None, None
+
+
+hradius_lognorm_fwd.register_autograd(_hl_backward, setup_context=_hl_setup)
+
+
+def hradius_lognorm(sigma: Tensor, dim: int, c: float) -> Tensor:
+    shape = sigma.shape
+    return hradius_lognorm_fwd(_c(sigma).view(-1), int(dim), c)[0].view(shape)
+
+
+_philox_offset = 0
+
+
+def hradius_sample(sigma: Tensor, S: int, dim: int, c: float, seed: Optional[int] = None, offset: Optional[int] = None) -> Tensor:
+    """r (S,B) ~ rho(.; sigma_b) by in-kernel rejection sampling (Philox4x32-10).  No gradient."""
+    global _philox_offset
+    C.require_cuda(sigma)
+    sig = _c(sigma.detach()).view(-1)
+    B = sig.numel()
+    if seed is None:
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if offset is None:
+        offset = _philox_offset
+        _philox_offset += S * B
+    r = sig.new_empty(S, B)
+    C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r), S, B, dim, c, seed, offset, C.stream())
+    return r
+
+
+@_op("hvae::hradius_reparam", mutates_args=())
+def hradius_reparam(r: Tensor, sigma: Tensor, dim: int, c: float) -> Tuple[Tensor, Tensor]:
+    """Identity on r (S,B) carrying the implicit-reparameterisation gradient dr/dsigma (pvae impl_rsample)."""
+    C.require_cuda(r, sigma)
+    S, B = r.shape
+    dr = torch.empty_like(r)
+    C.call("hvae_hradius_rgrad_f32", C.ptr(sigma), C.ptr(r), C.ptr(dr), None, S, B, dim, c, C.stream())
+    return r.clone(), dr
+
+
+@hradius_reparam.register_fake
+def _(r, sigma, dim, c):
+    return torch.empty_like(r), torch.empty_like(r)
+
+
+def _hr_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _hr_backward(ctx, g, _g2):
+    (dr,) = ctx.saved_tensors
+    return None, (g * dr).sum(0), None, None
+
+
+hradius_reparam.register_autograd(_hr_backward, setup_context=_hr_setup)
+
+
+def hradius_cdf(r: Tensor, sigma: Tensor, dim: int, c: float) -> Tensor:
+    C.require_cuda(r, sigma)
+    S, B = r.shape
+    dr, cdf = torch.empty_like(r), torch.empty_like(r)
+    C.call("hvae_hradius_rgrad_f32", C.ptr(_c(sigma).view(-1)), C.ptr(_c(r)), C.ptr(dr), C.ptr(cdf), S, B, dim, c, C.stream())
+    return cdf
+
+
+@_op("hvae::expmap_polar_fwd", mutates_args=())
+def expmap_polar_fwd(mu: Tensor, alpha: Tensor, r: Tensor, c: float) -> Tensor:
+    """mu (B,D); alpha (S,B,D) directions; r (S,B) radii -> z (S,B,D)"""
+    C.require_cuda(mu, alpha, r)
+    S, B, D = alpha.shape
+    z = torch.empty_like(alpha)
+    C.call("hvae_expmap_polar_fwd_f32", C.ptr(mu), C.ptr(alpha), C.ptr(r), C.ptr(z), S, B, D, c, C.stream())
+    return z
+
+
+@expmap_polar_fwd.register_fake
+def _(mu, alpha, r, c):
+    return torch.empty_like(alpha)
+
+
+@_op("hvae::expmap_polar_bwd", mutates_args=())
+def expmap_polar_bwd(mu: Tensor, alpha: Tensor, r: Tensor, gz: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(mu, alpha, r, gz)
+    S, B, D = alpha.shape
+    gmu, gr = torch.empty_like(mu), torch.empty_like(r)
+    C.call("hvae_expmap_polar_bwd_f32", C.ptr(mu), C.ptr(alpha), C.ptr(r), C.ptr(gz), C.ptr(gmu), C.ptr(gr), S, B, D, c,
+           C.stream())
+    return gmu, gr
+
+
+@expmap_polar_bwd.register_fake
+def _(mu, alpha, r, gz, c):
+    return torch.empty_like(mu), torch.empty_like(r)
+
+
+def _ep_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], inputs[2])
+    ctx.c = inputs[3]
+
+
+def _ep_backward(ctx, gz):
+    mu, alpha, r = ctx.saved_tensors
+    gmu, gr = expmap_polar_bwd(mu, alpha, r, _c(gz), ctx.c)
+    return gmu, None, gr, None
+
+
+expmap_polar_fwd.register_autograd(_ep_backward, setup_context=_ep_setup)
+
+
+def expmap_polar(mu: Tensor, alpha: Tensor, r: Tensor, c: float) -> Tensor:
+    """pvae PoincareBall.expmap_polar(x, u, r): mu (..., D) broadcast against alpha (S, ..., D), r (S, ..., 1)."""
+    D = alpha.shape[-1]
+    if alpha.dim() == mu.dim():
+        alpha, r = alpha.unsqueeze(0), r.unsqueeze(0)
+        squeeze = True
+    else:
+        squeeze = False
+    S = alpha.shape[0]
+    mu_b = mu.expand(alpha.shape[1:]) if mu.shape != alpha.shape[1:] else mu
+    B = mu_b.numel() // D
+    z = expmap_polar_fwd(_c(mu_b).view(B, D), _c(alpha).view(S, B, D), _c(r.expand(*alpha.shape[:-1], 1)).view(S, B), c)
+    z = z.view(alpha.shape)
+    return z.squeeze(0) if squeeze else z

@@ -127,7 +127,6 @@ int hvae_mobius_matvec_bwd_f32(const float* x, const float* M, const float* mx, 
                                float* gx, float* gM, int64_t B, int64_t F, int64_t P, float c,
                                void* workspace, size_t workspace_bytes, void* stream);
 
-#ifdef HVAE_PENDING /* declared ahead of implementation; enabled as each kernel lands */
 /* ---- K6/K7: HyperbolicRadius  (distributions/old_pvae_riemannian_normal.py:31,51 -> pvae, App. A.2) ------
  * sigma: (B,) per-row scale (already clamped to [0.1,7] by the caller as RiemannianNormal does). */
 int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, float* dlogZ_dsigma, int64_t B, int64_t dim,
@@ -143,8 +142,6 @@ int hvae_expmap_polar_fwd_f32(const float* mu, const float* alpha, const float* 
                               int64_t S, int64_t B, int64_t D, float c, void* stream);
 int hvae_expmap_polar_bwd_f32(const float* mu, const float* alpha, const float* r, const float* gz,
                               float* gmu, float* gr, int64_t S, int64_t B, int64_t D, float c, void* stream);
-
-#endif /* HVAE_PENDING */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,181 @@
+"""GPU parity: K6/K7 HyperbolicRadius (log-normaliser + sigma-gradient, CDF, implicit reparameterisation
+gradient, rejection sampler), expmap_polar, RiemannianNormal, and the config-2 (pvae MNIST) train step."""
+import math
+
+import pytest
+import torch
+
+from util_parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+GRID = [(2, 1.0), (3, 0.5), (5, 1.0), (10, 1.0), (10, 2.0), (16, 0.7), (32, 1.0)]
+
+
+def _sigmas(dim):
+    lo = 0.1 if dim <= 10 else 0.3  # below this the alternating series itself loses digits (in the reference too)
+    return torch.cat([torch.linspace(lo, 1.0, 40), torch.linspace(1.0, 7.0, 40)])
+
+
+@pytest.mark.parametrize("dim,c", GRID)
+def test_lognorm_and_grad(dim, c):
+    from hvae import ops
+    from oracle.pvae_min.distributions import hyperbolic_radius as hr
+
+    sig = _sigmas(dim)
+    s64 = sig.double().requires_grad_(True)
+    o = hr.log_normalizer(s64.unsqueeze(-1), torch.tensor(c, dtype=torch.float64), dim).squeeze(-1)
+    o.sum().backward()
+    sc = sig.cuda().requires_grad_(True)
+    lz = ops.hradius_lognorm(sc, dim, c)
+    lz.sum().backward()
+    assert_parity(lz, None, o.detach(), what="logZ dim=%d" % dim, rtol=1e-5, atol=1e-5, row_relative=False)
+    assert_parity(sc.grad, None, s64.grad, what="dlogZ dim=%d" % dim, rtol=2e-5, atol=1e-5, row_relative=False)
+
+
+@pytest.mark.parametrize("dim,c", GRID)
+def test_cdf_and_implicit_grad(dim, c):
+    from hvae import ops
+    from oracle.pvae_min.distributions import hyperbolic_radius as hr
+
+    torch.manual_seed(dim)
+    sig = torch.rand(64) * 2.0 + 0.3
+    ct = torch.tensor(c, dtype=torch.float64)
+    mean, var = hr._moments(sig.unsqueeze(-1), ct, dim)
+    r = (mean + var.sqrt() * torch.randn(3, 64, dtype=torch.float64) * 0.8).clamp_min(0.05).float()  # (S,B)
+    F64 = hr.cdf_r(r.double(), sig.double().expand(3, 64), ct, dim)
+    gv, gs = hr.grad_cdf_value_scale(r, sig.expand(3, 64), ct, dim)
+    cdf = ops.hradius_cdf(r.cuda(), sig.cuda(), dim, c)
+    assert_parity(cdf, None, F64, what="cdf", rtol=1e-5, atol=2e-6, row_relative=False)
+    rr = r.cuda()
+    s = sig.cuda().requires_grad_(True)
+    out, _ = ops.hradius_reparam(rr, s, dim, c)
+    g = torch.randn(3, 64)
+    out.backward(g.cuda())
+    ref = (g.double() * (-gs / gv)).sum(0)
+    assert torch.equal(out.cpu(), r)
+    assert_parity(s.grad, None, ref, what="implicit reparam grad", rtol=5e-5, atol=1e-5, row_relative=False)
+
+
+@pytest.mark.parametrize("dim,c,sigma", [(2, 1.0, 0.5), (2, 1.0, 3.0), (5, 1.0, 0.15), (10, 1.0, 1.0), (10, 2.0, 0.3), (32, 0.7, 1.5), (1, 1.0, 0.8)])
+def test_sampler_kolmogorov_smirnov(dim, c, sigma):
+    """Distributional parity: the rejection sampler's radii against the closed-form CDF (oracle, float64)."""
+    from hvae import ops
+    from oracle.pvae_min.distributions import hyperbolic_radius as hr
+
+    N = 200_000
+    sig = torch.full((N,), sigma, device="cuda")
+    r = ops.hradius_sample(sig, 1, dim, c, seed=1234, offset=0).view(-1)
+    assert torch.isfinite(r).all() and (r > 0).all()
+    rs = r.double().cpu().sort().values
+    F = hr.cdf_r(rs, torch.full_like(rs, sigma), torch.tensor(c, dtype=torch.float64), dim)
+    i = torch.arange(1, N + 1, dtype=torch.float64)
+    D = torch.maximum((i / N - F).abs().max(), (F - (i - 1) / N).abs().max()).item()
+    # KS critical value at alpha = 1e-3: 1.95/sqrt(N)
+    assert D < 1.95 / math.sqrt(N), "KS statistic %.5f (dim=%d c=%g sigma=%g)" % (D, dim, c, sigma)
+    # determinism + stream disjointness of the counter-based RNG
+    r2 = ops.hradius_sample(sig, 1, dim, c, seed=1234, offset=0).view(-1)
+    assert torch.equal(r, r2)
+    r3 = ops.hradius_sample(sig[:1000], 1, dim, c, seed=1234, offset=N).view(-1)
+    assert not torch.equal(r3, r[:1000])
+
+
+def _oracle_pball(dim, c, dtype):
+    from oracle.pvae_min.manifolds import PoincareBall
+
+    b = PoincareBall(dim, c)
+    if dtype == torch.float64:
+        b.isp_c.data = torch.log(torch.expm1(torch.tensor(float(b.c), dtype=torch.float64)))
+    return b
+
+
+@pytest.mark.parametrize("D,c", [(2, 1.0), (5, 0.5), (10, 1.0)])
+def test_riemannian_normal_injected_noise(D, c):
+    import hvae
+    from hvae.distributions import RiemannianNormal
+    from oracle import ref_port as R
+    from oracle.geoopt_min.manifolds.stereographic import math as gmath
+
+    torch.manual_seed(D)
+    B = 200
+    ob32 = _oracle_pball(D, c, torch.float32)
+    mu0 = ob32.expmap0(torch.randn(B, D) * 0.6 / D ** 0.5).detach()
+    sg0 = torch.rand(B, 1) * 1.5 + 0.3
+    alpha = torch.randn(1, B, D)
+    alpha = alpha / alpha.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        r0 = R.RiemannianNormal(mu0, sg0, ob32).radius.sample(torch.Size([1]))  # (1,B,1) oracle ARS radii
+    gz, glp = torch.randn(1, B, D), torch.randn(1, B, 1)
+
+    def oracle(dtype):
+        ball = _oracle_pball(D, c, dtype)
+        mu = mu0.clone().to(dtype).requires_grad_(True)
+        sg = sg0.clone().to(dtype).requires_grad_(True)
+        with gmath.fp32_semantics(dtype == torch.float64):
+            q = R.RiemannianNormal(mu, sg, ball)
+            z = q.rsample(torch.Size([1]), alpha=alpha.to(dtype), r=r0.to(dtype))
+            lp = q.log_prob(z)
+            ((z * gz.to(dtype)).sum() + (lp * glp.to(dtype)).sum()).backward()
+        return z.detach(), lp.detach(), mu.grad, sg.grad
+
+    o32, o64 = oracle(torch.float32), oracle(torch.float64)
+    ball = hvae.PoincareBall(c)
+    mu = mu0.cuda().requires_grad_(True)
+    sg = sg0.cuda().requires_grad_(True)
+    q = RiemannianNormal(mu, sg, ball)
+    z = q.rsample(torch.Size([1]), alpha=alpha.cuda(), r=r0.cuda())
+    lp = q.log_prob(z)
+    ((z * gz.cuda()).sum() + (lp * glp.cuda()).sum()).backward()
+    assert_parity(z, o32[0], o64[0], what="RN z", rtol=2e-5, atol=2e-6)
+    assert_parity(lp, o32[1], o64[1], what="RN log_prob", rtol=2e-5, atol=2e-5, row_relative=False, slack_mult=2.0)
+    assert_parity(mu.grad, o32[2], o64[2], what="RN gmu", rtol=5e-5, atol=2e-5, slack_mult=2.0)
+    assert_parity(sg.grad, o32[3], o64[3], what="RN gsigma", rtol=5e-5, atol=2e-5, row_relative=False, slack_mult=2.0)
+
+
+def test_pvae_mnist_step_matches_oracle():
+    """Config 2 at reduced width: same weights, same data, same injected (alpha, r)."""
+    from hvae import models as HM
+    from oracle import ref_port as R
+    from oracle.geoopt_min.manifolds.stereographic import math as gmath
+    from oracle.geoopt_min.manifolds.stereographic.manifold import PoincareBall as OBall
+
+    torch.manual_seed(7)
+    B, D, H = 96, 10, 64
+    o32 = R.PvaeMnist(latent_dim=D, hidden_dim=H, c=1.0)
+    x = torch.rand(B, 1, 28, 28).clamp(1e-5, 1 - 1e-5)
+    alpha = torch.randn(1, B, D)
+    alpha = alpha / alpha.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        mu_, sg_ = o32.encode(x)
+        r = R.RiemannianNormal(mu_, sg_, o32.manifold).radius.sample(torch.Size([1]))
+    sd = {k: v.clone() for k, v in o32.state_dict().items()}
+
+    def run_oracle(dtype):
+        m = R.PvaeMnist(latent_dim=D, hidden_dim=H, c=1.0)
+        m.load_state_dict(sd)
+        if dtype == torch.float64:
+            c32 = {id(b): float(b.c) for b in m.modules() if isinstance(b, OBall)}
+            m = m.double()
+            for b in m.modules():
+                if isinstance(b, OBall):
+                    b.isp_c.data = torch.log(torch.expm1(torch.tensor(c32[id(b)], dtype=torch.float64)))
+        with gmath.fp32_semantics(dtype == torch.float64):
+            L = m.loss(x.to(dtype), alpha=alpha.to(dtype), r=r.to(dtype))
+            L["loss_total"].backward()
+        return L, {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+
+    L32, G32 = run_oracle(torch.float32)
+    L64, G64 = run_oracle(torch.float64)
+    model = HM.PvaeMnist(latent_dim=D, hidden_dim=H, c=1.0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("isp_c" in k or k == "manifold.dim" for k in missing), (missing, unexpected)
+    model = model.cuda()
+    L = model.loss(x.cuda(), alpha=alpha.cuda(), r=r.cuda())
+    L["loss_total"].backward()
+    for k in L32:
+        assert_parity(L[k].reshape(1), L32[k].reshape(1), L64[k].reshape(1), what="pvae " + k, rtol=1e-5, atol=1e-4,
+                      row_relative=False, slack_mult=2.0)
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads) == set(G32), set(grads) ^ set(G32)
+    for k in G32:
+        assert_parity(grads[k], G32[k], G64[k], what="pvae grad " + k, rtol=5e-5, atol=1e-6, norm_relative=True, slack_mult=2.0)

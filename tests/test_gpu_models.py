@@ -77,5 +77,5 @@ def test_model_step_matches_reference(golden_models, name, fused):
     grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(grads) == set(g["grads"]), set(grads) ^ set(g["grads"])
     for k, v in g["grads"].items():
-        assert_parity(grads[k], v, g64[k], what="%s grad %s" % (name, k), rtol=2e-5, atol=1e-7, norm_relative=True,
+        assert_parity(grads[k], v, g64[k], what="%s grad %s" % (name, k), rtol=5e-5, atol=1e-7, norm_relative=True,
                       slack_mult=2.0)
