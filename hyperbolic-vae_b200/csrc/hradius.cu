@@ -108,7 +108,7 @@ __device__ __forceinline__ float rad_hpp(float r, float inv2s2, float sc, float 
 }
 
 __global__ void k_hradius_sample(const float* __restrict__ sigma, float* __restrict__ r_out, int64_t S, int64_t B, int dim,
-                                 float c, uint64_t seed, uint64_t offset) {
+                                 float c, uint64_t seed, uint64_t offset, const int64_t* __restrict__ offset_dev) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S * B) return;
     const float s = sigma[i % B];
@@ -116,7 +116,7 @@ __global__ void k_hradius_sample(const float* __restrict__ sigma, float* __restr
     const float n = (float)(dim - 1);
     const float inv2s2 = 0.5f / (s * s);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint64_t cnt = offset + (uint64_t)i;
+    const uint64_t cnt = offset + (offset_dev ? (uint64_t)__ldg(offset_dev) : 0ull) + (uint64_t)i;
     uint32_t iter = 0;
     if (dim == 1) {  // half normal
         const uint4 rn = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), 0u, 0u), key);
@@ -304,12 +304,13 @@ extern "C" int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, flo
 }
 
 extern "C" int hvae_hradius_sample_f32(const float* sigma, float* r, int64_t S, int64_t B, int64_t dim, float c,
-                                       uint64_t seed, uint64_t offset, void* stream) {
+                                       uint64_t seed, uint64_t offset, const int64_t* offset_dev, void* stream) {
     if (S < 0 || B < 0 || dim < 1 || dim > kMaxRadiusDim) return HVAE_ESHAPE;
     if (S == 0 || B == 0) return HVAE_OK;
     if (!sigma || !r) return HVAE_EARG;
     const int64_t n = S * B;
-    k_hradius_sample<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sigma, r, S, B, (int)dim, c, seed, offset);
+    k_hradius_sample<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sigma, r, S, B, (int)dim, c, seed, offset,
+                                                                                     offset_dev);
     return check_launch();
 }
 

@@ -64,9 +64,12 @@ class HyperbolicRadius(torch.distributions.Distribution):
         self.log_normalizer = ops.hradius_lognorm(scale, self.dim, self.c_value)
         super().__init__(self.scale.size(), validate_args=False)
 
+    philox_counter: Tensor = None  # optional int64 device scalar: graph-safe noise counter shared by all instances
+
     def sample(self, sample_shape=torch.Size(), seed=None, offset=None) -> Tensor:
         S = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
-        r = ops.hradius_sample(self.scale, S, self.dim, self.c_value, seed=seed, offset=offset)
+        r = ops.hradius_sample(self.scale, S, self.dim, self.c_value, seed=seed, offset=offset,
+                               offset_dev=HyperbolicRadius.philox_counter)
         return r.view(S, *self.scale.shape)
 
     def rsample(self, sample_shape=torch.Size(), r: Tensor = None) -> Tensor:

@@ -665,8 +665,10 @@ def hradius_lognorm(sigma: Tensor, dim: int, c: float) -> Tensor:
 _philox_offset = 0
 
 
-def hradius_sample(sigma: Tensor, S: int, dim: int, c: float, seed: Optional[int] = None, offset: Optional[int] = None) -> Tensor:
-    """r (S,B) ~ rho(.; sigma_b) by in-kernel rejection sampling (Philox4x32-10).  No gradient."""
+def hradius_sample(sigma: Tensor, S: int, dim: int, c: float, seed: Optional[int] = None, offset: Optional[int] = None,
+                   offset_dev: Optional[Tensor] = None) -> Tensor:
+    """r (S,B) ~ rho(.; sigma_b) by in-kernel rejection sampling (Philox4x32-10).  No gradient.
+    offset_dev: optional int64 device scalar added to the counter and advanced in-stream (CUDA-graph safe)."""
     global _philox_offset
     C.require_cuda(sigma)
     sig = _c(sigma.detach()).view(-1)
@@ -674,10 +676,15 @@ def hradius_sample(sigma: Tensor, S: int, dim: int, c: float, seed: Optional[int
     if seed is None:
         seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
     if offset is None:
-        offset = _philox_offset
-        _philox_offset += S * B
+        if offset_dev is not None:
+            offset = 0
+        else:
+            offset = _philox_offset
+            _philox_offset += S * B
     r = sig.new_empty(S, B)
-    C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r), S, B, dim, c, seed, offset, C.stream())
+    C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r), S, B, dim, c, seed, offset, C.ptr(offset_dev), C.stream())
+    if offset_dev is not None:
+        offset_dev.add_(S * B)
     return r
 
 

@@ -131,9 +131,11 @@ int hvae_mobius_matvec_bwd_f32(const float* x, const float* M, const float* mx, 
  * sigma: (B,) per-row scale (already clamped to [0.1,7] by the caller as RiemannianNormal does). */
 int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, float* dlogZ_dsigma, int64_t B, int64_t dim,
                                  float c, void* stream);
-/* r: (S,B) samples by rejection from a tangent hull, Philox4x32-10 stream (seed, offset) */
+/* r: (S,B) samples by rejection from a tangent hull, Philox4x32-10 stream (seed, counter).  Sample i uses
+ * counter offset + (offset_dev ? *offset_dev : 0) + i; the device-side word lets a captured CUDA graph draw
+ * fresh noise on every replay (the caller bumps it in-graph). */
 int hvae_hradius_sample_f32(const float* sigma, float* r, int64_t S, int64_t B, int64_t dim, float c,
-                            uint64_t seed, uint64_t offset, void* stream);
+                            uint64_t seed, uint64_t offset, const int64_t* offset_dev, void* stream);
 /* implicit reparameterisation: dr/dsigma = -(dF/dsigma)/(dF/dr) at the given (r, sigma); cdf optional */
 int hvae_hradius_rgrad_f32(const float* sigma, const float* r, float* dr_dsigma, float* cdf,
                            int64_t S, int64_t B, int64_t dim, float c, void* stream);
