@@ -296,6 +296,13 @@ def run_ours(args, wl):
         e.record()
         barrier()
         e2e_s = s.elapsed_time(e) * 1e-3
+        # nvidia-smi takes ~0.1 s per sample: keep the same step running (untimed) until the clock record
+        # under load has a handful of samples
+        t_end = time.perf_counter() + 3.0
+        while len(clk.samples) < 6 and time.perf_counter() < t_end:
+            for _ in range(20):
+                ts.run()
+            torch.cuda.synchronize()
     loss = float(loss_host)
     t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
     if world > 1:

@@ -144,10 +144,9 @@ __device__ __forceinline__ GyroPairGrad gyro_pair_bwd(float g, float px, float x
 // smem: xs[TB][D4] (row-major, broadcast reads), ps[D4][TJ] / as[D4][TJ] (plane-minor, conflict-free).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGyroThreads = 128;
-constexpr int kGyroTB = 64;   // rows per CTA
 constexpr int kGyroRB = 8;    // rows per register block
 
-template <int D4, bool kAliased>
+template <int D4, bool kAliased, int kGyroTB /* rows per CTA */>
 __global__ void __launch_bounds__(kGyroThreads)
 k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
            const float* __restrict__ bias, float* __restrict__ out, int B, int D, int P_, GyroParams prm) {
@@ -239,7 +238,8 @@ constexpr int kGyroBxTJ = 32;        // planes per smem stage
 template <int D4, bool kAliased>
 __global__ void __launch_bounds__(kGyroBxThreads)
 k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
-             const float* __restrict__ gout, float* __restrict__ gx, int B, int D, int P_, GyroParams prm) {
+             const float* __restrict__ gout, float* __restrict__ gx, int B, int D, int P_, int planes_per_chunk,
+             GyroParams prm) {
     constexpr int TJ = kGyroBxTJ;
     __shared__ float ps[TJ][D4];
     __shared__ float as[kAliased ? 1 : TJ][D4];
@@ -256,17 +256,21 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
         x2 = fmaf(xr[d], xr[d], x2);
         acc[d] = 0.0f;
     }
-    for (int j0 = 0; j0 < P_; j0 += TJ) {
+    // this CTA's slice of the planes; gx points at this chunk's (B,D) slab (the final gx when there is one chunk)
+    const int jlo = blockIdx.y * planes_per_chunk;
+    const int jhi = min(P_, jlo + planes_per_chunk);
+    gx += (int64_t)blockIdx.y * B * D;
+    for (int j0 = jlo; j0 < jhi; j0 += TJ) {
         __syncthreads();
         for (int i = tid; i < TJ * D4; i += kGyroBxThreads) {
             const int jj = i / D4, d = i - jj * D4;
-            const bool ok = (j0 + jj) < P_ && d < D;
+            const bool ok = (j0 + jj) < jhi && d < D;
             ps[jj][d] = ok ? __ldg(p + (int64_t)(j0 + jj) * D + d) : 0.0f;
             if (!kAliased) as[jj][d] = ok ? __ldg(a + (int64_t)(j0 + jj) * D + d) : 0.0f;
         }
         for (int i = tid; i < kGyroBxThreads * TJ; i += kGyroBxThreads) {
             const int rr = i / TJ, jj = i - rr * TJ;
-            gs[rr][jj] = ((b0 + rr) < B && (j0 + jj) < P_) ? __ldg(gout + (int64_t)(b0 + rr) * P_ + j0 + jj) : 0.0f;
+            gs[rr][jj] = ((b0 + rr) < B && (j0 + jj) < jhi) ? __ldg(gout + (int64_t)(b0 + rr) * P_ + j0 + jj) : 0.0f;
         }
         __syncthreads();
         if (tid < TJ) {
@@ -281,7 +285,7 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
             pst[tid][0] = p2; pst[tid][1] = pa; pst[tid][2] = sqrtf(a2);
         }
         __syncthreads();
-        const int jn = min(TJ, P_ - j0);
+        const int jn = min(TJ, jhi - j0);
         for (int jj = 0; jj < jn; ++jj) {
             GyroDiff df;
             df.e = df.q = df.qa = 0.0f;
@@ -443,6 +447,16 @@ inline int gyro_slabs(int64_t B, int64_t P) {
     return (int)want;
 }
 
+// gx kernel: how many plane-chunks (gridDim.y) so that ~4 CTAs/SM are in flight
+inline int gyro_x_chunks(int64_t B, int64_t P) {
+    const int64_t rb = (B + kGyroBxThreads - 1) / kGyroBxThreads;
+    int64_t want = (4 * kNumSMs + rb - 1) / rb;
+    const int64_t maxc = (P + kGyroBxTJ - 1) / kGyroBxTJ;
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
 inline GyroParams make_gyro_params(float c, uint32_t flags) {
     const Ball b = make_ball(c);
     GyroParams p;
@@ -450,20 +464,29 @@ inline GyroParams make_gyro_params(float c, uint32_t flags) {
     return p;
 }
 
+template <int D4, bool kAliased, int TB>
+int gyro_fwd_launch_tb(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B, int64_t D,
+                       int64_t P, const GyroParams& prm, cudaStream_t s) {
+    dim3 grid((unsigned)((P + kGyroThreads - 1) / kGyroThreads), (unsigned)((B + TB - 1) / TB));
+    const size_t smem = sizeof(float) * ((size_t)TB * D4 + TB + (size_t)D4 * kGyroThreads * (kAliased ? 1 : 2));
+    auto kern = k_gyro_fwd<D4, kAliased, TB>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kGyroThreads, smem, s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, prm);
+    return check_launch();
+}
+
 template <int D4>
 int gyro_fwd_launch(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B, int64_t D,
                     int64_t P, const GyroParams& prm, cudaStream_t s) {
     const bool aliased = (a == p);
-    dim3 grid((unsigned)((P + kGyroThreads - 1) / kGyroThreads), (unsigned)((B + kGyroTB - 1) / kGyroTB));
-    const size_t smem = sizeof(float) * ((size_t)kGyroTB * D4 + kGyroTB + (size_t)D4 * kGyroThreads * (aliased ? 1 : 2));
-    if (aliased) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gyro_fwd<D4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_gyro_fwd<D4, true><<<grid, kGyroThreads, smem, s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, prm);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_gyro_fwd<D4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_gyro_fwd<D4, false><<<grid, kGyroThreads, smem, s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, prm);
-    }
-    return check_launch();
+    // rows per CTA: 64 when that already gives >= 4 waves of CTAs, else 16 (the epilogue is a long dependent
+    // chain of div/sqrt/log: small problems need many resident warps, not big tiles)
+    const int64_t ctas64 = ((P + kGyroThreads - 1) / kGyroThreads) * ((B + 63) / 64);
+    const bool big = ctas64 >= 4 * (int64_t)kNumSMs * 4;
+    if (aliased) return big ? gyro_fwd_launch_tb<D4, true, 64>(x, p, a, bias, out, B, D, P, prm, s)
+                            : gyro_fwd_launch_tb<D4, true, 16>(x, p, a, bias, out, B, D, P, prm, s);
+    return big ? gyro_fwd_launch_tb<D4, false, 64>(x, p, a, bias, out, B, D, P, prm, s)
+               : gyro_fwd_launch_tb<D4, false, 16>(x, p, a, bias, out, B, D, P, prm, s);
 }
 
 template <int D4>
@@ -474,11 +497,17 @@ int gyro_bwd_launch(const float* x, const float* p, const float* a, const float*
     const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBpTB - 1) / kGyroBpTB * kGyroBpTB);
     float* wp = ws;
     float* wa = wp + (int64_t)slabs * P * D;
-    float* wb = wa + (aliased ? 0 : (int64_t)slabs * P * D);
+    float* wb = wa + (int64_t)slabs * P * D;
+    float* wx = wb + (int64_t)slabs * P;
     if (gx) {
-        dim3 grid((unsigned)((B + kGyroBxThreads - 1) / kGyroBxThreads));
-        if (aliased) k_gyro_bwd_x<D4, true><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, gx, (int)B, (int)D, (int)P, prm);
-        else         k_gyro_bwd_x<D4, false><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, gx, (int)B, (int)D, (int)P, prm);
+        const int chunks = gyro_x_chunks(B, P);
+        const int ppc = (int)((((P + chunks - 1) / chunks) + kGyroBxTJ - 1) / kGyroBxTJ * kGyroBxTJ);
+        const int nch = (int)((P + ppc - 1) / ppc);
+        float* dst = nch == 1 ? gx : wx;
+        dim3 grid((unsigned)((B + kGyroBxThreads - 1) / kGyroBxThreads), (unsigned)nch);
+        if (aliased) k_gyro_bwd_x<D4, true><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, (int)B, (int)D, (int)P, ppc, prm);
+        else         k_gyro_bwd_x<D4, false><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, (int)B, (int)D, (int)P, ppc, prm);
+        if (nch > 1) k_gyro_reduce_slabs<<<(unsigned)((B * D + 255) / 256), 256, 0, s>>>(wx, gx, B * D, nch);
     }
     if (gp || ga || gbias) {
         dim3 grid((unsigned)((P + kGyroBpThreads - 1) / kGyroBpThreads), (unsigned)slabs);
@@ -515,7 +544,7 @@ extern "C" int hvae_gyroplane_fwd_f32(const float* x, const float* p, const floa
 extern "C" size_t hvae_gyroplane_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P) {
     if (B <= 0 || P <= 0 || D <= 0) return 0;
     const int slabs = gyro_slabs(B, P);
-    return sizeof(float) * ((size_t)slabs * P * D * 2 + (size_t)slabs * P);
+    return sizeof(float) * ((size_t)slabs * P * D * 2 + (size_t)slabs * P + (size_t)gyro_x_chunks(B, P) * B * D);
 }
 
 extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout, float* gx,

@@ -31,7 +31,7 @@ def _series(scale: torch.Tensor, c: torch.Tensor, dim: int):
     return k, signs, logbinom, b
 
 
-def log_normalizer(scale: torch.Tensor, c: torch.Tensor, dim: int) -> torch.Tensor:
+def _log_normalizer_value(scale: torch.Tensor, c: torch.Tensor, dim: int) -> torch.Tensor:
     s = scale.double().unsqueeze(-1)
     cd = c.double()
     _, signs, logbinom, b = _series(scale, c, dim)
@@ -39,6 +39,36 @@ def log_normalizer(scale: torch.Tensor, c: torch.Tensor, dim: int) -> torch.Tens
     lse = log_sum_exp_signs(v, signs, dim=-1)
     n = dim - 1
     return 0.5 * (math.log(math.pi) - math.log(2)) + scale.double().log() - n * (0.5 * cd.log() + math.log(2)) + lse
+
+
+class _LogNormalizer(Function):
+    """pvae wraps logZ in a custom Function with a hand-written sigma-gradient, because autograd through
+    log1p(erf(x)) is NaN once erf saturates at -1.  d logZ/d s = 1/s + sum_k (-1)^k [b_k^2 s E_k + C_k b_k sqrt(2/pi)]
+    / sum_k (-1)^k E_k with E_k = C_k e^{b_k^2 s^2/2}(1 + erf(b_k s/sqrt2))  (no gradient to c, as in pvae)."""
+
+    @staticmethod
+    def forward(ctx, scale, c, dim):
+        ctx.save_for_backward(scale.detach())
+        ctx.c, ctx.dim = c.detach(), dim
+        return _log_normalizer_value(scale.detach(), c.detach(), dim).to(torch.float64)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (scale,) = ctx.saved_tensors
+        s = scale.double().unsqueeze(-1)
+        _, signs, logbinom, b = _series(scale, ctx.c, ctx.dim)
+        v = logbinom + (b * s).pow(2) / 2 + torch.log1p(torch.erf(b * s / SQRT2))
+        m = v.max(dim=-1, keepdim=True)[0]
+        E = torch.exp(v - m)
+        num = (signs * (b * b * s * E + torch.exp(logbinom - m) * b * math.sqrt(2 / math.pi))).sum(-1)
+        den = (signs * E).sum(-1)
+        g = 1.0 / scale.double() + num / den
+        return (grad * g).to(scale.dtype), None, None
+
+
+def log_normalizer(scale: torch.Tensor, c: torch.Tensor, dim: int) -> torch.Tensor:
+    """float64 logZ(scale) with pvae's analytic sigma-gradient."""
+    return _LogNormalizer.apply(scale, c, dim)
 
 
 def cdf_r(value: torch.Tensor, scale: torch.Tensor, c: torch.Tensor, dim: int) -> torch.Tensor:
