@@ -237,7 +237,9 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     torch.backends.cuda.matmul.allow_tf32 = False  # fp32 trunk: parity contract is 1e-5 against the fp32 reference
     torch.backends.cudnn.allow_tf32 = False
     C.lib()
@@ -296,11 +298,10 @@ def run_ours(args, wl):
         e.record()
         barrier()
         e2e_s = s.elapsed_time(e) * 1e-3
-        # nvidia-smi takes ~0.1 s per sample: keep the same step running (untimed) until the clock record
-        # under load has a handful of samples
-        t_end = time.perf_counter() + 3.0
-        while len(clk.samples) < 6 and time.perf_counter() < t_end:
-            for _ in range(20):
+        # nvidia-smi takes ~0.1 s per sample: keep the same step running (untimed, the SAME count on every
+        # rank — each step holds a collective) so the clock record under load has a handful of samples
+        for _ in range(8):
+            for _ in range(50):
                 ts.run()
             torch.cuda.synchronize()
     loss = float(loss_host)
