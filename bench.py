@@ -224,6 +224,12 @@ def kernel_roofline(wl, device, pk, pk_kind):
     return roof, others, big
 
 
+def dbg(msg):
+    if os.environ.get("HVAE_BENCH_DEBUG"):
+        sys.stderr.write("[bench r%s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter() % 1000, msg))
+        sys.stderr.flush()
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
 
@@ -243,6 +249,7 @@ def run_ours(args, wl):
     torch.backends.cuda.matmul.allow_tf32 = False  # fp32 trunk: parity contract is 1e-5 against the fp32 reference
     torch.backends.cudnn.allow_tf32 = False
     C.lib()
+    dbg('init done')
 
     from hvae.train import TrainStep
 
@@ -257,9 +264,11 @@ def run_ours(args, wl):
     n0 = C.launch_count
     ts = TrainStep(model, x_dev, average_grads=False, use_graph=False)
     launches_per_step = (C.launch_count - n0) // 3  # TrainStep runs 3 eager warm-up steps
+    dbg('eager warmup done')
     if not args.no_graph:
         ts._capture()
     graph_on = ts.graph is not None
+    dbg('capture done graph=%s' % graph_on)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
@@ -283,6 +292,7 @@ def run_ours(args, wl):
             evs.append((s, e))
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        dbg('timed loop done')
         dev_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
 
         # ---- e2e: host batch -> pinned H2D -> TrainStep.run (public API) -> D2H loss, every step ------------
@@ -298,6 +308,7 @@ def run_ours(args, wl):
         e.record()
         barrier()
         e2e_s = s.elapsed_time(e) * 1e-3
+        dbg('e2e done')
         # nvidia-smi takes ~0.1 s per sample: keep the same step running (untimed, the SAME count on every
         # rank — each step holds a collective) so the clock record under load has a handful of samples
         for _ in range(8):
@@ -305,11 +316,13 @@ def run_ours(args, wl):
                 ts.run()
             torch.cuda.synchronize()
     loss = float(loss_host)
+    dbg('postroll done')
     t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, e2e_s = t.tolist()
 
+    dbg('allreduce timing done')
     if rank == 0:
         pk, pk_kind = peaks()
         roof, others, big = kernel_roofline(wl, device, pk, pk_kind)
@@ -339,8 +352,14 @@ def run_ours(args, wl):
         }
         print(json.dumps(line))
     if world > 1:
+        # Teardown: the captured graph holds NCCL work; destroying the process group under it can hang, so
+        # synchronize, drop the graph, and leave without the collective teardown.
         dist.barrier(device_ids=[local])
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        ts.graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
