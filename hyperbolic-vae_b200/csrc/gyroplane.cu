@@ -231,21 +231,33 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
     }
 }
 
-// gx: thread = one row, planes streamed from smem (broadcast); upstream-grad tile staged through smem.
+// ---------------------------------------------------------------------------------------------------
+// backward.  The pair math (forward recompute + scalar backward, ~400 instructions) runs ONCE per (row, plane):
+//   G1  k_gyro_bwd_pairs : thread = one row of a 128-row block, planes of one chunk streamed through smem;
+//                          accumulates gx in registers, writes the coefficient matrices
+//                            CP[b][j] = dL/d<p_j,x_b> (+ dL/d<a_j,x_b> when a aliases p),  CA[b][j] = dL/d<a_j,x_b>
+//                          and per-(row-block, plane) sums of the scalar terms (d|p|^2, d<p,a>, d|a|, g).
+//   G2  k_gyro_bwd_planes: thread = one plane; gp_j = sum_b CP[b][j] x_b + (scalar terms) — a skinny GEMM over a
+//                          slab of rows, partials per slab, then k_gyro_reduce_slabs (deterministic, no atomics).
+// ---------------------------------------------------------------------------------------------------
 constexpr int kGyroBxThreads = 128;  // rows per CTA
 constexpr int kGyroBxTJ = 32;        // planes per smem stage
 
 template <int D4, bool kAliased>
 __global__ void __launch_bounds__(kGyroBxThreads)
-k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
-             const float* __restrict__ gout, float* __restrict__ gx, int B, int D, int P_, int planes_per_chunk,
-             GyroParams prm) {
-    constexpr int TJ = kGyroBxTJ;
+k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
+                 const float* __restrict__ gout, float* __restrict__ gx, float* __restrict__ CP, float* __restrict__ CA,
+                 float* __restrict__ wsum /* [rowblocks][P][4] */, int B, int D, int P_, int planes_per_chunk,
+                 GyroParams prm) {
+    constexpr int TJ = (D4 >= 64) ? 16 : kGyroBxTJ;  // keep the static smem under 48 KB at D4 = 64
     __shared__ float ps[TJ][D4];
     __shared__ float as[kAliased ? 1 : TJ][D4];
     __shared__ float pst[TJ][4];                      // p2, pa, an_raw
-    __shared__ float gs[kGyroBxThreads][TJ + 1];      // upstream grad tile [row][plane]
+    __shared__ float gs[kGyroBxThreads][TJ + 1];      // upstream grad tile [row][plane]; reused for CP
+    __shared__ float cs[kAliased ? 1 : kGyroBxThreads][TJ + 1];  // CA tile
+    __shared__ float psum[4][TJ][4];                  // per-warp partial sums of the scalar terms
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * kGyroBxThreads;
     const int b = b0 + tid;
     float xr[D4], acc[D4];
@@ -256,10 +268,9 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
         x2 = fmaf(xr[d], xr[d], x2);
         acc[d] = 0.0f;
     }
-    // this CTA's slice of the planes; gx points at this chunk's (B,D) slab (the final gx when there is one chunk)
     const int jlo = blockIdx.y * planes_per_chunk;
     const int jhi = min(P_, jlo + planes_per_chunk);
-    gx += (int64_t)blockIdx.y * B * D;
+    gx += (int64_t)blockIdx.y * B * D;  // this chunk's (B,D) slab (the final gx when there is one chunk)
     for (int j0 = jlo; j0 < jhi; j0 += TJ) {
         __syncthreads();
         for (int i = tid; i < TJ * D4; i += kGyroBxThreads) {
@@ -304,9 +315,11 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
             const float p2 = pst[jj][0], pa = pst[jj][1], an_raw = pst[jj][2];
             const float px = p2 - df.q;
             const float xa = kAliased ? px : pa - df.qa;
+            const float g = gs[tid][jj];
             GyroPairCtx k;
             gyro_pair_fwd(px, xa, x2, p2, pa, an_raw, prm, k, &df);
-            const GyroPairGrad gr = gyro_pair_bwd(gs[tid][jj], px, xa, x2, p2, pa, an_raw, prm, k);
+            GyroPairGrad gr = gyro_pair_bwd(g, px, xa, x2, p2, pa, an_raw, prm, k);
+            if (b >= B) { gr.dpx = gr.dxa = gr.dx2 = gr.dp2 = gr.dpa = gr.dan = 0.0f; }
             sdx2 += gr.dx2;
             const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
 #pragma unroll
@@ -320,6 +333,31 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
                     acc[d + 2] = fmaf(gr.dxa, av.z, acc[d + 2]); acc[d + 3] = fmaf(gr.dxa, av.w, acc[d + 3]);
                 }
             }
+            gs[tid][jj] = cp;                       // own element: no hazard
+            if (!kAliased) cs[tid][jj] = gr.dxa;
+            // per-plane sums over this warp's 32 rows
+            float s0 = gr.dp2, s1 = gr.dpa, s2 = gr.dan, s3 = (b < B) ? g : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+            }
+            if (lane == 0) { psum[warp][jj][0] = s0; psum[warp][jj][1] = s1; psum[warp][jj][2] = s2; psum[warp][jj][3] = s3; }
+        }
+        __syncthreads();
+        // coalesced write-out of the coefficient tiles and the per-row-block sums
+        for (int i = tid; i < kGyroBxThreads * TJ; i += kGyroBxThreads) {
+            const int rr = i / TJ, jj = i - rr * TJ;
+            if ((b0 + rr) < B && jj < jn) {
+                CP[(int64_t)(b0 + rr) * P_ + j0 + jj] = gs[rr][jj];
+                if (!kAliased) CA[(int64_t)(b0 + rr) * P_ + j0 + jj] = cs[rr][jj];
+            }
+        }
+        if (tid < jn * 4) {
+            const int jj = tid >> 2, q = tid & 3;
+            wsum[((int64_t)blockIdx.x * P_ + j0 + jj) * 4 + q] = psum[0][jj][q] + psum[1][jj][q] + psum[2][jj][q] + psum[3][jj][q];
         }
     }
     if (b < B) {
@@ -329,38 +367,28 @@ k_gyro_bwd_x(const float* __restrict__ x, const float* __restrict__ p, const flo
     }
 }
 
-// gp / ga / gbias: thread = one plane; a CTA covers TJ planes x a slab of rows; partial sums go to the
-// workspace [slab][P][D] (+[slab][P] for bias) and a second kernel reduces over slabs (deterministic).
 constexpr int kGyroBpThreads = 128;
 constexpr int kGyroBpTB = 32;  // rows per smem stage
 
 template <int D4, bool kAliased>
 __global__ void __launch_bounds__(kGyroBpThreads)
-k_gyro_bwd_p(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
-             const float* __restrict__ gout, float* __restrict__ wp, float* __restrict__ wa, float* __restrict__ wb,
-             int B, int D, int P_, int rows_per_slab, GyroParams prm) {
+k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
+                  const float* __restrict__ CP, const float* __restrict__ CA, const float* __restrict__ wsum,
+                  float* __restrict__ wp, float* __restrict__ wa, float* __restrict__ wb, int B, int D, int P_,
+                  int rows_per_slab /* multiple of 128 */) {
     constexpr int TJ = kGyroBpThreads;
     __shared__ float xs[kGyroBpTB][D4];
-    __shared__ float xs2[kGyroBpTB];
     const int tid = threadIdx.x;
     const int j = blockIdx.x * TJ + tid;
     const int slab = blockIdx.y;
     const int bs = slab * rows_per_slab;
     const int be = min(B, bs + rows_per_slab);
-    float pr[D4], ar[kAliased ? 1 : D4], accp[D4], acca[kAliased ? 1 : D4];
-    float p2 = 0.0f, pa = 0.0f, a2 = 0.0f;
+    float accp[D4], acca[kAliased ? 1 : D4];
 #pragma unroll
     for (int d = 0; d < D4; ++d) {
-        pr[d] = (j < P_ && d < D) ? __ldg(p + (int64_t)j * D + d) : 0.0f;
-        const float av = kAliased ? pr[d] : ((j < P_ && d < D) ? __ldg(a + (int64_t)j * D + d) : 0.0f);
-        if (!kAliased) { ar[d] = av; acca[d] = 0.0f; }
-        p2 = fmaf(pr[d], pr[d], p2);
-        pa = fmaf(pr[d], av, pa);
-        a2 = fmaf(av, av, a2);
         accp[d] = 0.0f;
+        if (!kAliased) acca[d] = 0.0f;
     }
-    const float an_raw = sqrtf(a2);
-    float sdp2 = 0.0f, sdpa = 0.0f, sdan = 0.0f, sg = 0.0f;
     for (int b0 = bs; b0 < be; b0 += kGyroBpTB) {
         __syncthreads();
         for (int i = tid; i < kGyroBpTB * D4; i += kGyroBpThreads) {
@@ -368,61 +396,51 @@ k_gyro_bwd_p(const float* __restrict__ x, const float* __restrict__ p, const flo
             xs[bb][d] = ((b0 + bb) < be && d < D) ? __ldg(x + (int64_t)(b0 + bb) * D + d) : 0.0f;
         }
         __syncthreads();
-        if (tid < kGyroBpTB) {
-            float s = 0.0f;
-            for (int d = 0; d < D4; ++d) s = fmaf(xs[tid][d], xs[tid][d], s);
-            xs2[tid] = s;
-        }
-        __syncthreads();
         const int bn = min(kGyroBpTB, be - b0);
         if (j < P_) {
+#pragma unroll 4
             for (int bb = 0; bb < bn; ++bb) {
-                GyroDiff df;
-                df.e = df.q = df.qa = 0.0f;
-#pragma unroll
-                for (int d = 0; d < D4; d += 4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][d]);
-                    const float t0 = pr[d] - xv.x, t1 = pr[d + 1] - xv.y, t2 = pr[d + 2] - xv.z, t3 = pr[d + 3] - xv.w;
-                    df.e = fmaf(t0, t0, fmaf(t1, t1, fmaf(t2, t2, fmaf(t3, t3, df.e))));
-                    df.q = fmaf(pr[d], t0, fmaf(pr[d + 1], t1, fmaf(pr[d + 2], t2, fmaf(pr[d + 3], t3, df.q))));
-                    if (!kAliased)
-                        df.qa = fmaf(ar[d], t0, fmaf(ar[d + 1], t1, fmaf(ar[d + 2], t2, fmaf(ar[d + 3], t3, df.qa))));
-                }
-                if (kAliased) df.qa = df.q;
-                const float px = p2 - df.q;
-                const float xa = kAliased ? px : pa - df.qa;
-                const float g = __ldg(gout + (int64_t)(b0 + bb) * P_ + j);  // coalesced across the CTA's planes
-                GyroPairCtx k;
-                gyro_pair_fwd(px, xa, xs2[bb], p2, pa, an_raw, prm, k, &df);
-                const GyroPairGrad gr = gyro_pair_bwd(g, px, xa, xs2[bb], p2, pa, an_raw, prm, k);
-                sdp2 += gr.dp2; sdpa += gr.dpa; sdan += gr.dan; sg += g;
-                const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
+                const float cp = __ldg(CP + (int64_t)(b0 + bb) * P_ + j);  // coalesced across the CTA's planes
+                const float ca = kAliased ? 0.0f : __ldg(CA + (int64_t)(b0 + bb) * P_ + j);
 #pragma unroll
                 for (int d = 0; d < D4; d += 4) {
                     const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][d]);
                     accp[d] = fmaf(cp, xv.x, accp[d]); accp[d + 1] = fmaf(cp, xv.y, accp[d + 1]);
                     accp[d + 2] = fmaf(cp, xv.z, accp[d + 2]); accp[d + 3] = fmaf(cp, xv.w, accp[d + 3]);
                     if (!kAliased) {
-                        acca[d] = fmaf(gr.dxa, xv.x, acca[d]); acca[d + 1] = fmaf(gr.dxa, xv.y, acca[d + 1]);
-                        acca[d + 2] = fmaf(gr.dxa, xv.z, acca[d + 2]); acca[d + 3] = fmaf(gr.dxa, xv.w, acca[d + 3]);
+                        acca[d] = fmaf(ca, xv.x, acca[d]); acca[d + 1] = fmaf(ca, xv.y, acca[d + 1]);
+                        acca[d + 2] = fmaf(ca, xv.z, acca[d + 2]); acca[d + 3] = fmaf(ca, xv.w, acca[d + 3]);
                     }
                 }
             }
         }
     }
     if (j < P_) {
+        float sdp2 = 0.0f, sdpa = 0.0f, sdan = 0.0f, sg = 0.0f;
+        for (int rb = bs / kGyroBxThreads; rb * kGyroBxThreads < be; ++rb) {
+            const float4 w = *reinterpret_cast<const float4*>(wsum + ((int64_t)rb * P_ + j) * 4);
+            sdp2 += w.x; sdpa += w.y; sdan += w.z; sg += w.w;
+        }
+        float a2 = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float av = __ldg((kAliased ? p : a) + (int64_t)j * D + d);
+            a2 = fmaf(av, av, a2);
+        }
+        const float an_raw = sqrtf(a2);
         const float inv_an = an_raw > 0.0f ? 1.0f / an_raw : 0.0f;
         float* wpj = wp + ((int64_t)slab * P_ + j) * D;
         float* waj = kAliased ? nullptr : wa + ((int64_t)slab * P_ + j) * D;
 #pragma unroll
         for (int d = 0; d < D4; ++d) {
             if (d < D) {
+                const float pv = __ldg(p + (int64_t)j * D + d);
                 if (kAliased) {
-                    // a == p: pa = p2 and an = |p| all flow into the single parameter
-                    wpj[d] = accp[d] + (2.0f * sdp2 + 2.0f * sdpa + sdan * inv_an) * pr[d];
+                    // a == p: <p,a> = |p|^2 and |a| = |p| all flow into the single parameter
+                    wpj[d] = accp[d] + (2.0f * sdp2 + 2.0f * sdpa + sdan * inv_an) * pv;
                 } else {
-                    wpj[d] = accp[d] + 2.0f * sdp2 * pr[d] + sdpa * ar[d];
-                    waj[d] = acca[d] + sdpa * pr[d] + sdan * inv_an * ar[d];
+                    const float av = __ldg(a + (int64_t)j * D + d);
+                    wpj[d] = accp[d] + 2.0f * sdp2 * pv + sdpa * av;
+                    waj[d] = acca[d] + sdpa * pv + sdan * inv_an * av;
                 }
             }
         }
@@ -438,16 +456,17 @@ __global__ void k_gyro_reduce_slabs(const float* __restrict__ w, float* __restri
     out[i] = s;
 }
 
+// G2 slabs of rows (multiples of the 128-row blocks of G1)
 inline int gyro_slabs(int64_t B, int64_t P) {
     const int64_t jb = (P + kGyroBpThreads - 1) / kGyroBpThreads;
-    int64_t want = (2 * kNumSMs + jb - 1) / jb;            // ~2 CTAs per SM in flight
-    const int64_t maxs = (B + kGyroBpTB - 1) / kGyroBpTB;   // at least one stage of rows per slab
+    int64_t want = (4 * kNumSMs + jb - 1) / jb;
+    const int64_t maxs = (B + kGyroBxThreads - 1) / kGyroBxThreads;
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     return (int)want;
 }
 
-// gx kernel: how many plane-chunks (gridDim.y) so that ~4 CTAs/SM are in flight
+// G1: how many plane-chunks (gridDim.y) so that ~4 CTAs/SM are in flight
 inline int gyro_x_chunks(int64_t B, int64_t P) {
     const int64_t rb = (B + kGyroBxThreads - 1) / kGyroBxThreads;
     int64_t want = (4 * kNumSMs + rb - 1) / rb;
@@ -455,6 +474,27 @@ inline int gyro_x_chunks(int64_t B, int64_t P) {
     if (want > maxc) want = maxc;
     if (want < 1) want = 1;
     return (int)want;
+}
+
+struct GyroWs {
+    size_t cp, ca, wsum, wx, wp, wa, wb, total;  // offsets in floats
+};
+
+inline GyroWs gyro_ws_layout(int64_t B, int64_t D, int64_t P) {
+    GyroWs w;
+    const size_t rbs = (size_t)((B + kGyroBxThreads - 1) / kGyroBxThreads);
+    const size_t slabs = (size_t)gyro_slabs(B, P), chunks = (size_t)gyro_x_chunks(B, P);
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 3) / 4 * 4; return at; };
+    w.cp = take((size_t)B * P);
+    w.ca = take((size_t)B * P);
+    w.wsum = take(rbs * P * 4);
+    w.wx = take(chunks * B * D);
+    w.wp = take(slabs * P * D);
+    w.wa = take(slabs * P * D);
+    w.wb = take(slabs * P);
+    w.total = o;
+    return w;
 }
 
 inline GyroParams make_gyro_params(float c, uint32_t flags) {
@@ -493,30 +533,30 @@ template <int D4>
 int gyro_bwd_launch(const float* x, const float* p, const float* a, const float* gout, float* gx, float* gp, float* ga,
                     float* gbias, int64_t B, int64_t D, int64_t P, const GyroParams& prm, float* ws, cudaStream_t s) {
     const bool aliased = (a == p);
-    const int slabs = gyro_slabs(B, P);
-    const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBpTB - 1) / kGyroBpTB * kGyroBpTB);
-    float* wp = ws;
-    float* wa = wp + (int64_t)slabs * P * D;
-    float* wb = wa + (int64_t)slabs * P * D;
-    float* wx = wb + (int64_t)slabs * P;
-    if (gx) {
-        const int chunks = gyro_x_chunks(B, P);
-        const int ppc = (int)((((P + chunks - 1) / chunks) + kGyroBxTJ - 1) / kGyroBxTJ * kGyroBxTJ);
-        const int nch = (int)((P + ppc - 1) / ppc);
-        float* dst = nch == 1 ? gx : wx;
+    const GyroWs L = gyro_ws_layout(B, D, P);
+    float *CP = ws + L.cp, *CA = ws + L.ca, *wsum = ws + L.wsum, *wx = ws + L.wx, *wp = ws + L.wp, *wa = ws + L.wa,
+          *wb = ws + L.wb;
+    const int chunks = gyro_x_chunks(B, P);
+    const int ppc = (int)((((P + chunks - 1) / chunks) + kGyroBxTJ - 1) / kGyroBxTJ * kGyroBxTJ);
+    const int nch = (int)((P + ppc - 1) / ppc);
+    float* dst = nch == 1 ? gx : wx;
+    {
         dim3 grid((unsigned)((B + kGyroBxThreads - 1) / kGyroBxThreads), (unsigned)nch);
-        if (aliased) k_gyro_bwd_x<D4, true><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, (int)B, (int)D, (int)P, ppc, prm);
-        else         k_gyro_bwd_x<D4, false><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, (int)B, (int)D, (int)P, ppc, prm);
+        if (aliased) k_gyro_bwd_pairs<D4, true><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, CP, CA, wsum, (int)B, (int)D, (int)P, ppc, prm);
+        else         k_gyro_bwd_pairs<D4, false><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, CP, CA, wsum, (int)B, (int)D, (int)P, ppc, prm);
         if (nch > 1) k_gyro_reduce_slabs<<<(unsigned)((B * D + 255) / 256), 256, 0, s>>>(wx, gx, B * D, nch);
     }
     if (gp || ga || gbias) {
-        dim3 grid((unsigned)((P + kGyroBpThreads - 1) / kGyroBpThreads), (unsigned)slabs);
-        if (aliased) k_gyro_bwd_p<D4, true><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, gout, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab, prm);
-        else         k_gyro_bwd_p<D4, false><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, gout, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab, prm);
+        const int slabs = gyro_slabs(B, P);
+        const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBxThreads - 1) / kGyroBxThreads * kGyroBxThreads);
+        const int nsl = (int)((B + rows_per_slab - 1) / rows_per_slab);
+        dim3 grid((unsigned)((P + kGyroBpThreads - 1) / kGyroBpThreads), (unsigned)nsl);
+        if (aliased) k_gyro_bwd_planes<D4, true><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);
+        else         k_gyro_bwd_planes<D4, false><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);
         const int64_t n = P * D;
-        if (gp) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wp, gp, n, slabs);
-        if (ga && !aliased) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wa, ga, n, slabs);
-        if (gbias) k_gyro_reduce_slabs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(wb, gbias, P, slabs);
+        if (gp) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wp, gp, n, nsl);
+        if (ga && !aliased) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wa, ga, n, nsl);
+        if (gbias) k_gyro_reduce_slabs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(wb, gbias, P, nsl);
     }
     return check_launch();
 }
@@ -543,8 +583,7 @@ extern "C" int hvae_gyroplane_fwd_f32(const float* x, const float* p, const floa
 
 extern "C" size_t hvae_gyroplane_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P) {
     if (B <= 0 || P <= 0 || D <= 0) return 0;
-    const int slabs = gyro_slabs(B, P);
-    return sizeof(float) * ((size_t)slabs * P * D * 2 + (size_t)slabs * P + (size_t)gyro_x_chunks(B, P) * B * D);
+    return sizeof(float) * gyro_ws_layout(B, D, P).total;
 }
 
 extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout, float* gx,
@@ -554,6 +593,7 @@ extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const floa
     if (B == 0 || P == 0) return HVAE_OK;
     if (!x || !p || !a || !gout) return HVAE_EARG;
     if (a != p && gp && !ga) return HVAE_EARG;
+    if (!gx) return HVAE_EARG;
     if (!workspace || workspace_bytes < hvae_gyroplane_bwd_workspace_bytes(B, D, P)) return HVAE_EARG;
     const GyroParams prm = make_gyro_params(c, flags);
     cudaStream_t s = (cudaStream_t)stream;
