@@ -13,131 +13,9 @@
 // Memory is O(B*P) for the output only.  Algorithmic bytes: fwd 4(BD + 2PD + BP), bwd 4(BP + 2BD + 4PD).
 // At D <= 64 the kernel is bound by the B*P output write / epilogue math, not by the FMA count.
 #include "hvae_common.cuh"
+#include "gyro_pair.cuh"
 
 namespace hvae {
-
-struct GyroParams {
-    float c, sc, rsc, maxnorm;
-    uint32_t flags;
-};
-
-struct GyroPairCtx {
-    float A, Bc, den, N1, N2, da, dn2, an, w, denom, y, out0, out1, rho_n;  // rho_n: |diff| when projected
-    bool den_ok, dn2_ok, w_ok, projected;
-};
-
-// scalar epilogue shared by forward and backward (and, later, by the tensor-core path)
-// Difference form (SIMT path): with e = |x-p|^2, q = <p,p-x>, qa = <a,p-x> accumulated from elementwise
-// differences (exact when x -> p), A = Bc + c e and
-//   N1 = -A<p,a> + Bc<x,a> = -Bc qa - c e <p,a>,   N2 = e (Bc^2 + 2 Bc c q + c^2 e |p|^2)
-// so the x -> p cancellation that the plain inner-product form suffers (abs error eps*|p|^2) is gone.
-struct GyroDiff {
-    float e, q, qa;
-};
-
-__device__ __forceinline__ float gyro_pair_fwd(float px, float xa, float x2, float p2, float pa, float an_raw,
-                                               const GyroParams& P, GyroPairCtx& k, const GyroDiff* df = nullptr) {
-    const float c = P.c;
-    const bool pvae = P.flags & HVAE_GYRO_PVAE;
-    k.Bc = 1.0f - c * p2;
-    const float den0 = 1.0f - 2.0f * c * px + c * c * p2 * x2;
-    k.den_ok = den0 >= kMinNorm;
-    k.den = fmaxf(den0, kMinNorm);
-    if (df) {
-        k.A = k.Bc + c * df->e;
-        k.N1 = -k.Bc * df->qa - c * df->e * pa;
-        k.N2 = fmaxf(df->e * (k.Bc * k.Bc + 2.0f * k.Bc * c * df->q + c * c * df->e * p2), 0.0f);
-    } else {
-        k.A = 1.0f - 2.0f * c * px + c * x2;
-        k.N1 = -k.A * pa + k.Bc * xa;
-        k.N2 = fmaxf(k.A * k.A * p2 - 2.0f * k.A * k.Bc * px + k.Bc * k.Bc * x2, 0.0f);
-    }
-    const float rden = 1.0f / k.den;
-    k.da = k.N1 * rden;
-    float dn2r = k.N2 * rden * rden;
-    k.projected = false;
-    if (pvae) {
-        const float n = fmaxf(sqrtf(dn2r), kMinNorm);
-        if (n > P.maxnorm) {  // (-p)(+)x was projected back into the ball
-            k.projected = true;
-            k.rho_n = n;
-            k.da = k.da / n * P.maxnorm;
-            dn2r = P.maxnorm * P.maxnorm;
-        }
-    }
-    k.dn2_ok = dn2r >= kMinNorm;
-    k.dn2 = fmaxf(dn2r, kMinNorm);
-    const float s = (P.flags & HVAE_GYRO_SIGNED) ? k.da : fabsf(k.da);
-    k.an = pvae ? fmaxf(an_raw, kMinNorm) : an_raw;
-    k.w = (1.0f - c * k.dn2) * k.an;
-    if (pvae) {
-        k.w_ok = k.w >= kMinNorm;
-        k.denom = fmaxf(k.w, kMinNorm);
-    } else {
-        k.w_ok = true;
-        k.denom = (k.w >= 0.0f ? 1.0f : -1.0f) * (fabsf(k.w) + kMinNorm);  // clamp_abs, sign(0) = +1
-    }
-    k.y = 2.0f * P.sc * s / k.denom;
-    k.out0 = asinhf(k.y) * P.rsc;
-    k.out1 = (P.flags & HVAE_GYRO_SCALED) ? k.out0 * k.an : k.out0;
-    float o = k.out1;
-    if (P.flags & HVAE_GYRO_SQUARED) {
-        const float sg = (o > 0.0f) ? 1.0f : ((o < 0.0f) ? -1.0f : 0.0f);
-        o = (P.flags & HVAE_GYRO_SIGNED) ? o * o * sg : o * o;
-    }
-    return o;
-}
-
-struct GyroPairGrad {
-    float dpx, dxa, dx2, dp2, dpa, dan;  // dan: gradient wrt the RAW ||a||
-};
-
-__device__ __forceinline__ GyroPairGrad gyro_pair_bwd(float g, float px, float xa, float x2, float p2, float pa,
-                                                      float an_raw, const GyroParams& P, const GyroPairCtx& k) {
-    GyroPairGrad r;
-    const float c = P.c;
-    const bool pvae = P.flags & HVAE_GYRO_PVAE;
-    float g1 = g;
-    if (P.flags & HVAE_GYRO_SQUARED) g1 = (P.flags & HVAE_GYRO_SIGNED) ? g * 2.0f * fabsf(k.out1) : g * 2.0f * k.out1;
-    float gan = 0.0f;  // wrt the (possibly clamped) an
-    float g0 = g1;
-    if (P.flags & HVAE_GYRO_SCALED) {
-        gan += g1 * k.out0;
-        g0 = g1 * k.an;
-    }
-    const float dy = g0 * P.rsc * rsqrtf(1.0f + k.y * k.y);
-    const float ds = dy * 2.0f * P.sc / k.denom;
-    const float ddenom = -dy * k.y / k.denom;
-    const float dw = k.w_ok ? ddenom : 0.0f;
-    const float ddn2 = dw * (-c * k.an);
-    gan += dw * (1.0f - c * k.dn2);
-    float dda = ds;
-    if (!(P.flags & HVAE_GYRO_SIGNED)) dda = (k.da > 0.0f) ? ds : ((k.da < 0.0f) ? -ds : 0.0f);
-    float dN1, dN2, dden;
-    if (k.projected) {
-        // da = maxnorm * N1 / sqrt(N2); |diff|^2 == maxnorm^2 carries no gradient
-        const float rs = rsqrtf(k.N2);
-        dN1 = dda * P.maxnorm * rs;
-        dN2 = -dda * P.maxnorm * k.N1 * 0.5f * rs * rs * rs;
-        dden = 0.0f;
-    } else {
-        const float ddn2r = k.dn2_ok ? ddn2 : 0.0f;
-        const float rden = 1.0f / k.den;
-        dN1 = dda * rden;
-        dN2 = ddn2r * rden * rden;
-        dden = -dda * k.N1 * rden * rden - 2.0f * ddn2r * k.N2 * rden * rden * rden;
-    }
-    const float dden0 = k.den_ok ? dden : 0.0f;
-    const float dA = -pa * dN1 + (2.0f * k.A * p2 - 2.0f * k.Bc * px) * dN2;
-    const float dBc = xa * dN1 + (-2.0f * k.A * px + 2.0f * k.Bc * x2) * dN2;
-    r.dpa = -k.A * dN1;
-    r.dxa = k.Bc * dN1;
-    r.dp2 = k.A * k.A * dN2 - c * dBc + c * c * x2 * dden0;
-    r.dx2 = k.Bc * k.Bc * dN2 + c * dA + c * c * p2 * dden0;
-    r.dpx = -2.0f * k.A * k.Bc * dN2 - 2.0f * c * dA - 2.0f * c * dden0;
-    r.dan = (pvae && an_raw < kMinNorm) ? 0.0f : gan;
-    return r;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // tiling: a CTA of 128 threads owns TB rows x TJ planes; thread = one plane, 8 rows at a time.

@@ -1,0 +1,438 @@
+// K1-TC / K2-TC: the two dense contractions of the path as tcgen05 GEMMs (bf16 operands, fp32 TMEM accumulators)
+// with the hyperbolic math fused into the epilogue — forward, large shapes (config 5: B=2^20, F/D=512, P=4096).
+//
+// reference: hyperbolic_vae/layers.py:145-147 (MobiusLayer -> geoopt mobius_matvec's tensordot) and
+//            layers.py:193-210 (gyroplane: the reference broadcasts (B,D,P); here <x,p> is a GEMM).
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage smem ring, mbarrier expect_tx
+//   warp 1      MMA issuer     one elected lane: tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16 x4 per stage,
+//                              tcgen05.commit frees the smem stage / publishes the accumulator
+//   warps 2-5   epilogue       tcgen05.ld 32x32b.x32 from TMEM (2 accumulator stages of 128 columns, so the
+//                              epilogue of tile i overlaps the MMAs of tile i+1), fused math, global stores
+// Operands are K-major: A = rows of x (B,K), B = rows of the weight (P,K); both are converted fp32 -> bf16 by a
+// streaming pre-pass that also produces the row norms the epilogues need.
+//
+// Epilogues
+//   PLAIN : D = acc (* rowscale) ; optional per-(row, n-tile) sum of acc^2  (Mobius pass 1: mx and |mx|^2 partials)
+//   GYRO  : D = asinh-distance of row b to plane j from <x_b,p_j>, |x_b|^2, |p_j|^2  (gyro_pair_fwd, a == p)
+// The Mobius rescale y = psi(|x|,|mx|) mx needs |mx_b| over ALL of P, i.e. across n-tiles: v1 finishes it with a
+// light second pass (k_mobius_rescale_rows); DESIGN.md lists the Gram-matrix single-pass variant as next.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "hvae_common.cuh"
+#include "gyro_pair.cuh"
+
+namespace hvae {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64;   // BK * sizeof(bf16) = 128 B = one swizzle atom
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 192;
+constexpr uint32_t TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
+constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
+
+enum { EPI_PLAIN = 0, EPI_GYRO = 1 };
+
+struct Params {
+    float* D;              // (M, N) row-major output
+    int64_t M, N, K;
+    const float* rowscale; // PLAIN: optional (M,)
+    float* rowsq;          // PLAIN: optional [n_tiles][M] partial sums of acc^2
+    const float* x2;       // GYRO: (M,) |x|^2
+    const float* p2;       // GYRO: (N,) |p|^2
+    const float* bias;     // GYRO: optional (N,)
+    GyroParams gp;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), one atom along K
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address >> 4
+    d |= (uint64_t)0 << 16;                             // leading byte offset (unused: one swizzle atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle wants 1024-byte aligned tiles
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
+    const int64_t tiles = m_tiles * n_tiles;
+    const int k_blocks = (int)((prm.K + BK - 1) / BK);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(sa + TILE_A_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(as), aphase ^ 1u);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    const uint64_t da = make_desc(sa), db = make_desc(sa + TILE_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(as));                 // accumulator complete
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int64_t mt = t / n_tiles, nt = t % n_tiles;
+            const int64_t m = mt * BM + q * 32 + lane;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const bool row_ok = m < prm.M;
+            float rs = 1.0f, x2 = 0.0f, sq = 0.0f;
+            if (EPI == EPI_PLAIN && prm.rowscale && row_ok) rs = __ldg(prm.rowscale + m);
+            if (EPI == EPI_GYRO && row_ok) x2 = __ldg(prm.x2 + m);
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb), v);
+                const int64_t n0 = nt * BN + cb;
+                if (EPI == EPI_PLAIN) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        sq = fmaf(v[i], v[i], sq);  // out-of-range columns are TMA zero-filled -> contribute 0
+                        v[i] *= rs;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int64_t n = n0 + i;
+                        if (n < prm.N) {
+                            const float p2 = __ldg(prm.p2 + n);
+                            GyroPairCtx k;
+                            float o = gyro_pair_fwd(v[i], v[i], x2, p2, p2, sqrtf(p2), prm.gp, k);
+                            if (prm.bias) o += __ldg(prm.bias + n);
+                            v[i] = o;
+                        }
+                    }
+                }
+                if (row_ok) {
+                    float* dst = prm.D + m * prm.N + n0;
+                    if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < prm.N) dst[i] = v[i];
+                    }
+                }
+            }
+            if (EPI == EPI_PLAIN && prm.rowsq && row_ok) prm.rowsq[nt * prm.M + m] = sq;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// fp32 -> bf16 rows (+ sum of squares of the ROUNDED values, so the epilogue algebra stays consistent)
+__global__ void k_rows_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, float* __restrict__ sumsq,
+                               int64_t rows, int64_t cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nw) {
+        float s = 0.0f;
+        for (int64_t c = lane * 4; c < cols; c += 128) {
+            if (c + 4 <= cols && (cols & 3) == 0) {
+                const float4 v = *reinterpret_cast<const float4*>(in + r * cols + c);
+                const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+                *reinterpret_cast<__nv_bfloat162*>(out + r * cols + c) = a;
+                *reinterpret_cast<__nv_bfloat162*>(out + r * cols + c + 2) = b;
+                const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+                s += fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+            } else {
+                for (int64_t cc = c; cc < cols && cc < c + 4; ++cc) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(in[r * cols + cc]);
+                    out[r * cols + cc] = h;
+                    const float f = __bfloat162float(h);
+                    s += f * f;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (sumsq && lane == 0) sumsq[r] = s;
+    }
+}
+
+// Mobius pass 2: y_b = psi(|x_b|, |mx_b|) mx_b, projected.  one warp per row.
+__global__ void k_mobius_rescale_rows(const float* __restrict__ mx, const float* __restrict__ x2, const float* __restrict__ rowsq,
+                                      float* __restrict__ y, int64_t B, int64_t P, int n_tiles, Ball ball) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nw) {
+        float s = 0.0f;
+        for (int t = lane; t < n_tiles; t += 32) s += rowsq[(int64_t)t * B + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float xn = fmaxf(sqrtf(x2[b]), kMinNorm);
+        const float mxn_raw = sqrtf(s), mxn = fmaxf(mxn_raw, kMinNorm);
+        const float th = mxn / xn * artanh_c(ball.sc * xn);
+        const float t = tanh_c(th);
+        float scale = ball.rsc * t / mxn;
+        const float yn = fmaxf(ball.rsc * t * (mxn_raw / mxn), kMinNorm);
+        if (yn > ball.maxnorm) scale = scale / yn * ball.maxnorm;
+        if (s == 0.0f) scale = 0.0f;  // all-zero mx row -> exact zero (geoopt's `cond`)
+        for (int64_t j = lane; j < P; j += 32) y[b * P + j] = scale * mx[b * P + j];
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// bf16 row-major (rows, K) -> 2-D tensor map with a {BK, box_rows} box, 128B swizzle
+static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm, cudaStream_t s) {
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, A, prm.M, prm.K, BM) || !make_map(&mb, Bm, prm.N, prm.K, BN)) return HVAE_ELAUNCH;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        attr_set = true;
+    }
+    const int64_t tiles = ((prm.M + BM - 1) / BM) * ((prm.N + BN - 1) / BN);
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    k_tc_gemm<EPI><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, prm);
+    return check_launch();
+}
+
+struct Ws {
+    size_t a16, b16, x2, p2, rowsq, total;  // byte offsets
+};
+static Ws ws_layout(int64_t B, int64_t K, int64_t P) {
+    Ws w;
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return at; };
+    w.a16 = take((size_t)B * K * 2);
+    w.b16 = take((size_t)P * K * 2);
+    w.x2 = take((size_t)B * 4);
+    w.p2 = take((size_t)P * 4);
+    w.rowsq = take((size_t)((P + BN - 1) / BN) * B * 4);
+    w.total = o;
+    return w;
+}
+
+}  // namespace tc
+}  // namespace hvae
+
+using namespace hvae;
+
+extern "C" size_t hvae_tc_workspace_bytes(int64_t B, int64_t K, int64_t P) {
+    if (B <= 0 || K <= 0 || P <= 0) return 0;
+    return tc::ws_layout(B, K, P).total;
+}
+
+static int tc_check(int64_t B, int64_t K, int64_t P) {
+    if (B <= 0 || P <= 0 || K <= 0 || (K % 8) != 0) return HVAE_ESHAPE;  // TMA row stride must be a multiple of 16 B
+    return HVAE_OK;
+}
+
+extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, int64_t B, int64_t F,
+                                             int64_t P, float c, void* workspace, size_t workspace_bytes, void* stream) {
+    if (tc_check(B, F, P) != HVAE_OK) return HVAE_ESHAPE;
+    if (!x || !M || !y || !mx_out || !workspace) return HVAE_EARG;
+    const tc::Ws L = tc::ws_layout(B, F, P);
+    if (workspace_bytes < L.total) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* a16 = (__nv_bfloat16*)(ws + L.a16);
+    auto* b16 = (__nv_bfloat16*)(ws + L.b16);
+    float* x2 = (float*)(ws + L.x2);
+    float* rowsq = (float*)(ws + L.rowsq);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, a16, x2, B, F);
+    tc::k_rows_to_bf16<<<(unsigned)((P + 7) / 8 < 1 ? 1 : (P + 7) / 8), 256, 0, s>>>(M, b16, nullptr, P, F);
+    tc::Params prm{};
+    prm.D = mx_out; prm.M = B; prm.N = P; prm.K = F; prm.rowscale = nullptr; prm.rowsq = rowsq;
+    int rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
+    if (rc != HVAE_OK) return rc;
+    tc::k_mobius_rescale_rows<<<kNumSMs * 8, 256, 0, s>>>(mx_out, x2, rowsq, y, B, P, (int)((P + tc::BN - 1) / tc::BN), make_ball(c));
+    return check_launch();
+}
+
+extern "C" int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
+                                         int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+    if (tc_check(B, D, P) != HVAE_OK) return HVAE_ESHAPE;
+    if (!x || !p || !out || !workspace) return HVAE_EARG;
+    const tc::Ws L = tc::ws_layout(B, D, P);
+    if (workspace_bytes < L.total) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* a16 = (__nv_bfloat16*)(ws + L.a16);
+    auto* b16 = (__nv_bfloat16*)(ws + L.b16);
+    float* x2 = (float*)(ws + L.x2);
+    float* p2 = (float*)(ws + L.p2);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, a16, x2, B, D);
+    tc::k_rows_to_bf16<<<(unsigned)((P + 7) / 8 < 1 ? 1 : (P + 7) / 8), 256, 0, s>>>(p, b16, p2, P, D);
+    tc::Params prm{};
+    prm.D = out; prm.M = B; prm.N = P; prm.K = D; prm.x2 = x2; prm.p2 = p2; prm.bias = bias;
+    const Ball b = make_ball(c);
+    prm.gp.c = b.c; prm.gp.sc = b.sc; prm.gp.rsc = b.rsc; prm.gp.maxnorm = b.maxnorm; prm.gp.flags = flags;
+    return tc::launch_gemm<tc::EPI_GYRO>(a16, b16, prm, s);
+}

@@ -468,7 +468,10 @@ def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor],
     lead = x.shape[:-1]
     xr = _rows(x)
     a_arg = None if (a is None or a is p) else _c(a)
-    out = gyroplane_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
+    if a_arg is None and _tc_eligible(xr.shape[0], xr.shape[1], p.shape[0]):
+        out = gyroplane_tc_fwd(xr, _c(p), None if bias is None else _c(bias), c, int(flags))
+    else:
+        out = gyroplane_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
     return out.view(*lead, p.shape[0])
 
 
@@ -624,7 +627,11 @@ mobius_matvec_fwd.register_autograd(_mm_backward, setup_context=_mm_setup)
 def mobius_matvec(x: Tensor, M: Tensor, c: float) -> Tensor:
     """project(M (x)_c x) for every row of x (..., F) -> (..., P)"""
     lead = x.shape[:-1]
-    y, _ = mobius_matvec_fwd(_rows(x), _c(M), c)
+    xr = _rows(x)
+    if _tc_eligible(xr.shape[0], xr.shape[1], M.shape[0]):
+        y, _ = mobius_matvec_tc_fwd(xr, _c(M), c)
+    else:
+        y, _ = mobius_matvec_fwd(xr, _c(M), c)
     return y.view(*lead, M.shape[0])
 
 
@@ -781,3 +788,82 @@ def expmap_polar(mu: Tensor, alpha: Tensor, r: Tensor, c: float) -> Tensor:
     z = expmap_polar_fwd(_c(mu_b).view(B, D), _c(alpha).view(S, B, D), _c(r.expand(*alpha.shape[:-1], 1)).view(S, B), c)
     z = z.view(alpha.shape)
     return z.squeeze(0) if squeeze else z
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1-TC / K2-TC: tcgen05 bf16 GEMM paths (forward) for GEMM-sized shapes
+# ---------------------------------------------------------------------------------------------------
+_gemm_mode = "fp32"
+
+
+def set_gemm_mode(mode: str):
+    """'fp32' (default: SIMT fp32 kernels, 1e-5 parity) or 'bf16' (tcgen05 GEMMs with bf16 operands / fp32
+    accumulation for GEMM-sized Mobius / gyroplane shapes, 1e-2 parity — BASELINE.json's "bf16 GEMM mode")."""
+    global _gemm_mode
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(mode)
+    _gemm_mode = mode
+
+
+def get_gemm_mode() -> str:
+    return _gemm_mode
+
+
+def _tc_eligible(B: int, K: int, P: int) -> bool:
+    return _gemm_mode == "bf16" and B >= 128 and P >= 128 and K >= 64 and K % 8 == 0
+
+
+@_op("hvae::mobius_matvec_tc_fwd", mutates_args=())
+def mobius_matvec_tc_fwd(x: Tensor, M: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(x, M)
+    B, F = x.shape
+    P = M.shape[0]
+    y, mx = x.new_empty(B, P), x.new_empty(B, P)
+    ws = _workspace(C.lib().hvae_tc_workspace_bytes(B, F, P), x.device)
+    C.call("hvae_mobius_matvec_tc_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), C.ptr(mx), B, F, P, c, C.ptr(ws), ws.numel(),
+           C.stream())
+    C.launch_count += 3
+    return y, mx
+
+
+@mobius_matvec_tc_fwd.register_fake
+def _(x, M, c):
+    return x.new_empty(x.shape[0], M.shape[0]), x.new_empty(x.shape[0], M.shape[0])
+
+
+mobius_matvec_tc_fwd.register_autograd(_mm_backward, setup_context=_mm_setup)  # backward: the fp32 kernels on the saved mx
+
+
+@_op("hvae::gyroplane_tc_fwd", mutates_args=())
+def gyroplane_tc_fwd(x: Tensor, p: Tensor, bias: Optional[Tensor], c: float, flags: int) -> Tensor:
+    C.require_cuda(x, p, bias)
+    B, D = x.shape
+    P = p.shape[0]
+    out = x.new_empty(B, P)
+    ws = _workspace(C.lib().hvae_tc_workspace_bytes(B, D, P), x.device)
+    C.call("hvae_gyroplane_tc_fwd_f32", C.ptr(x), C.ptr(p), C.ptr(bias), C.ptr(out), B, D, P, c, flags, C.ptr(ws),
+           ws.numel(), C.stream())
+    C.launch_count += 2
+    return out
+
+
+@gyroplane_tc_fwd.register_fake
+def _(x, p, bias, c, flags):
+    return x.new_empty(x.shape[0], p.shape[0])
+
+
+def _gtc_setup(ctx, inputs, output):
+    x, p, bias, c, flags = inputs
+    ctx.save_for_backward(x, p)
+    ctx.has_bias, ctx.c, ctx.flags = bias is not None, c, flags
+
+
+def _gtc_backward(ctx, g):
+    x, p = ctx.saved_tensors
+    if x.shape[1] > 64:
+        raise NotImplementedError("gyroplane backward for D > 64 (tensor-core shapes) is not implemented yet")
+    gx, gp, _, gb = gyroplane_bwd(x, p, None, _c(g), ctx.c, ctx.flags, ctx.has_bias)
+    return gx, gp, (gb if ctx.has_bias else None), None, None
+
+
+gyroplane_tc_fwd.register_autograd(_gtc_backward, setup_context=_gtc_setup)

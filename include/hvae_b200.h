@@ -145,6 +145,15 @@ int hvae_expmap_polar_fwd_f32(const float* mu, const float* alpha, const float* 
 int hvae_expmap_polar_bwd_f32(const float* mu, const float* alpha, const float* r, const float* gz,
                               float* gmu, float* gr, int64_t S, int64_t B, int64_t D, float c, void* stream);
 
+/* ---- K1-TC / K2-TC: tcgen05 (bf16 operands, fp32 accumulate) forward paths for GEMM-sized shapes --------------
+ * Same math as hvae_mobius_matvec_fwd_f32 / hvae_gyroplane_fwd_f32 (a == p), operands rounded to bf16: the
+ * "bf16 GEMM mode" of BASELINE.json (1e-2 tolerance).  K (= F or D) must be a multiple of 8. */
+size_t hvae_tc_workspace_bytes(int64_t B, int64_t K, int64_t P);
+int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, int64_t B, int64_t F,
+                                  int64_t P, float c, void* workspace, size_t workspace_bytes, void* stream);
+int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
+                              int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,82 @@
+"""GPU parity of the tcgen05 (bf16-operand) forward paths against the fp32 oracle: BASELINE.json's
+"1e-2 in bf16 GEMM mode".  Inputs are kept away from the projection radius (conditioning, see util_parity)."""
+import pytest
+import torch
+
+from util_parity import pair_kappa
+
+pytestmark = pytest.mark.gpu
+
+
+def _oball(c):
+    from oracle.geoopt_min import PoincareBall
+
+    return PoincareBall(c=c)
+
+
+@pytest.mark.parametrize("B,F,P", [(128, 64, 128), (256, 128, 256), (384, 256, 640), (1000, 512, 300), (4096, 512, 1024)])
+def test_mobius_tc_forward(B, F, P):
+    import hvae
+    from hvae import ops
+    from oracle.geoopt_min.manifolds.stereographic import math as gm
+
+    torch.manual_seed(B + P)
+    c = 1.0
+    ob = _oball(c)
+    x = ob.expmap0(torch.randn(B, F) * 0.5 / F ** 0.5).detach()
+    M = torch.randn(P, F) / F ** 0.5 * 0.7
+    ref = gm.project(gm.mobius_matvec(M.double(), x.double(), k=torch.tensor(-c, dtype=torch.float64)), k=torch.tensor(-c, dtype=torch.float64), eps=4e-3)
+    ops.set_gemm_mode("bf16")
+    try:
+        y, mx = ops.mobius_matvec_tc_fwd(x.cuda(), M.cuda(), hvae.PoincareBall(c).c_value)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode("fp32")
+    mx_ref = x.double() @ M.double().t()
+    err_mx = (mx.double().cpu() - mx_ref).abs().max() / mx_ref.abs().max()
+    assert err_mx < 1e-2, err_mx
+    scale = ref.abs().amax(dim=-1, keepdim=True)
+    err = ((y.double().cpu() - ref).abs() / scale).max()
+    assert err < 1e-2, err
+    # the fp32 SIMT path on the same inputs agrees with the TC path to bf16 accuracy as well
+    y32, _ = ops.mobius_matvec_fwd(x.cuda(), M.cuda(), hvae.PoincareBall(c).c_value)
+    assert ((y32 - y).abs().cpu() / scale.float()).max() < 1e-2
+
+
+@pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024)])
+def test_gyroplane_tc_forward(B, D, P):
+    import hvae
+    from hvae import ops
+    from oracle.geoopt_min.manifolds.stereographic import math as gm
+
+    torch.manual_seed(B + D)
+    c = 1.0
+    ob = _oball(c)
+    x = ob.expmap0(torch.randn(B, D) * 0.6 / D ** 0.5).detach()
+    p = ob.expmap0(torch.randn(P, D) * 0.6 / D ** 0.5).detach()
+    bias = torch.randn(P)
+    k = torch.tensor(-c, dtype=torch.float64)
+    ref = gm.dist2plane(x.double().unsqueeze(-1), p.double().t(), p.double().t(), k=k, signed=True, dim=-2) + bias.double()
+    out = ops.gyroplane_tc_fwd(x.cuda(), p.cuda(), bias.cuda(), hvae.PoincareBall(c).c_value, ops.GYRO_SIGNED)
+    torch.cuda.synchronize()
+    pk = pair_kappa(c, x, p)
+    err = (out.double().cpu() - ref).abs()
+    bound = 1e-2 * ref.abs() + 1e-2 * pk  # bf16 operands: eps ~ 4e-3 on <x,p>, amplified by the pair conditioning
+    assert bool((err <= bound).all()), (err / bound).max()
+    assert float(err.max()) < 0.05 * float(ref.abs().max()) + 1e-2
+
+
+def test_layer_dispatches_to_tc_in_bf16_mode():
+    import hvae
+    from hvae import _cabi, layers, ops
+
+    ball = hvae.PoincareBall(1.0)
+    lay = layers.MobiusLayer(256, 512, ball).cuda()
+    x = torch.randn(256, 256, device="cuda") * 0.05
+    y32 = lay(x)
+    ops.set_gemm_mode("bf16")
+    try:
+        y16 = lay(x)
+    finally:
+        ops.set_gemm_mode("fp32")
+    assert (y16 - y32).abs().max() < 1e-2 * y32.abs().max() + 1e-4
