@@ -51,25 +51,59 @@ __device__ __forceinline__ bool group_all(bool p) {
     return (m & gm) == gm;
 }
 
-// ---- a row slice held in registers: element idx = lg + i*G for i < EPL ------------------------------
+// ---- a row slice held in registers ----------------------------------------------------------------------
+// Lane lg of the row's G-lane group holds EPL elements.  When D % 4 == 0 (and EPL % 4 == 0) a lane owns
+// contiguous float4 chunks (index 4*(lg + G*j) + e): 128-bit coalesced loads/stores.  Otherwise elements are
+// interleaved (index lg + i*G): 32-bit accesses, consecutive lanes on consecutive addresses.  D == 2 with one
+// lane per row uses one 64-bit access.
 template <int G, int EPL>
 struct RowSlice {
     float v[EPL];
 
+    __device__ __forceinline__ static bool vec4(int D) { return (EPL % 4 == 0) && ((D & 3) == 0); }
+    __device__ __forceinline__ static int index(int lg, int i, int D) {
+        return vec4(D) ? (((lg + G * (i >> 2)) << 2) + (i & 3)) : (lg + i * G);
+    }
+
     __device__ __forceinline__ void load(const float* __restrict__ base, int64_t row, int D, int lg, bool valid) {
         const float* p = base + row * (int64_t)D;
+        if (EPL % 4 == 0 && vec4(D)) {
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const int idx = lg + i * G;
-            v[i] = (valid && idx < D) ? __ldg(p + idx) : 0.0f;
+            for (int j = 0; j < EPL / 4; ++j) {
+                const int idx = (lg + G * j) << 2;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && idx < D) t = __ldg(reinterpret_cast<const float4*>(p + idx));
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+        } else if (G == 1 && EPL == 2 && D == 2) {
+            float2 t = make_float2(0.f, 0.f);
+            if (valid) t = __ldg(reinterpret_cast<const float2*>(p));
+            v[0] = t.x; v[1] = t.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const int idx = lg + i * G;
+                v[i] = (valid && idx < D) ? __ldg(p + idx) : 0.0f;
+            }
         }
     }
     __device__ __forceinline__ void store(float* __restrict__ base, int64_t row, int D, int lg, bool valid) const {
         float* p = base + row * (int64_t)D;
+        if (EPL % 4 == 0 && vec4(D)) {
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const int idx = lg + i * G;
-            if (valid && idx < D) p[idx] = v[i];
+            for (int j = 0; j < EPL / 4; ++j) {
+                const int idx = (lg + G * j) << 2;
+                if (valid && idx < D)
+                    *reinterpret_cast<float4*>(p + idx) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        } else if (G == 1 && EPL == 2 && D == 2) {
+            if (valid) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const int idx = lg + i * G;
+                if (valid && idx < D) p[idx] = v[i];
+            }
         }
     }
     __device__ __forceinline__ void zero() {
@@ -92,47 +126,79 @@ __device__ __forceinline__ float sqnorm(const RowSlice<G, EPL>& a) {
 }
 
 // ---- scalar functions with the reference's clamps, plus the derivative masks ----------------------
-__device__ __forceinline__ float tanh_c(float x) { return tanhf(fminf(fmaxf(x, -kTanhClamp), kTanhClamp)); }
+// Branch-free fast-intrinsic evaluations, each accurate to ~1e-6 relative (parity budget 1e-5):
+//   tanh   : odd Taylor polynomial to x^13 below 0.4 (3.9e-9), (E-1)/(E+1) with E = ex2.approx above
+//   artanh : odd series to x^11 below 0.2 (3.2e-10), 0.5*lg2.approx((1+x)/(1-x)) above (1-x exact for x >= 0.5)
+__device__ __forceinline__ float rcpf(float v) { return __fdividef(1.0f, v); }
+
+// t = tanh(clamp(x, +-15)); s2 = sech^2 of the clamped argument (0 outside the clamp: clamp has zero gradient there)
+__device__ __forceinline__ void tanh_sech2(float x, float& t, float& s2) {
+    const float ax = fminf(fabsf(x), kTanhClamp);
+    const float x2 = ax * ax;
+    const float poly = ax * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 21844.0f / 6081075.0f, -1382.0f / 155925.0f),
+                       62.0f / 2835.0f), -17.0f / 315.0f), 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);
+    const float E = __expf(2.0f * ax);
+    const float r = rcpf(E + 1.0f);
+    const float big = (E - 1.0f) * r;
+    const float tt = ax < 0.4f ? poly : big;
+    t = copysignf(tt, x);
+    // sech^2 = 4E/(E+1)^2 has no cancellation when tanh saturates (1 - t^2 does)
+    s2 = (fabsf(x) <= kTanhClamp) ? 4.0f * E * r * r : 0.0f;
+}
+__device__ __forceinline__ float tanh_c(float x) {
+    float t, s2;
+    tanh_sech2(x, t, s2);
+    return t;
+}
 __device__ __forceinline__ float tanh_mask(float x) { return (x >= -kTanhClamp && x <= kTanhClamp) ? 1.0f : 0.0f; }
 
-__device__ __forceinline__ float artanh_c(float x) { return atanhf(fminf(fmaxf(x, -kArtanhClamp), kArtanhClamp)); }
+__device__ __forceinline__ float artanh_c(float x) {
+    const float ax = fminf(fabsf(x), kArtanhClamp);
+    const float x2 = ax * ax;
+    const float poly = ax * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 1.0f / 11.0f, 1.0f / 9.0f), 1.0f / 7.0f), 1.0f / 5.0f),
+                       1.0f / 3.0f), 1.0f);
+    const float big = 0.5f * __logf(__fdividef(1.0f + ax, 1.0f - ax));
+    return copysignf(ax < 0.2f ? poly : big, x);
+}
 // d/dx artanh(clamp(x)) = 1/(1-xc^2) inside the clamp, 0 outside
 __device__ __forceinline__ float artanh_grad(float x) {
     if (!(x >= -kArtanhClamp && x <= kArtanhClamp)) return 0.0f;
-    return 1.0f / ((1.0f - x) * (1.0f + x));
+    return rcpf((1.0f - x) * (1.0f + x));
 }
 
 // log(sinh(x)/x) for x >= 0, accurate at small x (the reference's log sinh - log x cancels there)
 __device__ __forceinline__ float log_sinhc(float x) {
-    if (x < 0.5f) {
-        const float x2 = x * x;
-        // log(sinh x / x) = x^2/6 - x^4/180 + x^6/2835 - x^8/37800
-        return x2 * (1.0f / 6.0f + x2 * (-1.0f / 180.0f + x2 * (1.0f / 2835.0f + x2 * (-1.0f / 37800.0f))));
-    }
-    // log sinh x = x + log(1 - e^{-2x}) - log 2
-    return x + log1pf(-expf(-2.0f * x)) - 0.69314718055994530942f - logf(x);
+    const float x2 = x * x;
+    // x^2/6 - x^4/180 + x^6/2835 - x^8/37800 + x^10/467775   (|x| < 0.75: next term 3e-9)
+    const float small = x2 * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 1.0f / 467775.0f, -1.0f / 37800.0f), 1.0f / 2835.0f), -1.0f / 180.0f), 1.0f / 6.0f);
+    // log sinh x - log x = x + log((1 - e^{-2x})/(2x))
+    const float big = x + __logf(__fdividef(1.0f - __expf(-2.0f * x), 2.0f * x));
+    return x < 0.75f ? small : big;
 }
 // d/dx log(sinh(x)/x) = coth x - 1/x
 __device__ __forceinline__ float dlog_sinhc(float x) {
-    if (x < 0.5f) {
-        const float x2 = x * x;
-        // x/3 - x^3/45 + 2x^5/945 - x^7/4725
-        return x * (1.0f / 3.0f + x2 * (-1.0f / 45.0f + x2 * (2.0f / 945.0f + x2 * (-1.0f / 4725.0f))));
-    }
-    const float e = expf(-2.0f * x);
-    return (1.0f + e) / (1.0f - e) - 1.0f / x;
+    const float x2 = x * x;
+    // x/3 - x^3/45 + 2x^5/945 - x^7/4725 + 2x^9/93555
+    const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.0f / 93555.0f, -1.0f / 4725.0f), 2.0f / 945.0f), -1.0f / 45.0f), 1.0f / 3.0f);
+    const float e = __expf(-2.0f * x);
+    const float big = __fdividef(1.0f + e, 1.0f - e) - rcpf(x);
+    return x < 0.75f ? small : big;
 }
+
+// sqrt via rsqrt (1 ulp-ish), exact 0 at 0
+__device__ __forceinline__ float sqrt_fast(float v) { return v > 0.0f ? v * rsqrtf(v) : 0.0f; }
 
 // ---- project(x): where(||x|| > maxnorm, x/||x||*maxnorm, x) ----------------------------------------
 // Returns scale s so that y = s*x; *norm_out gets clamp_min(||x||, 1e-15).
 template <int G, int EPL>
 __device__ __forceinline__ bool project_inplace(RowSlice<G, EPL>& y, const Ball& ball, float& norm_out) {
-    const float n = fmaxf(sqrtf(sqnorm<G, EPL>(y)), kMinNorm);
+    const float n = fmaxf(sqrt_fast(sqnorm<G, EPL>(y)), kMinNorm);
     norm_out = n;
     const bool hit = n > ball.maxnorm;
     if (hit) {
+        const float s = ball.maxnorm * rcpf(n);
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) y.v[i] = y.v[i] / n * ball.maxnorm;
+        for (int i = 0; i < EPL; ++i) y.v[i] *= s;
     }
     return hit;
 }
@@ -143,8 +209,9 @@ __device__ __forceinline__ void project_bwd(RowSlice<G, EPL>& g, const RowSlice<
                                             const Ball& ball) {
     const float gy = dot<G, EPL>(g, ypre);  // all lanes take part in the shuffle
     if (hit) {
-        const float s = ball.maxnorm / n;
-        const float r = gy / (n * n);
+        const float rn = rcpf(n);
+        const float s = ball.maxnorm * rn;
+        const float r = gy * rn * rn;
 #pragma unroll
         for (int i = 0; i < EPL; ++i) g.v[i] = s * (g.v[i] - r * ypre.v[i]);
     }
@@ -169,8 +236,10 @@ __device__ __forceinline__ MAddCtx mobius_add_raw(const RowSlice<G, EPL>& x, con
     const float den = 1.0f + 2.0f * c * m.xy + c * c * m.x2 * m.y2;
     m.den_clamped = den < kMinNorm;
     m.den = fmaxf(den, kMinNorm);
+    const float rden = rcpf(m.den);
+    const float ar = m.A * rden, br = m.B * rden;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) out.v[i] = (m.A * x.v[i] + m.B * y.v[i]) / m.den;
+    for (int i = 0; i < EPL; ++i) out.v[i] = fmaf(ar, x.v[i], br * y.v[i]);
     return m;
 }
 
@@ -180,7 +249,7 @@ __device__ __forceinline__ void mobius_add_raw_bwd(const RowSlice<G, EPL>& x, co
                                                    const MAddCtx& m, const RowSlice<G, EPL>& g,
                                                    RowSlice<G, EPL>& gx, RowSlice<G, EPL>& gy, const Ball& ball) {
     const float c = ball.c;
-    const float s = 1.0f / m.den;
+    const float s = rcpf(m.den);
     const float gdx = dot<G, EPL>(g, x);
     const float gdy = dot<G, EPL>(g, y);
     const float dA = s * gdx;

@@ -52,23 +52,23 @@ __global__ void __launch_bounds__(kRowThreads) k_logmap0_fwd(const float* __rest
         const bool valid = row < rows;
         RowSlice<G, EPL> yr;
         yr.load(y, row, D, lg, valid);
-        const float n = fmaxf(sqrtf(sqnorm<G, EPL>(yr)), kMinNorm);
-        const float at = ball.rsc * artanh_c(ball.sc * n);
+        const float n = fmaxf(sqrt_fast(sqnorm<G, EPL>(yr)), kMinNorm);
+        const float at = ball.rsc * artanh_c(ball.sc * n) * rcpf(n);
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) yr.v[i] = (yr.v[i] / n) * at;
+        for (int i = 0; i < EPL; ++i) yr.v[i] *= at;
         yr.store(u, row, D, lg, valid);
     }
 }
 
 template <int G, int EPL>
 __device__ __forceinline__ void logmap0_row_bwd(const RowSlice<G, EPL>& y, RowSlice<G, EPL>& g, const Ball& ball) {
-    const float n_raw = sqrtf(sqnorm<G, EPL>(y));
+    const float n_raw = sqrt_fast(sqnorm<G, EPL>(y));
     const float n = fmaxf(n_raw, kMinNorm);
     const float a = ball.sc * n;
-    const float h = artanh_c(a) / a;                    // artanh(sc n)/(sc n)
-    const float hp = (artanh_grad(a) - h) / n;           // h'(n)
+    const float h = artanh_c(a) * rcpf(a);              // artanh(sc n)/(sc n)
+    const float hp = (artanh_grad(a) - h) * rcpf(n);     // h'(n)
     const float gdot = dot<G, EPL>(g, y);
-    const float coef = (n_raw >= kMinNorm) ? hp * gdot / n_raw : 0.0f;
+    const float coef = (n_raw >= kMinNorm) ? hp * gdot * rcpf(n_raw) : 0.0f;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) g.v[i] = h * g.v[i] + coef * y.v[i];
 }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kRowThreads) k_mobius_add_bwd(const float* __r
 template <int G, int EPL>
 struct ExpmapCtx {
     RowSlice<G, EPL> w;  // second term
-    float x2, m, lam, un_raw, un, th, t;
+    float x2, m, lam, un_raw, un, th, t, sech2;
     bool m_clamped;
     MAddCtx ma;
 };
@@ -156,14 +156,14 @@ __device__ __forceinline__ void expmap_row(const RowSlice<G, EPL>& x, const RowS
     const float m = 1.0f - ball.c * k.x2;
     k.m_clamped = m < kMinNorm;
     k.m = fmaxf(m, kMinNorm);
-    k.lam = 2.0f / k.m;
-    k.un_raw = sqrtf(sqnorm<G, EPL>(u));
+    k.lam = 2.0f * rcpf(k.m);
+    k.un_raw = sqrt_fast(sqnorm<G, EPL>(u));
     k.un = fmaxf(k.un_raw, kMinNorm);
-    k.th = ball.sc * ((k.lam / 2.0f) * k.un);
-    k.t = tanh_c(k.th);
-    const float q = ball.rsc * k.t;
+    k.th = ball.sc * ((k.lam * 0.5f) * k.un);
+    tanh_sech2(k.th, k.t, k.sech2);
+    const float q = ball.rsc * k.t * rcpf(k.un);
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) k.w.v[i] = q * (u.v[i] / k.un);
+    for (int i = 0; i < EPL; ++i) k.w.v[i] = q * u.v[i];
     k.ma = mobius_add_raw<G, EPL>(x, k.w, out, ball);
 }
 
@@ -175,17 +175,19 @@ __device__ __forceinline__ void expmap_row_bwd(const RowSlice<G, EPL>& x, const 
     RowSlice<G, EPL> gw;
     mobius_add_raw_bwd<G, EPL>(x, k.w, k.ma, g, gx, gw, ball);
     // w = q(un, lam) u,  q = tanh(th)/(sc un),  th = sc lam un / 2
-    const float sech2 = (1.0f - k.t * k.t) * tanh_mask(k.th);
-    const float q = ball.rsc * k.t / k.un;
-    const float dq_dun = (sech2 * (k.lam * 0.5f) - q) / k.un;  // sech^2*th' /(sc un) - tanh/(sc un^2)
+    const float sech2 = k.sech2;
+    const float run = rcpf(k.un);
+    const float q = ball.rsc * k.t * run;
+    const float dq_dun = (sech2 * (k.lam * 0.5f) - q) * run;   // sech^2*th' /(sc un) - tanh/(sc un^2)
     const float dq_dlam = sech2 * 0.5f;                          // sech^2 * (sc un/2) / (sc un)
     const float gwu = dot<G, EPL>(gw, u);
-    const float coef = (k.un_raw >= kMinNorm) ? dq_dun * gwu / k.un_raw : 0.0f;
+    const float coef = (k.un_raw >= kMinNorm) ? dq_dun * gwu * rcpf(k.un_raw) : 0.0f;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) gu.v[i] = q * gw.v[i] + coef * u.v[i];
     // lam = 2/m, m = clamp_min(1 - c x2): d lam/d x = (2/m^2) * 2 c x  when unclamped
     const float glam = dq_dlam * gwu;
-    const float gx2 = k.m_clamped ? 0.0f : glam * (2.0f / (k.m * k.m)) * ball.c;
+    const float rm = rcpf(k.m);
+    const float gx2 = k.m_clamped ? 0.0f : glam * (2.0f * rm * rm) * ball.c;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) gx.v[i] += 2.0f * gx2 * x.v[i];
 }
@@ -246,16 +248,16 @@ __global__ void __launch_bounds__(kRowThreads) k_logmap_fwd(const float* __restr
 #pragma unroll
         for (int i = 0; i < EPL; ++i) xr.v[i] = -xr.v[i];
         const MAddCtx ma = mobius_add_raw<G, EPL>(xr, yr, s, ball);
-        const float r = sqrtf(sqnorm<G, EPL>(s));
+        const float r = sqrt_fast(sqnorm<G, EPL>(s));
         if (kDist) {
             const float d = 2.0f * (ball.rsc * artanh_c(ball.sc * r));
             if (valid && lg == 0) out[row] = d;
         } else {
             const float sn = fmaxf(r, kMinNorm);
-            const float lam = 2.0f / fmaxf(1.0f - ball.c * ma.x2, kMinNorm);
-            const float at2 = 2.0f * (ball.rsc * artanh_c(ball.sc * sn));
+            const float inv_lam = 0.5f * fmaxf(1.0f - ball.c * ma.x2, kMinNorm);
+            const float f = 2.0f * (ball.rsc * artanh_c(ball.sc * sn)) * inv_lam * rcpf(sn);
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) s.v[i] = at2 * (s.v[i] / (lam * sn));
+            for (int i = 0; i < EPL; ++i) s.v[i] *= f;
             s.store(out, row, D, lg, valid);
         }
     }
@@ -275,13 +277,13 @@ __global__ void __launch_bounds__(kRowThreads) k_logmap_bwd(const float* __restr
 #pragma unroll
         for (int i = 0; i < EPL; ++i) xr.v[i] = -xr.v[i];
         const MAddCtx ma = mobius_add_raw<G, EPL>(xr, yr, s, ball);
-        const float r = sqrtf(sqnorm<G, EPL>(s));
+        const float r = sqrt_fast(sqnorm<G, EPL>(s));
         float glam = 0.0f, m = 1.0f;
         bool m_clamped = false;
         if (kDist) {
             const float gd = valid ? __ldg(gout + row) : 0.0f;
             // d = 2 artanh(sc r)/sc ; dd/dr = 2 * artanh'(sc r); d r/d s = s/r (0 at r = 0)
-            const float coef = (r > 0.0f) ? gd * 2.0f * artanh_grad(ball.sc * r) / r : 0.0f;
+            const float coef = (r > 0.0f) ? gd * 2.0f * artanh_grad(ball.sc * r) * rcpf(r) : 0.0f;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) gs.v[i] = coef * s.v[i];
         } else {
@@ -291,20 +293,20 @@ __global__ void __launch_bounds__(kRowThreads) k_logmap_bwd(const float* __restr
             const float mm = 1.0f - ball.c * ma.x2;
             m_clamped = mm < kMinNorm;
             m = fmaxf(mm, kMinNorm);
-            const float lam = 2.0f / m;
+            const float inv_lam = 0.5f * m;
             // out = phi(sn)/lam * s,  phi = 2 artanh(sc sn)/(sc sn)
             const float a = ball.sc * sn;
-            const float phi = 2.0f * artanh_c(a) / a;
-            const float dphi = (2.0f * artanh_grad(a) - phi) / sn;
+            const float phi = 2.0f * artanh_c(a) * rcpf(a);
+            const float dphi = (2.0f * artanh_grad(a) - phi) * rcpf(sn);
             const float gds = dot<G, EPL>(g, s);
-            const float coef = (r >= kMinNorm) ? dphi * gds / (lam * r) : 0.0f;
+            const float coef = (r >= kMinNorm) ? dphi * gds * inv_lam * rcpf(r) : 0.0f;
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) gs.v[i] = (phi / lam) * g.v[i] + coef * s.v[i];
-            glam = -phi * gds / (lam * lam);
+            for (int i = 0; i < EPL; ++i) gs.v[i] = (phi * inv_lam) * g.v[i] + coef * s.v[i];
+            glam = -phi * gds * inv_lam * inv_lam;
         }
         mobius_add_raw_bwd<G, EPL>(xr, yr, ma, gs, gxr, gyr, ball);
         // x entered negated; lambda depends on ||x||^2
-        const float gx2 = (kDist || m_clamped) ? 0.0f : glam * (2.0f / (m * m)) * ball.c;
+        const float gx2 = (kDist || m_clamped) ? 0.0f : glam * (2.0f * rcpf(m * m)) * ball.c;
 #pragma unroll
         for (int i = 0; i < EPL; ++i) gxr.v[i] = -gxr.v[i] + 2.0f * gx2 * (-xr.v[i]);
         gxr.store(gx, row, D, lg, valid);

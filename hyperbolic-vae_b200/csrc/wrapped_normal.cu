@@ -12,16 +12,17 @@ namespace hvae {
 
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2 pi))
 
-// ---- expmap with lambda given (shared with row_ops' formula; repeated here to keep TU-local inlining) ---
+// ---- reparameterised sample --------------------------------------------------------------------------
 template <int G, int EPL>
 struct SampleCtx {
     RowSlice<G, EPL> u, w, zpre;
-    float mu2, m, lam, un_raw, un, th, t, pn;
+    float mu2, m, lam, un_raw, un, th, t, sech2, pn;
     bool m_clamped, hit;
     MAddCtx ma;
 };
 
 // z = project(mu (+) tanh(sc lam ||u||/2)/sc * u/||u||),  u = (sigma*eps)/lam   (lam = lambda_mu; lambda_0 = 2 cancels)
+// Per-element divisions of the reference are hoisted into per-row reciprocals (1-2 ulp different rounding).
 template <int G, int EPL>
 __device__ __forceinline__ void sample_row(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& sig,
                                            const RowSlice<G, EPL>& eps, RowSlice<G, EPL>& z, SampleCtx<G, EPL>& k,
@@ -30,22 +31,23 @@ __device__ __forceinline__ void sample_row(const RowSlice<G, EPL>& mu, const Row
     const float m = 1.0f - ball.c * k.mu2;
     k.m_clamped = m < kMinNorm;
     k.m = fmaxf(m, kMinNorm);
-    k.lam = 2.0f / k.m;
+    k.lam = 2.0f * rcpf(k.m);
+    const float inv_lam = 0.5f * k.m;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) k.u.v[i] = (sig.v[i] * eps.v[i]) / k.lam;
-    k.un_raw = sqrtf(sqnorm<G, EPL>(k.u));
+    for (int i = 0; i < EPL; ++i) k.u.v[i] = (sig.v[i] * eps.v[i]) * inv_lam;
+    k.un_raw = sqrt_fast(sqnorm<G, EPL>(k.u));
     k.un = fmaxf(k.un_raw, kMinNorm);
-    k.th = ball.sc * ((k.lam / 2.0f) * k.un);
-    k.t = tanh_c(k.th);
-    const float q = ball.rsc * k.t;
+    k.th = ball.sc * ((k.lam * 0.5f) * k.un);
+    tanh_sech2(k.th, k.t, k.sech2);
+    const float q = ball.rsc * k.t * rcpf(k.un);
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) k.w.v[i] = q * (k.u.v[i] / k.un);
+    for (int i = 0; i < EPL; ++i) k.w.v[i] = q * k.u.v[i];
     k.ma = mobius_add_raw<G, EPL>(mu, k.w, k.zpre, ball);
     z = k.zpre;
     k.hit = project_inplace<G, EPL>(z, ball, k.pn);
 }
 
-// g: dL/dz (post-projection). Adds into gmu, writes gsig.
+// g: dL/dz (post-projection). Adds into gmu, gsig.
 template <int G, int EPL>
 __device__ __forceinline__ void sample_row_bwd(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& eps,
                                                const SampleCtx<G, EPL>& k, RowSlice<G, EPL> g,
@@ -53,23 +55,25 @@ __device__ __forceinline__ void sample_row_bwd(const RowSlice<G, EPL>& mu, const
     project_bwd<G, EPL>(g, k.zpre, k.pn, k.hit, ball);
     RowSlice<G, EPL> gx, gw;
     mobius_add_raw_bwd<G, EPL>(mu, k.w, k.ma, g, gx, gw, ball);
-    const float sech2 = (1.0f - k.t * k.t) * tanh_mask(k.th);
-    const float q = ball.rsc * k.t / k.un;
-    const float dq_dun = (sech2 * (k.lam * 0.5f) - q) / k.un;
-    const float dq_dlam = sech2 * 0.5f;
+    const float run = rcpf(k.un);
+    const float q = ball.rsc * k.t * run;
+    const float dq_dun = (k.sech2 * (k.lam * 0.5f) - q) * run;
+    const float dq_dlam = k.sech2 * 0.5f;
     const float gwu = dot<G, EPL>(gw, k.u);
-    const float coef = (k.un_raw >= kMinNorm) ? dq_dun * gwu / k.un_raw : 0.0f;
+    const float coef = (k.un_raw >= kMinNorm) ? dq_dun * gwu * rcpf(k.un_raw) : 0.0f;
     RowSlice<G, EPL> gu;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) gu.v[i] = q * gw.v[i] + coef * k.u.v[i];
     // u = v/lam: gv = gu/lam ; glam += -(gu.u)/lam
     const float guu = dot<G, EPL>(gu, k.u);
-    const float glam = dq_dlam * gwu - guu / k.lam;
-    const float gmu2 = k.m_clamped ? 0.0f : glam * (2.0f / (k.m * k.m)) * ball.c;
+    const float inv_lam = 0.5f * k.m;
+    const float glam = dq_dlam * gwu - guu * inv_lam;
+    const float rm = rcpf(k.m);
+    const float gmu2 = k.m_clamped ? 0.0f : glam * (2.0f * rm * rm) * ball.c;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
         gmu_acc.v[i] += gx.v[i] + 2.0f * gmu2 * mu.v[i];
-        gsig_acc.v[i] += (gu.v[i] / k.lam) * eps.v[i];
+        gsig_acc.v[i] += (gu.v[i] * inv_lam) * eps.v[i];
     }
 }
 
@@ -85,25 +89,41 @@ template <int G, int EPL, bool kScalarSigma>
 __device__ __forceinline__ float logprob_row(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& sig, float sigma0,
                                              const RowSlice<G, EPL>& z, LogProbCtx<G, EPL>& k, const Ball& ball, int D,
                                              int lg) {
+    if (kScalarSigma) {
+        // prior at the origin: (-0)(+)z = z exactly
+        k.s = z;
+        k.xn.zero();
+        k.ma.A = 1.0f; k.ma.B = 1.0f; k.ma.den = 1.0f; k.ma.den_clamped = false; k.ma.x2 = 0.0f; k.ma.xy = 0.0f;
+        k.ma.y2 = 0.0f;
+    } else {
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) k.xn.v[i] = -mu.v[i];
-    k.ma = mobius_add_raw<G, EPL>(k.xn, z, k.s, ball);
-    k.r = sqrtf(sqnorm<G, EPL>(k.s));
+        for (int i = 0; i < EPL; ++i) k.xn.v[i] = -mu.v[i];
+        k.ma = mobius_add_raw<G, EPL>(k.xn, z, k.s, ball);
+    }
+    k.r = sqrt_fast(sqnorm<G, EPL>(k.s));
     k.sn = fmaxf(k.r, kMinNorm);
     k.a = ball.sc * k.sn;
-    k.phi = 2.0f * artanh_c(k.a) / k.a;  // u = phi * s  (lambda_mu cancels: logmap /lam, transp *lam/2, *lambda_0)
+    const float at = artanh_c(k.a);
+    k.phi = 2.0f * at * rcpf(k.a);  // u = phi * s  (lambda_mu cancels: logmap /lam, transp *lam/2, *lambda_0)
     float acc = 0.0f;
+    if (kScalarSigma) {
+        // sum_i -(phi s_i)^2/(2 s0^2) - D log s0 - D log sqrt(2 pi)
+        const float ss = k.r * k.r;
+        acc = -(k.phi * k.phi * ss) * (0.5f * rcpf(sigma0 * sigma0)) - (float)D * (__logf(sigma0) + kHalfLog2Pi);
+    } else {
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        const int idx = lg + i * G;
-        if (idx < D) {
-            const float sg = kScalarSigma ? sigma0 : sig.v[i];
-            const float ui = k.phi * k.s.v[i];
-            acc += -(ui * ui) / (2.0f * (sg * sg)) - logf(sg) - kHalfLog2Pi;
+        for (int i = 0; i < EPL; ++i) {
+            const int idx = RowSlice<G, EPL>::index(lg, i, D);
+            if (idx < D) {
+                const float sg = sig.v[i];
+                const float ui = k.phi * k.s.v[i] * rcpf(sg);
+                acc += -0.5f * (ui * ui) - __logf(sg) - kHalfLog2Pi;
+            }
         }
+        acc = group_sum<G>(acc);
     }
-    acc = group_sum<G>(acc);
-    k.d = 2.0f * (ball.rsc * artanh_c(ball.sc * k.r));
+    // d = 2 artanh(clamp(sc r))/sc (no clamp_min on r in the reference's dist): identical to 2 at/sc unless r < 1e-15
+    k.d = (k.r >= kMinNorm) ? 2.0f * ball.rsc * at : 2.0f * ball.rsc * artanh_c(ball.sc * k.r);
     // logdetexp = (D-1) (log sinh(sc d) - log sc - log d) = (D-1) log(sinh(sc d)/(sc d))
     return acc - (float)(D - 1) * log_sinhc(ball.sc * k.d);
 }
@@ -115,31 +135,85 @@ __device__ __forceinline__ void logprob_row_bwd(const RowSlice<G, EPL>& sig, flo
                                                 RowSlice<G, EPL>& gsig_acc, RowSlice<G, EPL>& gz_acc, const Ball& ball,
                                                 int D, int lg) {
     RowSlice<G, EPL> gu;
+    const float rs0 = kScalarSigma ? rcpf(sigma0 * sigma0) : 0.0f;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
-        const int idx = lg + i * G;
-        const float sg = kScalarSigma ? sigma0 : sig.v[i];
-        const float ui = k.phi * k.s.v[i];
+        const int idx = RowSlice<G, EPL>::index(lg, i, D);
         const bool on = idx < D;
-        gu.v[i] = on ? -g * ui / (sg * sg) : 0.0f;
-        if (!kScalarSigma && on) gsig_acc.v[i] += g * ((ui * ui) / (sg * sg * sg) - 1.0f / sg);
+        const float ui = k.phi * k.s.v[i];
+        if (kScalarSigma) {
+            gu.v[i] = on ? -g * ui * rs0 : 0.0f;
+        } else {
+            const float rsg = on ? rcpf(sig.v[i]) : 0.0f;
+            const float un = ui * rsg;  // u_i / sigma_i
+            gu.v[i] = -g * un * rsg;
+            if (on) gsig_acc.v[i] += g * (un * un - 1.0f) * rsg;
+        }
     }
-    const float dphi = (2.0f * artanh_grad(k.a) - k.phi) / k.sn;
+    const float rsn = rcpf(k.sn);
+    const float dphi = (2.0f * artanh_grad(k.a) - k.phi) * rsn;
     const float gus = dot<G, EPL>(gu, k.s);
-    float coef = (k.r >= kMinNorm) ? dphi * gus / k.r : 0.0f;
+    const float rr = (k.r > 0.0f) ? rcpf(k.r) : 0.0f;
+    float coef = (k.r >= kMinNorm) ? dphi * gus * rr : 0.0f;
     // -(D-1) d/dr log_sinhc(sc d(r)),  dd/dr = 2 artanh'(sc r)
-    if (k.r > 0.0f) {
+    {
         const float dL = (float)(D - 1) * dlog_sinhc(ball.sc * k.d) * ball.sc * (2.0f * artanh_grad(ball.sc * k.r));
-        coef -= g * dL / k.r;
+        coef -= g * dL * rr;
     }
-    RowSlice<G, EPL> gs, gx, gy;
+    RowSlice<G, EPL> gs;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) gs.v[i] = k.phi * gu.v[i] + coef * k.s.v[i];
-    mobius_add_raw_bwd<G, EPL>(k.xn, z, k.ma, gs, gx, gy, ball);
+    if (kScalarSigma) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) gz_acc.v[i] += gs.v[i];
+    } else {
+        RowSlice<G, EPL> gx, gy;
+        mobius_add_raw_bwd<G, EPL>(k.xn, z, k.ma, gs, gx, gy, ball);
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            gmu_acc.v[i] -= gx.v[i];
+            gz_acc.v[i] += gy.v[i];
+        }
+    }
+}
+
+// ---- posterior log-density AT ITS OWN SAMPLE, closed form -------------------------------------------------
+// For z = rsample(mu, sigma; eps) with no clamp / projection binding, left-cancellation gives (-mu)(+)z = w, the
+// tangent vector recovered by log_prob is exactly v = sigma*eps and dist(mu, z) = |v|, so
+//   log q(z) = sum_i [-eps_i^2/2 - log sigma_i - log sqrt(2 pi)] - (D-1) log(sinh(sc |v|)/(sc |v|)),
+// independent of mu.  The reference evaluates the same quantity the long way round (logmap, transport, Normal
+// log-pdf); the two agree to rounding, this one is the better conditioned.  Rows where a clamp or the projection
+// binds take the general path (logprob_row).
+template <int G, int EPL>
+__device__ __forceinline__ bool sample_is_regular(const SampleCtx<G, EPL>& k) {
+    return !k.hit && !k.m_clamped && !k.ma.den_clamped && k.un_raw >= kMinNorm && k.th <= 8.0f;
+}
+
+template <int G, int EPL>
+__device__ __forceinline__ float logq_at_sample(const RowSlice<G, EPL>& sig, const RowSlice<G, EPL>& eps,
+                                                const SampleCtx<G, EPL>& k, const Ball& ball, int D, int lg) {
+    float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
-        gmu_acc.v[i] -= gx.v[i];
-        gz_acc.v[i] += gy.v[i];
+        const int idx = RowSlice<G, EPL>::index(lg, i, D);
+        if (idx < D) acc += -0.5f * eps.v[i] * eps.v[i] - __logf(sig.v[i]) - kHalfLog2Pi;
+    }
+    acc = group_sum<G>(acc);
+    const float nv = k.lam * k.un;  // |sigma*eps|
+    return acc - (float)(D - 1) * log_sinhc(ball.sc * nv);
+}
+
+// d log q / d sigma_i on the regular path (d/d mu = 0)
+template <int G, int EPL>
+__device__ __forceinline__ void logq_at_sample_bwd(const RowSlice<G, EPL>& sig, const RowSlice<G, EPL>& eps,
+                                                   const SampleCtx<G, EPL>& k, float g, RowSlice<G, EPL>& gsig_acc,
+                                                   const Ball& ball, int D, int lg) {
+    const float nv = k.lam * k.un;
+    const float cL = (float)(D - 1) * dlog_sinhc(ball.sc * nv) * ball.sc * rcpf(nv);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int idx = RowSlice<G, EPL>::index(lg, i, D);
+        if (idx < D) gsig_acc.v[i] += g * (-rcpf(sig.v[i]) - cL * sig.v[i] * eps.v[i] * eps.v[i]);
     }
 }
 
@@ -292,8 +366,14 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_fwd(const float* __
         SampleCtx<G, EPL> k;
         sample_row<G, EPL>(m, sg, e, zr, k, ball);
         zr.store(z, b, D, lg, valid);
-        LogProbCtx<G, EPL> kq, kp;
-        const float lq = logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
+        LogProbCtx<G, EPL> kp;
+        const bool regular = sample_is_regular<G, EPL>(k);
+        float lq = logq_at_sample<G, EPL>(sg, e, k, ball, D, lg);
+        if (__any_sync(0xffffffffu, valid && !regular)) {  // warp-uniform: the general path shuffles
+            LogProbCtx<G, EPL> kq;
+            const float lq_gen = logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
+            if (!regular) lq = lq_gen;
+        }
         const float lp = logprob_row<G, EPL, true>(zero, zero, prior_scale, zr, kp, ball, D, lg);
         if (valid && lg == 0) kl[b] = lq - lp;
     }
@@ -325,11 +405,13 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __
         const float g = (gkl && valid) ? __ldg(gkl + b) : 0.0f;
         SampleCtx<G, EPL> k;
         sample_row<G, EPL>(m, sg, e, zr, k, ball);
-        {
+        const bool regular = sample_is_regular<G, EPL>(k);
+        if (__any_sync(0xffffffffu, valid && !regular)) {  // warp-uniform: the general path shuffles
             LogProbCtx<G, EPL> kq;
             logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
-            logprob_row_bwd<G, EPL, false>(sg, 0.0f, zr, kq, g, gm, gs, gzt, ball, D, lg);
+            logprob_row_bwd<G, EPL, false>(sg, 0.0f, zr, kq, regular ? 0.0f : g, gm, gs, gzt, ball, D, lg);
         }
+        if (regular) logq_at_sample_bwd<G, EPL>(sg, e, k, g, gs, ball, D, lg);
         {
             LogProbCtx<G, EPL> kp;
             logprob_row<G, EPL, true>(zero, zero, prior_scale, zr, kp, ball, D, lg);
