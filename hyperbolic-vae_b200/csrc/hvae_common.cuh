@@ -290,11 +290,11 @@ inline int check_launch() {
     do {                                                                                          \
         if ((D) <= 2)        HVAE_ROW_LAUNCH(KERN, 1, 2, rows, stream, __VA_ARGS__);              \
         else if ((D) <= 4)   HVAE_ROW_LAUNCH(KERN, 1, 4, rows, stream, __VA_ARGS__);              \
-        else if ((D) <= 8)   HVAE_ROW_LAUNCH(KERN, 2, 4, rows, stream, __VA_ARGS__);              \
-        else if ((D) <= 16)  HVAE_ROW_LAUNCH(KERN, 4, 4, rows, stream, __VA_ARGS__);              \
-        else if ((D) <= 32)  HVAE_ROW_LAUNCH(KERN, 8, 4, rows, stream, __VA_ARGS__);              \
-        else if ((D) <= 64)  HVAE_ROW_LAUNCH(KERN, 16, 4, rows, stream, __VA_ARGS__);             \
-        else if ((D) <= 128) HVAE_ROW_LAUNCH(KERN, 32, 4, rows, stream, __VA_ARGS__);             \
+        else if ((D) <= 8)   HVAE_ROW_LAUNCH(KERN, 1, 8, rows, stream, __VA_ARGS__);              \
+        else if ((D) <= 16)  HVAE_ROW_LAUNCH(KERN, 2, 8, rows, stream, __VA_ARGS__);              \
+        else if ((D) <= 32)  HVAE_ROW_LAUNCH(KERN, 4, 8, rows, stream, __VA_ARGS__);              \
+        else if ((D) <= 64)  HVAE_ROW_LAUNCH(KERN, 8, 8, rows, stream, __VA_ARGS__);              \
+        else if ((D) <= 128) HVAE_ROW_LAUNCH(KERN, 16, 8, rows, stream, __VA_ARGS__);             \
         else if ((D) <= 256) HVAE_ROW_LAUNCH(KERN, 32, 8, rows, stream, __VA_ARGS__);             \
         else if ((D) <= 512) HVAE_ROW_LAUNCH(KERN, 32, 16, rows, stream, __VA_ARGS__);            \
         else                 HVAE_ROW_LAUNCH(KERN, 32, 32, rows, stream, __VA_ARGS__);            \

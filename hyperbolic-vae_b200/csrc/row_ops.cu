@@ -396,8 +396,8 @@ extern "C" int hvae_logmap_fwd_f32(const float* x, const float* y, float* out, i
     const Ball ball = make_ball(c);
     const int d = (int)D;
 #define L_(G_, E_) k_logmap_fwd<G_, E_, false><<<row_grid(rows, G_), kRowThreads, 0, s>>>(x, y, out, rows, d, ball)
-    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(2, 4); else if (D <= 16) L_(4, 4);
-    else if (D <= 32) L_(8, 4); else if (D <= 64) L_(16, 4); else if (D <= 128) L_(32, 4); else if (D <= 256) L_(32, 8);
+    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(1, 8); else if (D <= 16) L_(2, 8);
+    else if (D <= 32) L_(4, 8); else if (D <= 64) L_(8, 8); else if (D <= 128) L_(16, 8); else if (D <= 256) L_(32, 8);
     else if (D <= 512) L_(32, 16); else L_(32, 32);
 #undef L_
     return check_launch();
@@ -411,8 +411,8 @@ extern "C" int hvae_dist_fwd_f32(const float* x, const float* y, float* dd, int6
     const Ball ball = make_ball(c);
     const int d = (int)D;
 #define L_(G_, E_) k_logmap_fwd<G_, E_, true><<<row_grid(rows, G_), kRowThreads, 0, s>>>(x, y, dd, rows, d, ball)
-    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(2, 4); else if (D <= 16) L_(4, 4);
-    else if (D <= 32) L_(8, 4); else if (D <= 64) L_(16, 4); else if (D <= 128) L_(32, 4); else if (D <= 256) L_(32, 8);
+    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(1, 8); else if (D <= 16) L_(2, 8);
+    else if (D <= 32) L_(4, 8); else if (D <= 64) L_(8, 8); else if (D <= 128) L_(16, 8); else if (D <= 256) L_(32, 8);
     else if (D <= 512) L_(32, 16); else L_(32, 32);
 #undef L_
     return check_launch();
@@ -427,8 +427,8 @@ extern "C" int hvae_logmap_bwd_f32(const float* x, const float* y, const float* 
     const int d = (int)D;
 #define L_(G_, E_) \
     k_logmap_bwd<G_, E_, false><<<row_grid(rows, G_), kRowThreads, 0, s>>>(x, y, gout, gx, gy, rows, d, ball)
-    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(2, 4); else if (D <= 16) L_(4, 4);
-    else if (D <= 32) L_(8, 4); else if (D <= 64) L_(16, 4); else if (D <= 128) L_(32, 4); else if (D <= 256) L_(32, 8);
+    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(1, 8); else if (D <= 16) L_(2, 8);
+    else if (D <= 32) L_(4, 8); else if (D <= 64) L_(8, 8); else if (D <= 128) L_(16, 8); else if (D <= 256) L_(32, 8);
     else if (D <= 512) L_(32, 16); else L_(32, 32);
 #undef L_
     return check_launch();
@@ -443,8 +443,8 @@ extern "C" int hvae_dist_bwd_f32(const float* x, const float* y, const float* gd
     const int d = (int)D;
 #define L_(G_, E_) \
     k_logmap_bwd<G_, E_, true><<<row_grid(rows, G_), kRowThreads, 0, s>>>(x, y, gd, gx, gy, rows, d, ball)
-    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(2, 4); else if (D <= 16) L_(4, 4);
-    else if (D <= 32) L_(8, 4); else if (D <= 64) L_(16, 4); else if (D <= 128) L_(32, 4); else if (D <= 256) L_(32, 8);
+    if (D <= 2) L_(1, 2); else if (D <= 4) L_(1, 4); else if (D <= 8) L_(1, 8); else if (D <= 16) L_(2, 8);
+    else if (D <= 32) L_(4, 8); else if (D <= 64) L_(8, 8); else if (D <= 128) L_(16, 8); else if (D <= 256) L_(32, 8);
     else if (D <= 512) L_(32, 16); else L_(32, 32);
 #undef L_
     return check_launch();

@@ -345,6 +345,93 @@ __global__ void __launch_bounds__(kRowThreads) k_wrapped_logprob_bwd(const float
 }
 
 // ---- fused latent head: z = rsample, kl = log q(z) - log p(z) ------------------------------------------
+// Lean evaluation: with v = sigma*eps, every norm / inner product the sample needs follows from FOUR row
+// reductions (|mu|^2, |v|^2, <mu,v>, sum_i[-eps_i^2/2 - log sigma_i]):  w = qv*v, |w|^2 = qv^2|v|^2,
+// <mu,w> = qv<mu,v>, |z_pre|^2 = (A^2|mu|^2 + 2AB<mu,w> + B^2|w|^2)/den^2, |z| = min(|z_pre|, maxnorm) — so the
+// projection test and the whole prior density (a function of |z| only) cost no further reductions.
+template <int G, int EPL>
+struct HeadScalars {
+    float mu2, vv, muv, lqa;
+    float vn, qv, inv_lam, rz, rho, at_p;
+    bool regular;
+};
+
+template <int G, int EPL>
+__device__ __forceinline__ void head_forward(const RowSlice<G, EPL>& mu, const RowSlice<G, EPL>& sig,
+                                             const RowSlice<G, EPL>& eps, RowSlice<G, EPL>& z, SampleCtx<G, EPL>& k,
+                                             HeadScalars<G, EPL>& h, const Ball& ball, int D, int lg) {
+    float mu2 = 0.0f, vv = 0.0f, muv = 0.0f, lqa = 0.0f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int idx = RowSlice<G, EPL>::index(lg, i, D);
+        const float v = sig.v[i] * eps.v[i];
+        k.u.v[i] = v;  // holds v for now
+        mu2 = fmaf(mu.v[i], mu.v[i], mu2);
+        vv = fmaf(v, v, vv);
+        muv = fmaf(mu.v[i], v, muv);
+        if (idx < D) lqa += -0.5f * eps.v[i] * eps.v[i] - __logf(sig.v[i]) - kHalfLog2Pi;
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        mu2 += __shfl_xor_sync(0xffffffffu, mu2, o);
+        vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        muv += __shfl_xor_sync(0xffffffffu, muv, o);
+        lqa += __shfl_xor_sync(0xffffffffu, lqa, o);
+    }
+    h.mu2 = mu2; h.vv = vv; h.muv = muv; h.lqa = lqa;
+    const float c = ball.c;
+    k.mu2 = mu2;
+    const float m0 = 1.0f - c * mu2;
+    k.m_clamped = m0 < kMinNorm;
+    k.m = fmaxf(m0, kMinNorm);
+    const float rm = rcpf(k.m);
+    k.lam = 2.0f * rm;
+    h.inv_lam = 0.5f * k.m;
+    h.vn = sqrt_fast(vv);
+    k.un_raw = h.inv_lam * h.vn;
+    k.un = fmaxf(k.un_raw, kMinNorm);
+    k.th = ball.sc * (k.un * rm);
+    tanh_sech2(k.th, k.t, k.sech2);
+    const float q = ball.rsc * k.t * rcpf(k.un);
+    h.qv = q * h.inv_lam;
+    MAddCtx& ma = k.ma;
+    ma.x2 = mu2;
+    ma.y2 = h.qv * h.qv * vv;
+    ma.xy = h.qv * muv;
+    ma.A = 1.0f + 2.0f * c * ma.xy + c * ma.y2;
+    ma.B = 1.0f - c * mu2;
+    const float den0 = 1.0f + 2.0f * c * ma.xy + c * c * mu2 * ma.y2;
+    ma.den_clamped = den0 < kMinNorm;
+    ma.den = fmaxf(den0, kMinNorm);
+    const float rden = rcpf(ma.den);
+    const float ar = ma.A * rden, br = ma.B * rden * h.qv;
+    const float nz2 = fmaxf(ma.A * ma.A * mu2 + 2.0f * ma.A * ma.B * ma.xy + ma.B * ma.B * ma.y2, 0.0f) * rden * rden;
+    const float nz = sqrt_fast(nz2);
+    k.pn = fmaxf(nz, kMinNorm);
+    k.hit = k.pn > ball.maxnorm;
+    const float scale = k.hit ? ball.maxnorm * rcpf(k.pn) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const float v = k.u.v[i];
+        k.u.v[i] = v * h.inv_lam;
+        k.w.v[i] = v * h.qv;
+        k.zpre.v[i] = fmaf(ar, mu.v[i], br * v);
+        z.v[i] = k.zpre.v[i] * scale;
+    }
+    h.rz = k.hit ? ball.maxnorm * (nz * rcpf(k.pn)) : nz;
+    // prior WrappedNormal(0, sigma0): u_p = rho * z/|z|, rho = 2 artanh(sc |z|)/sc = dist(0, z)
+    const float rzc = fmaxf(h.rz, kMinNorm);
+    h.at_p = artanh_c(ball.sc * rzc);
+    h.rho = (h.rz >= kMinNorm) ? 2.0f * ball.rsc * h.at_p : 2.0f * h.at_p * rcpf(ball.sc * rzc) * h.rz;
+    h.regular = !k.hit && !k.m_clamped && !ma.den_clamped && k.un_raw >= kMinNorm && k.th <= 8.0f;
+}
+
+template <int G, int EPL>
+__device__ __forceinline__ float head_logp(const HeadScalars<G, EPL>& h, float sigma0, const Ball& ball, int D) {
+    return -(h.rho * h.rho) * (0.5f * rcpf(sigma0 * sigma0)) - (float)D * (__logf(sigma0) + kHalfLog2Pi) -
+           (float)(D - 1) * log_sinhc(ball.sc * h.rho);
+}
+
 template <int G, int EPL>
 __global__ void __launch_bounds__(kRowThreads) k_latent_head_fwd(const float* __restrict__ mu, const float* __restrict__ sigma,
                                                                   const float* __restrict__ eps, float prior_scale,
@@ -354,7 +441,7 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_fwd(const float* __
     for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
         const int64_t b = r0 + sub;
         const bool valid = b < B;
-        RowSlice<G, EPL> m, sg, e, zr, zero;
+        RowSlice<G, EPL> m, sg, e, zr;
         m.load(mu, b, D, lg, valid);
         sg.load(sigma, b, D, lg, valid);
         if (!valid) {
@@ -362,20 +449,17 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_fwd(const float* __
             for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
         }
         e.load(eps, b, D, lg, valid);
-        zero.zero();
         SampleCtx<G, EPL> k;
-        sample_row<G, EPL>(m, sg, e, zr, k, ball);
+        HeadScalars<G, EPL> h;
+        head_forward<G, EPL>(m, sg, e, zr, k, h, ball, D, lg);
         zr.store(z, b, D, lg, valid);
-        LogProbCtx<G, EPL> kp;
-        const bool regular = sample_is_regular<G, EPL>(k);
-        float lq = logq_at_sample<G, EPL>(sg, e, k, ball, D, lg);
-        if (__any_sync(0xffffffffu, valid && !regular)) {  // warp-uniform: the general path shuffles
+        float lq = h.lqa - (float)(D - 1) * log_sinhc(ball.sc * h.vn);
+        if (__any_sync(0xffffffffu, valid && !h.regular)) {  // warp-uniform: the general path shuffles
             LogProbCtx<G, EPL> kq;
             const float lq_gen = logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
-            if (!regular) lq = lq_gen;
+            if (!h.regular) lq = lq_gen;
         }
-        const float lp = logprob_row<G, EPL, true>(zero, zero, prior_scale, zr, kp, ball, D, lg);
-        if (valid && lg == 0) kl[b] = lq - lp;
+        if (valid && lg == 0) kl[b] = lq - head_logp<G, EPL>(h, prior_scale, ball, D);
     }
 }
 
@@ -389,7 +473,7 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __
     for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
         const int64_t b = r0 + sub;
         const bool valid = b < B;
-        RowSlice<G, EPL> m, sg, e, zr, zero, gm, gs, gzt, dummy;
+        RowSlice<G, EPL> m, sg, e, zr, gm, gs, gzt;
         m.load(mu, b, D, lg, valid);
         sg.load(sigma, b, D, lg, valid);
         if (!valid) {
@@ -397,25 +481,34 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __
             for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
         }
         e.load(eps, b, D, lg, valid);
-        zero.zero();
         gm.zero();
         gs.zero();
-        dummy.zero();
         if (gz) gzt.load(gz, b, D, lg, valid); else gzt.zero();
         const float g = (gkl && valid) ? __ldg(gkl + b) : 0.0f;
         SampleCtx<G, EPL> k;
-        sample_row<G, EPL>(m, sg, e, zr, k, ball);
-        const bool regular = sample_is_regular<G, EPL>(k);
-        if (__any_sync(0xffffffffu, valid && !regular)) {  // warp-uniform: the general path shuffles
+        HeadScalars<G, EPL> h;
+        head_forward<G, EPL>(m, sg, e, zr, k, h, ball, D, lg);
+        // -g * d log p / dz :  log p = f(|z|),  f' = [-rho/s0^2 - (D-1) sc L'(sc rho)] * 2 artanh'(sc |z|)
+        {
+            const float fp = (-h.rho * rcpf(prior_scale * prior_scale) - (float)(D - 1) * ball.sc * dlog_sinhc(ball.sc * h.rho)) *
+                             (2.0f * artanh_grad(ball.sc * h.rz));
+            const float coef = (h.rz >= kMinNorm) ? -g * fp * rcpf(h.rz) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) gzt.v[i] = fmaf(coef, zr.v[i], gzt.v[i]);
+        }
+        if (__any_sync(0xffffffffu, valid && !h.regular)) {  // warp-uniform: the general path shuffles
             LogProbCtx<G, EPL> kq;
             logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
-            logprob_row_bwd<G, EPL, false>(sg, 0.0f, zr, kq, regular ? 0.0f : g, gm, gs, gzt, ball, D, lg);
+            logprob_row_bwd<G, EPL, false>(sg, 0.0f, zr, kq, h.regular ? 0.0f : g, gm, gs, gzt, ball, D, lg);
         }
-        if (regular) logq_at_sample_bwd<G, EPL>(sg, e, k, g, gs, ball, D, lg);
-        {
-            LogProbCtx<G, EPL> kp;
-            logprob_row<G, EPL, true>(zero, zero, prior_scale, zr, kp, ball, D, lg);
-            logprob_row_bwd<G, EPL, true>(zero, prior_scale, zr, kp, -g, dummy, dummy, gzt, ball, D, lg);
+        if (h.regular) {
+            // d log q / d sigma_i = -1/sigma_i - (D-1) sc L'(sc |v|) sigma_i eps_i^2 / |v|   (d/d mu = 0)
+            const float cL = (float)(D - 1) * dlog_sinhc(ball.sc * h.vn) * ball.sc * rcpf(h.vn);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const int idx = RowSlice<G, EPL>::index(lg, i, D);
+                if (idx < D) gs.v[i] += g * (-rcpf(sg.v[i]) - cL * sg.v[i] * e.v[i] * e.v[i]);
+            }
         }
         sample_row_bwd<G, EPL>(m, e, k, gzt, gm, gs, ball);
         gm.store(gmu, b, D, lg, valid);
@@ -435,11 +528,11 @@ using namespace hvae;
     do {                                                                                                             \
         if ((D) <= 2)        KERN<1, 2, TARG><<<row_grid((rows), 1), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
         else if ((D) <= 4)   KERN<1, 4, TARG><<<row_grid((rows), 1), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
-        else if ((D) <= 8)   KERN<2, 4, TARG><<<row_grid((rows), 2), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
-        else if ((D) <= 16)  KERN<4, 4, TARG><<<row_grid((rows), 4), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
-        else if ((D) <= 32)  KERN<8, 4, TARG><<<row_grid((rows), 8), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
-        else if ((D) <= 64)  KERN<16, 4, TARG><<<row_grid((rows), 16), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
-        else if ((D) <= 128) KERN<32, 4, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
+        else if ((D) <= 8)   KERN<1, 8, TARG><<<row_grid((rows), 1), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 16)  KERN<2, 8, TARG><<<row_grid((rows), 2), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 32)  KERN<4, 8, TARG><<<row_grid((rows), 4), kRowThreads, 0, (s)>>>(__VA_ARGS__);             \
+        else if ((D) <= 64)  KERN<8, 8, TARG><<<row_grid((rows), 8), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
+        else if ((D) <= 128) KERN<16, 8, TARG><<<row_grid((rows), 16), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
         else if ((D) <= 256) KERN<32, 8, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);           \
         else if ((D) <= 512) KERN<32, 16, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);          \
         else                 KERN<32, 32, TARG><<<row_grid((rows), 32), kRowThreads, 0, (s)>>>(__VA_ARGS__);          \

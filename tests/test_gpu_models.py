@@ -72,8 +72,9 @@ def test_model_step_matches_reference(golden_models, name, fused):
     losses["loss_total"].backward()
     l64, g64 = _oracle64(name, g)
     for k, v in g["losses"].items():
-        assert_parity(losses[k].reshape(1), v.reshape(1), l64[k].reshape(1), what="%s %s" % (name, k), rtol=1e-5, atol=1e-6,
-                      row_relative=False, slack_mult=2.0)
+        # the KL is a batch sum of (log q - log p): a cancelling sum of O(1..10) terms per row -> absolute floor
+        assert_parity(losses[k].reshape(1), v.reshape(1), l64[k].reshape(1), what="%s %s" % (name, k), rtol=1e-5,
+                      atol=1e-5 if "kl" in k else 1e-6, row_relative=False, slack_mult=2.0)
     grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(grads) == set(g["grads"]), set(grads) ^ set(g["grads"])
     for k, v in g["grads"].items():
