@@ -302,6 +302,10 @@ inline int check_launch() {
 
 constexpr int kMaxRowDim = 1024;
 
+// Rows in flight per lane group.  At D <= 4 a row is 8-16 bytes: with one row per thread the kernels are bound by
+// memory-level parallelism (bytes in flight per SM), not bandwidth; loading U rows before the math fixes that.
+#define HVAE_ROW_UNROLL(EPL) ((EPL) <= 2 ? 4 : ((EPL) <= 4 ? 2 : 1))
+
 // rows owned per warp-iteration and the lane's place in its group
 #define HVAE_ROW_PROLOGUE(G)                                                  \
     const int lane = threadIdx.x & 31;                                        \

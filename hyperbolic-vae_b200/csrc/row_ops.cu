@@ -12,15 +12,20 @@ template <int G, int EPL>
 __global__ void __launch_bounds__(kRowThreads) k_expmap0_fwd(const float* __restrict__ u, float* __restrict__ y,
                                                               int64_t rows, int D, Ball ball) {
     HVAE_ROW_PROLOGUE(G)
-    for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
-        const int64_t row = r0 + sub;
-        const bool valid = row < rows;
-        RowSlice<G, EPL> ur, yr;
-        ur.load(u, row, D, lg, valid);
-        float n_raw, n, t, pn;
-        expmap0_row<G, EPL>(ur, yr, ball, n_raw, n, t);
-        project_inplace<G, EPL>(yr, ball, pn);
-        yr.store(y, row, D, lg, valid);
+    constexpr int U = HVAE_ROW_UNROLL(EPL);
+    for (int64_t r0 = warp_global * (RPW * U); r0 < rows; r0 += warps_total * (RPW * U)) {
+        RowSlice<G, EPL> ur[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) ur[j].load(u, r0 + j * RPW + sub, D, lg, r0 + j * RPW + sub < rows);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t row = r0 + j * RPW + sub;
+            RowSlice<G, EPL> yr;
+            float n_raw, n, t, pn;
+            expmap0_row<G, EPL>(ur[j], yr, ball, n_raw, n, t);
+            project_inplace<G, EPL>(yr, ball, pn);
+            yr.store(y, row, D, lg, row < rows);
+        }
     }
 }
 
@@ -28,14 +33,21 @@ template <int G, int EPL>
 __global__ void __launch_bounds__(kRowThreads) k_expmap0_bwd(const float* __restrict__ u, const float* __restrict__ gy,
                                                               float* __restrict__ gu, int64_t rows, int D, Ball ball) {
     HVAE_ROW_PROLOGUE(G)
-    for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
-        const int64_t row = r0 + sub;
-        const bool valid = row < rows;
-        RowSlice<G, EPL> ur, g;
-        ur.load(u, row, D, lg, valid);
-        g.load(gy, row, D, lg, valid);
-        expmap0_row_bwd<G, EPL>(ur, g, ball);
-        g.store(gu, row, D, lg, valid);
+    constexpr int U = HVAE_ROW_UNROLL(EPL);
+    for (int64_t r0 = warp_global * (RPW * U); r0 < rows; r0 += warps_total * (RPW * U)) {
+        RowSlice<G, EPL> ur[U], g[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t row = r0 + j * RPW + sub;
+            ur[j].load(u, row, D, lg, row < rows);
+            g[j].load(gy, row, D, lg, row < rows);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t row = r0 + j * RPW + sub;
+            expmap0_row_bwd<G, EPL>(ur[j], g[j], ball);
+            g[j].store(gu, row, D, lg, row < rows);
+        }
     }
 }
 

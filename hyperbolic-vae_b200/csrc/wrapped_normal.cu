@@ -227,17 +227,26 @@ __global__ void __launch_bounds__(kRowThreads) k_wrapped_sample_fwd(const float*
                                                                      int64_t S, int64_t B, int D, Ball ball) {
     HVAE_ROW_PROLOGUE(G)
     const int64_t rows = S * B;
-    for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warps_total * RPW) {
-        const int64_t row = r0 + sub;
-        const bool valid = row < rows;
-        const int64_t b = valid ? row % B : 0;
-        RowSlice<G, EPL> m, sg, e, zr;
-        m.load(mu, b, D, lg, valid);
-        sg.load(sigma, b, D, lg, valid);
-        e.load(eps, row, D, lg, valid);
-        SampleCtx<G, EPL> k;
-        sample_row<G, EPL>(m, sg, e, zr, k, ball);
-        zr.store(z, row, D, lg, valid);
+    constexpr int U = HVAE_ROW_UNROLL(EPL);
+    for (int64_t r0 = warp_global * (RPW * U); r0 < rows; r0 += warps_total * (RPW * U)) {
+        RowSlice<G, EPL> m[U], sg[U], e[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t row = r0 + j * RPW + sub;
+            const bool valid = row < rows;
+            const int64_t b = valid ? row % B : 0;
+            m[j].load(mu, b, D, lg, valid);
+            sg[j].load(sigma, b, D, lg, valid);
+            e[j].load(eps, row, D, lg, valid);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t row = r0 + j * RPW + sub;
+            RowSlice<G, EPL> zr;
+            SampleCtx<G, EPL> k;
+            sample_row<G, EPL>(m[j], sg[j], e[j], zr, k, ball);
+            zr.store(z, row, D, lg, row < rows);
+        }
     }
 }
 
@@ -438,31 +447,50 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_fwd(const float* __
                                                                   float* __restrict__ z, float* __restrict__ kl, int64_t B,
                                                                   int D, Ball ball) {
     HVAE_ROW_PROLOGUE(G)
-    for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
-        const int64_t b = r0 + sub;
-        const bool valid = b < B;
-        RowSlice<G, EPL> m, sg, e, zr;
-        m.load(mu, b, D, lg, valid);
-        sg.load(sigma, b, D, lg, valid);
-        if (!valid) {
+    constexpr int U = HVAE_ROW_UNROLL(EPL);
+    for (int64_t r0 = warp_global * (RPW * U); r0 < B; r0 += warps_total * (RPW * U)) {
+        RowSlice<G, EPL> mm[U], ss[U], ee[U];
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
+        for (int j = 0; j < U; ++j) {
+            const int64_t b = r0 + j * RPW + sub;
+            const bool valid = b < B;
+            mm[j].load(mu, b, D, lg, valid);
+            ss[j].load(sigma, b, D, lg, valid);
+            if (!valid) {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) ss[j].v[i] = 1.0f;
+            }
+            ee[j].load(eps, b, D, lg, valid);
         }
-        e.load(eps, b, D, lg, valid);
-        SampleCtx<G, EPL> k;
-        HeadScalars<G, EPL> h;
-        head_forward<G, EPL>(m, sg, e, zr, k, h, ball, D, lg);
-        zr.store(z, b, D, lg, valid);
-        float lq = h.lqa - (float)(D - 1) * log_sinhc(ball.sc * h.vn);
-        if (__any_sync(0xffffffffu, valid && !h.regular)) {  // warp-uniform: the general path shuffles
-            LogProbCtx<G, EPL> kq;
-            const float lq_gen = logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
-            if (!h.regular) lq = lq_gen;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t b = r0 + j * RPW + sub;
+            const bool valid = b < B;
+            const RowSlice<G, EPL>& m = mm[j];
+            const RowSlice<G, EPL>& sg = ss[j];
+            const RowSlice<G, EPL>& e = ee[j];
+            RowSlice<G, EPL> zr;
+            SampleCtx<G, EPL> k;
+            HeadScalars<G, EPL> h;
+            head_forward<G, EPL>(m, sg, e, zr, k, h, ball, D, lg);
+            zr.store(z, b, D, lg, valid);
+            float lq = h.lqa - (float)(D - 1) * log_sinhc(ball.sc * h.vn);
+            if (__any_sync(0xffffffffu, valid && !h.regular)) {  // warp-uniform: the general path shuffles
+                LogProbCtx<G, EPL> kq;
+                const float lq_gen = logprob_row<G, EPL, false>(m, sg, 0.0f, zr, kq, ball, D, lg);
+                if (!h.regular) lq = lq_gen;
+            }
+            if (valid && lg == 0) kl[b] = lq - head_logp<G, EPL>(h, prior_scale, ball, D);
         }
-        if (valid && lg == 0) kl[b] = lq - head_logp<G, EPL>(h, prior_scale, ball, D);
     }
 }
 
+// Backward of the head in closed form.  z_pre = a mu + b v with a = A/den, b = B qv/den and every scalar a
+// function of (|mu|^2, |v|^2, <mu,v>), so with H = dL/dz the pull-back needs only two more reductions (<H,mu>, <H,v>):
+//   h' = project^T H;  g_a = <h',mu>, g_b = <h',v>;  scalar chain -> g_|mu|^2, g_|v|^2, g_<mu,v>;
+//   g_mu = a h' + 2 g_mu2 mu + g_muv v ;  g_v = b h' + 2 g_vv v + g_muv mu ;  g_sigma = g_v * eps.
+// qv = tanh(sc|v|/2)/(sc|v|) depends on |v| only (lambda_mu cancels).  Rows where a clamp binds (m, |u|, den)
+// take the general path.
 template <int G, int EPL>
 __global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __restrict__ mu, const float* __restrict__ sigma,
                                                                   const float* __restrict__ eps, float prior_scale,
@@ -470,25 +498,39 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __
                                                                   float* __restrict__ gmu, float* __restrict__ gsigma,
                                                                   int64_t B, int D, Ball ball) {
     HVAE_ROW_PROLOGUE(G)
-    for (int64_t r0 = warp_global * RPW; r0 < B; r0 += warps_total * RPW) {
-        const int64_t b = r0 + sub;
-        const bool valid = b < B;
-        RowSlice<G, EPL> m, sg, e, zr, gm, gs, gzt;
-        m.load(mu, b, D, lg, valid);
-        sg.load(sigma, b, D, lg, valid);
-        if (!valid) {
+    constexpr int U = HVAE_ROW_UNROLL(EPL);
+    for (int64_t r0 = warp_global * (RPW * U); r0 < B; r0 += warps_total * (RPW * U)) {
+      RowSlice<G, EPL> mm[U], ss[U], ee[U], gg[U];
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) sg.v[i] = 1.0f;
-        }
-        e.load(eps, b, D, lg, valid);
+      for (int j = 0; j < U; ++j) {
+          const int64_t bj = r0 + j * RPW + sub;
+          const bool vj = bj < B;
+          mm[j].load(mu, bj, D, lg, vj);
+          ss[j].load(sigma, bj, D, lg, vj);
+          if (!vj) {
+#pragma unroll
+              for (int i = 0; i < EPL; ++i) ss[j].v[i] = 1.0f;
+          }
+          ee[j].load(eps, bj, D, lg, vj);
+          if (gz) gg[j].load(gz, bj, D, lg, vj); else gg[j].zero();
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int64_t b = r0 + j * RPW + sub;
+        const bool valid = b < B;
+        const RowSlice<G, EPL>& m = mm[j];
+        const RowSlice<G, EPL>& sg = ss[j];
+        const RowSlice<G, EPL>& e = ee[j];
+        RowSlice<G, EPL> zr, gm, gs;
+        RowSlice<G, EPL>& gzt = gg[j];
         gm.zero();
         gs.zero();
-        if (gz) gzt.load(gz, b, D, lg, valid); else gzt.zero();
         const float g = (gkl && valid) ? __ldg(gkl + b) : 0.0f;
         SampleCtx<G, EPL> k;
         HeadScalars<G, EPL> h;
         head_forward<G, EPL>(m, sg, e, zr, k, h, ball, D, lg);
-        // -g * d log p / dz :  log p = f(|z|),  f' = [-rho/s0^2 - (D-1) sc L'(sc rho)] * 2 artanh'(sc |z|)
+        const float c = ball.c;
+        // H = gz - g * d log p / dz :  log p = f(|z|),  f' = [-rho/s0^2 - (D-1) sc L'(sc rho)] * 2 artanh'(sc |z|)
         {
             const float fp = (-h.rho * rcpf(prior_scale * prior_scale) - (float)(D - 1) * ball.sc * dlog_sinhc(ball.sc * h.rho)) *
                              (2.0f * artanh_grad(ball.sc * h.rz));
@@ -510,9 +552,68 @@ __global__ void __launch_bounds__(kRowThreads) k_latent_head_bwd(const float* __
                 if (idx < D) gs.v[i] += g * (-rcpf(sg.v[i]) - cL * sg.v[i] * e.v[i] * e.v[i]);
             }
         }
-        sample_row_bwd<G, EPL>(m, e, k, gzt, gm, gs, ball);
+        const bool clamp_free = !k.m_clamped && !k.ma.den_clamped && k.un_raw >= kMinNorm;
+        if (__any_sync(0xffffffffu, valid && !clamp_free)) {
+            RowSlice<G, EPL> gm2, gs2;
+            gm2.zero();
+            gs2.zero();
+            sample_row_bwd<G, EPL>(m, e, k, gzt, gm2, gs2, ball);
+            if (!clamp_free) {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) { gm.v[i] += gm2.v[i]; gs.v[i] += gs2.v[i]; }
+            }
+        }
+        {
+            // two reductions: <H, mu>, <H, v>   (v = sigma*eps = u / inv_lam; use w = qv v to avoid recomputing)
+            float hm = 0.0f, hv = 0.0f;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                hm = fmaf(gzt.v[i], m.v[i], hm);
+                hv = fmaf(gzt.v[i], sg.v[i] * e.v[i], hv);
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                hm += __shfl_xor_sync(0xffffffffu, hm, o);
+                hv += __shfl_xor_sync(0xffffffffu, hv, o);
+            }
+            if (clamp_free) {
+                const MAddCtx& ma = k.ma;
+                const float rden = rcpf(ma.den);
+                const float a = ma.A * rden, bq = ma.B * h.qv * rden;
+                // projection: h' = s (H - (<H,zpre>/n^2) zpre)
+                float s = 1.0f, pr = 0.0f;
+                if (k.hit) {
+                    const float rn = rcpf(k.pn);
+                    s = ball.maxnorm * rn;
+                    pr = (a * hm + bq * hv) * rn * rn;
+                }
+                const float zm = a * h.mu2 + bq * h.muv;   // <zpre, mu>
+                const float zv = a * h.muv + bq * h.vv;    // <zpre, v>
+                const float ga = s * (hm - pr * zm);       // <h', mu>
+                const float gb = s * (hv - pr * zv);       // <h', v>
+                const float gA = ga * rden;
+                const float gB = gb * h.qv * rden;
+                float gqv = gb * ma.B * rden;
+                const float gden = -(ga * a + gb * bq) * rden;
+                const float gxy = 2.0f * c * (gA + gden);
+                const float gy2 = c * gA + c * c * h.mu2 * gden;
+                const float gmu2 = -c * gB + c * c * ma.y2 * gden;
+                gqv += gxy * h.muv + gy2 * 2.0f * h.qv * h.vv;
+                const float gmuv = gxy * h.qv;
+                // qv = tanh(sc|v|/2)/(sc|v|):  d qv / d vv = (sech^2/2 - qv) / (2 vv)
+                const float gvv = gy2 * h.qv * h.qv + gqv * (0.5f * k.sech2 - h.qv) * (0.5f * rcpf(h.vv));
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    const float v = sg.v[i] * e.v[i];
+                    const float hp = s * (gzt.v[i] - pr * k.zpre.v[i]);
+                    gm.v[i] += a * hp + 2.0f * gmu2 * m.v[i] + gmuv * v;
+                    gs.v[i] += (bq * hp + 2.0f * gvv * v + gmuv * m.v[i]) * e.v[i];
+                }
+            }
+        }
         gm.store(gmu, b, D, lg, valid);
         gs.store(gsigma, b, D, lg, valid);
+      }
     }
 }
 
