@@ -52,7 +52,7 @@ def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5, pk=None, squa
         # (squared outputs: d(out^2) = 2|out| d(out))
         amp = 1.0 + 2.0 * torch.Tensor(o64[0].detach()).double().abs().sqrt() if squared else 1.0
         atol_out = atol + 3e-6 * pk * amp
-        rg = 1e-5 + 3e-6 * pk.amax(dim=1, keepdim=True)
+        rg = 1e-5 + 4e-6 * pk.amax(dim=1, keepdim=True)
         pg_rows = torch.clamp(1e-5 * pk.amax(dim=0), min=pg_tol, max=5e-2)  # per plane
     else:
         atol_out, rg = atol, rtol
