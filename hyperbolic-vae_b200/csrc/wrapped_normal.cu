@@ -442,12 +442,12 @@ __device__ __forceinline__ float head_logp(const HeadScalars<G, EPL>& h, float s
 }
 
 template <int G, int EPL>
-__global__ void __launch_bounds__(kRowThreads, 3) k_latent_head_fwd(const float* __restrict__ mu, const float* __restrict__ sigma,
+__global__ void __launch_bounds__(kRowThreads, (EPL >= 8) ? 3 : 1) k_latent_head_fwd(const float* __restrict__ mu, const float* __restrict__ sigma,
                                                                   const float* __restrict__ eps, float prior_scale,
                                                                   float* __restrict__ z, float* __restrict__ kl, int64_t B,
                                                                   int D, Ball ball) {
     HVAE_ROW_PROLOGUE(G)
-    constexpr int U = (EPL <= 2) ? 2 : 1;
+    constexpr int U = 1;
     for (int64_t r0 = warp_global * (RPW * U); r0 < B; r0 += warps_total * (RPW * U)) {
         RowSlice<G, EPL> mm[U], ss[U], ee[U];
 #pragma unroll
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) k_latent_head_fwd(const float*
 // qv = tanh(sc|v|/2)/(sc|v|) depends on |v| only (lambda_mu cancels).  Rows where a clamp binds (m, |u|, den)
 // take the general path.
 template <int G, int EPL>
-__global__ void __launch_bounds__(kRowThreads, 2) k_latent_head_bwd(const float* __restrict__ mu, const float* __restrict__ sigma,
+__global__ void __launch_bounds__(kRowThreads, (EPL >= 8) ? 2 : 1) k_latent_head_bwd(const float* __restrict__ mu, const float* __restrict__ sigma,
                                                                   const float* __restrict__ eps, float prior_scale,
                                                                   const float* __restrict__ gz, const float* __restrict__ gkl,
                                                                   float* __restrict__ gmu, float* __restrict__ gsigma,

@@ -106,9 +106,14 @@ def test_golden_gyroplane_and_geodesic(golden_ops):
             cu = _cuda_layer_run(layer, params, g["x"], g["gout"])
             o64 = _oracle_layer_run(make_o, params, g["x"], g["gout"], torch.float64)
             gold = (g["out"], g["gx"], {k: g["g" + k] for k in names})
-            pk = None
             if kind != "geodesic":
                 pk = pair_kappa(rec["c"], g["x"], g["points"])
+            else:  # p = transported weight
+                from oracle import ref_port as R
+                lay = R.GeodesicLayer(D, P, _oball(c))
+                with torch.no_grad():
+                    lay._weight.copy_(g["_weight"]); lay._bias.copy_(g["_bias"])
+                    pk = pair_kappa(rec["c"], g["x"], lay.weight)
             _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64, pk=pk, squared=(kind == "squared"))
 
 
