@@ -31,13 +31,16 @@ constexpr int BM = 128, BN = 128, BK = 64;   // BK * sizeof(bf16) = 128 B = one 
 constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int UMMA_K = 16;
-constexpr int THREADS = 192;
+constexpr int CG = 4;                        // epilogue column groups: 4*CG epilogue warps, each BN/CG columns
+constexpr int EPI_WARPS = 4 * CG;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t COLC_BYTES = ACC_STAGES * BN * 16 + ACC_STAGES * BN * 4;  // per-column float4 constants + bias
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
 
-enum { EPI_PLAIN = 0, EPI_GYRO = 1 };
+enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3 };
 
 struct Params {
     float* D;              // (M, N) row-major output
@@ -48,6 +51,11 @@ struct Params {
     const float* p2;       // GYRO: (N,) |p|^2
     const float* bias;     // GYRO: optional (N,)
     GyroParams gp;
+    const float* xrow;     // ROWDOT: (M, N) fp32 rows dotted with the accumulator rows
+    float* rowdot;         // ROWDOT: [n_tiles][M] partial sums of acc * xrow
+    const float* mxsq;     // MOBIUS: [q_tiles][M] partials of |mx_b|^2 (from the Gram row-dot pass)
+    int q_tiles;
+    Ball ball;             // MOBIUS
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,7 +153,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -201,44 +209,113 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        // ===== epilogue: warp w owns TMEM lane quarter (w % 4) and column group (w - 2) / 4 =====
         const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;  // 0 .. 32*EPI_WARPS-1
+        float4* colc = reinterpret_cast<float4*>(smem_raw + (bars + 256u - raw));            // [ACC_STAGES][BN]
+        float* colb = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw) + ACC_STAGES * BN * 16);
         int as = 0;
         uint32_t aphase = 0;
+        constexpr int COLS = BN / CG;
         for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int64_t mt = t / n_tiles, nt = t % n_tiles;
             const int64_t m = mt * BM + q * 32 + lane;
-            mbar_wait(tfull_bar(as), aphase);
-            tc_fence_after();
             const bool row_ok = m < prm.M;
-            float rs = 1.0f, x2 = 0.0f, sq = 0.0f;
+            if (EPI == EPI_GYRO) {
+                // per-column constants of this tile: {|p|^2, 1 - c|p|^2, c^2 |p|^2, |p|} (+ bias), once per tile
+                if (et < BN) {
+                    const int64_t n = nt * BN + et;
+                    const float p2 = (n < prm.N) ? __ldg(prm.p2 + n) : 0.0f;
+                    const float c = prm.gp.c;
+                    colc[as * BN + et] = make_float4(p2, 1.0f - c * p2, c * c * p2, sqrt_fast(p2));
+                    colb[as * BN + et] = (prm.bias && n < prm.N) ? __ldg(prm.bias + n) : 0.0f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            }
+            float rs = 1.0f, x2 = 0.0f, acc_row = 0.0f;
             if (EPI == EPI_PLAIN && prm.rowscale && row_ok) rs = __ldg(prm.rowscale + m);
             if (EPI == EPI_GYRO && row_ok) x2 = __ldg(prm.x2 + m);
+            if (EPI == EPI_MOBIUS) {
+                // y = psi(|x|, |mx|) mx with |mx|^2 from the Gram pass; projection folded into the scale
+                float mx2 = 0.0f;
+                if (row_ok) {
+                    x2 = __ldg(prm.x2 + m);
+                    for (int qt = 0; qt < prm.q_tiles; ++qt) mx2 += __ldg(prm.mxsq + (int64_t)qt * prm.M + m);
+                }
+                mx2 = fmaxf(mx2, 0.0f);
+                const Ball& bl = prm.ball;
+                const float xn = fmaxf(sqrt_fast(x2), kMinNorm);
+                const float mxn_raw = sqrt_fast(mx2), mxn = fmaxf(mxn_raw, kMinNorm);
+                const float th = mxn * rcpf(xn) * artanh_c(bl.sc * xn);
+                const float tt = tanh_c(th);
+                rs = bl.rsc * tt * rcpf(mxn);
+                const float yn = fmaxf(bl.rsc * tt * (mxn_raw * rcpf(mxn)), kMinNorm);
+                if (yn > bl.maxnorm) rs = rs * rcpf(yn) * bl.maxnorm;
+                if (mx2 == 0.0f) rs = 0.0f;
+            }
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
 #pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
+            for (int cb = cg * COLS; cb < (cg + 1) * COLS; cb += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb), v);
                 const int64_t n0 = nt * BN + cb;
                 if (EPI == EPI_PLAIN) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        sq = fmaf(v[i], v[i], sq);  // out-of-range columns are TMA zero-filled -> contribute 0
+                        acc_row = fmaf(v[i], v[i], acc_row);  // out-of-range columns are TMA zero-filled -> contribute 0
                         v[i] *= rs;
                     }
-                } else {
+                } else if (EPI == EPI_MOBIUS) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int64_t n = n0 + i;
-                        if (n < prm.N) {
-                            const float p2 = __ldg(prm.p2 + n);
+                    for (int i = 0; i < 32; ++i) v[i] *= rs;
+                } else if (EPI == EPI_ROWDOT) {
+                    if (row_ok) {
+                        const float* xr = prm.xrow + m * prm.N + n0;
+                        if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + i));
+                                acc_row = fmaf(v[i], xv.x, fmaf(v[i + 1], xv.y, fmaf(v[i + 2], xv.z, fmaf(v[i + 3], xv.w, acc_row))));
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < prm.N) acc_row = fmaf(v[i], __ldg(xr + i), acc_row);
+                        }
+                    }
+                } else {
+                    const bool lean = (prm.gp.flags & ~(uint32_t)HVAE_GYRO_SIGNED) == 0u && (prm.gp.flags & HVAE_GYRO_SIGNED);
+                    const float c = prm.gp.c, two_c = 2.0f * c, sc2 = 2.0f * prm.gp.sc, rsc = prm.gp.rsc;
+                    const float rowA0 = fmaf(c, x2, 1.0f);
+                    if (lean) {
+                        // geoopt signed distance, a == p (the decoder's configuration): ~25 FMA + 4 MUFU per output
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float4 cc = colc[as * BN + cb + i];  // {p2, Bc, c^2 p2, |p|}  (smem broadcast)
+                            const float px = v[i];
+                            const float A = fmaf(-two_c, px, rowA0);
+                            const float den = fmaxf(fmaf(cc.z, x2, fmaf(-two_c, px, 1.0f)), kMinNorm);
+                            const float rden = rcpf(den);
+                            const float N1 = fmaf(cc.y, px, -A * cc.x);
+                            const float N2 = fmaxf(fmaf(A, fmaf(A, cc.x, -2.0f * cc.y * px), cc.y * cc.y * x2), 0.0f);
+                            const float da = N1 * rden;
+                            const float dn2 = fmaxf(N2 * rden * rden, kMinNorm);
+                            const float w = (1.0f - c * dn2) * cc.w;
+                            const float denom = copysignf(fabsf(w) + kMinNorm, w);
+                            const float y = sc2 * da * rcpf(denom);
+                            v[i] = fmaf(asinh_fast(y), rsc, colb[as * BN + cb + i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float4 cc = colc[as * BN + cb + i];
                             GyroPairCtx k;
-                            float o = gyro_pair_fwd(v[i], v[i], x2, p2, p2, sqrtf(p2), prm.gp, k);
-                            if (prm.bias) o += __ldg(prm.bias + n);
-                            v[i] = o;
+                            v[i] = gyro_pair_fwd(v[i], v[i], x2, cc.x, cc.x, cc.w, prm.gp, k) + colb[as * BN + cb + i];
                         }
                     }
                 }
-                if (row_ok) {
+                if (EPI != EPI_ROWDOT && row_ok) {
                     float* dst = prm.D + m * prm.N + n0;
                     if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
 #pragma unroll
@@ -249,7 +326,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     }
                 }
             }
-            if (EPI == EPI_PLAIN && prm.rowsq && row_ok) prm.rowsq[nt * prm.M + m] = sq;
+            // per-(row, n-tile, column-group) partials: [ (nt*CG + cg) ][M]
+            if (EPI == EPI_PLAIN && prm.rowsq && row_ok) prm.rowsq[(nt * CG + cg) * prm.M + m] = acc_row;
+            if (EPI == EPI_ROWDOT && row_ok) prm.rowdot[(nt * CG + cg) * prm.M + m] = acc_row;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -292,6 +371,21 @@ __global__ void k_rows_to_bf16(const float* __restrict__ in, __nv_bfloat16* __re
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (sumsq && lane == 0) sumsq[r] = s;
+    }
+}
+
+// (R, C) fp32 row-major -> (C, R) bf16 row-major (32x32 smem tiles)
+__global__ void k_transpose_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < C) ? in[(int64_t)r * C + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < C && r < R) out[(int64_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
     }
 }
 
@@ -363,7 +457,7 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
 }
 
 struct Ws {
-    size_t a16, b16, x2, p2, rowsq, total;  // byte offsets
+    size_t a16, b16, x2, p2, rowsq, mt16, g32, g16, rowdot, total;  // byte offsets
 };
 static Ws ws_layout(int64_t B, int64_t K, int64_t P) {
     Ws w;
@@ -373,7 +467,11 @@ static Ws ws_layout(int64_t B, int64_t K, int64_t P) {
     w.b16 = take((size_t)P * K * 2);
     w.x2 = take((size_t)B * 4);
     w.p2 = take((size_t)P * 4);
-    w.rowsq = take((size_t)((P + BN - 1) / BN) * B * 4);
+    w.rowsq = take((size_t)((P + BN - 1) / BN) * CG * B * 4);
+    w.mt16 = take((size_t)K * P * 2);
+    w.g32 = take((size_t)K * K * 4);
+    w.g16 = take((size_t)K * K * 2);
+    w.rowdot = take((size_t)((K + BN - 1) / BN) * CG * B * 4);
     w.total = o;
     return w;
 }
@@ -396,7 +494,7 @@ static int tc_check(int64_t B, int64_t K, int64_t P) {
 extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, int64_t B, int64_t F,
                                              int64_t P, float c, void* workspace, size_t workspace_bytes, void* stream) {
     if (tc_check(B, F, P) != HVAE_OK) return HVAE_ESHAPE;
-    if (!x || !M || !y || !mx_out || !workspace) return HVAE_EARG;
+    if (!x || !M || !y || !workspace) return HVAE_EARG;
     const tc::Ws L = tc::ws_layout(B, F, P);
     if (workspace_bytes < L.total) return HVAE_EARG;
     cudaStream_t s = (cudaStream_t)stream;
@@ -404,15 +502,49 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
     auto* a16 = (__nv_bfloat16*)(ws + L.a16);
     auto* b16 = (__nv_bfloat16*)(ws + L.b16);
     float* x2 = (float*)(ws + L.x2);
-    float* rowsq = (float*)(ws + L.rowsq);
+    const unsigned pgrid = (unsigned)((P + 7) / 8 < 1 ? 1 : (P + 7) / 8);
     tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, a16, x2, B, F);
-    tc::k_rows_to_bf16<<<(unsigned)((P + 7) / 8 < 1 ? 1 : (P + 7) / 8), 256, 0, s>>>(M, b16, nullptr, P, F);
+    tc::k_rows_to_bf16<<<pgrid, 256, 0, s>>>(M, b16, nullptr, P, F);
+    if (mx_out) {
+        // training path (backward consumes mx): GEMM writes mx + |mx|^2 partials, a light second pass rescales
+        float* rowsq = (float*)(ws + L.rowsq);
+        tc::Params prm{};
+        prm.D = mx_out; prm.M = B; prm.N = P; prm.K = F; prm.rowsq = rowsq;
+        int rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
+        if (rc != HVAE_OK) return rc;
+        tc::k_mobius_rescale_rows<<<kNumSMs * 8, 256, 0, s>>>(mx_out, x2, rowsq, y, B, P,
+                                                              (int)((P + tc::BN - 1) / tc::BN) * tc::CG, make_ball(c));
+        return check_launch();
+    }
+    // forward-only path, single pass over the output: |mx_b|^2 = x_b^T (M^T M) x_b from the Gram matrix, so the
+    // rescale + projection is known per row BEFORE the main GEMM and is fused into its epilogue.
+    if ((F % 8) != 0 || (P % 8) != 0) return HVAE_ESHAPE;
+    auto* mt16 = (__nv_bfloat16*)(ws + L.mt16);
+    float* g32 = (float*)(ws + L.g32);
+    auto* g16 = (__nv_bfloat16*)(ws + L.g16);
+    float* rowdot = (float*)(ws + L.rowdot);
+    {
+        dim3 grid((unsigned)((F + 31) / 32), (unsigned)((P + 31) / 32)), block(32, 8);
+        tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(M, mt16, (int)P, (int)F);
+    }
+    {   // G = M^T M : (F, F), contraction over P
+        tc::Params prm{};
+        prm.D = g32; prm.M = F; prm.N = F; prm.K = P;
+        int rc = tc::launch_gemm<tc::EPI_PLAIN>(mt16, mt16, prm, s);
+        if (rc != HVAE_OK) return rc;
+        tc::k_rows_to_bf16<<<(unsigned)((F + 7) / 8), 256, 0, s>>>(g32, g16, nullptr, F, F);
+    }
+    {   // q_b = <x_b G, x_b> partials
+        tc::Params prm{};
+        prm.D = nullptr; prm.M = B; prm.N = F; prm.K = F; prm.xrow = x; prm.rowdot = rowdot;
+        int rc = tc::launch_gemm<tc::EPI_ROWDOT>(a16, g16, prm, s);
+        if (rc != HVAE_OK) return rc;
+    }
     tc::Params prm{};
-    prm.D = mx_out; prm.M = B; prm.N = P; prm.K = F; prm.rowscale = nullptr; prm.rowsq = rowsq;
-    int rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
-    if (rc != HVAE_OK) return rc;
-    tc::k_mobius_rescale_rows<<<kNumSMs * 8, 256, 0, s>>>(mx_out, x2, rowsq, y, B, P, (int)((P + tc::BN - 1) / tc::BN), make_ball(c));
-    return check_launch();
+    prm.D = y; prm.M = B; prm.N = P; prm.K = F; prm.x2 = x2; prm.mxsq = rowdot;
+    prm.q_tiles = (int)((F + tc::BN - 1) / tc::BN) * tc::CG;
+    prm.ball = make_ball(c);
+    return tc::launch_gemm<tc::EPI_MOBIUS>(a16, b16, prm, s);
 }
 
 extern "C" int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,

@@ -629,7 +629,11 @@ def mobius_matvec(x: Tensor, M: Tensor, c: float) -> Tensor:
     lead = x.shape[:-1]
     xr = _rows(x)
     if _tc_eligible(xr.shape[0], xr.shape[1], M.shape[0]):
-        y, _ = mobius_matvec_tc_fwd(xr, _c(M), c)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or M.requires_grad)
+        if not needs_grad and M.shape[0] % 8 == 0:
+            y = mobius_matvec_tc_infer(xr, _c(M), c)
+        else:
+            y, _ = mobius_matvec_tc_fwd(xr, _c(M), c)
     else:
         y, _ = mobius_matvec_fwd(xr, _c(M), c)
     return y.view(*lead, M.shape[0])
@@ -832,6 +836,25 @@ def _(x, M, c):
 
 
 mobius_matvec_tc_fwd.register_autograd(_mm_backward, setup_context=_mm_setup)  # backward: the fp32 kernels on the saved mx
+
+
+@_op("hvae::mobius_matvec_tc_infer", mutates_args=())
+def mobius_matvec_tc_infer(x: Tensor, M: Tensor, c: float) -> Tensor:
+    """Forward-only single-pass variant: |mx_b|^2 = x_b^T (M^T M) x_b from the Gram matrix, rescale + projection
+    fused into the main GEMM's epilogue (no mx is materialised, so there is nothing for a backward to use)."""
+    C.require_cuda(x, M)
+    B, F = x.shape
+    P = M.shape[0]
+    y = x.new_empty(B, P)
+    ws = _workspace(C.lib().hvae_tc_workspace_bytes(B, F, P), x.device)
+    C.call("hvae_mobius_matvec_tc_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), None, B, F, P, c, C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += 6
+    return y
+
+
+@mobius_matvec_tc_infer.register_fake
+def _(x, M, c):
+    return x.new_empty(x.shape[0], M.shape[0])
 
 
 @_op("hvae::gyroplane_tc_fwd", mutates_args=())

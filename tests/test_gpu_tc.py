@@ -41,6 +41,12 @@ def test_mobius_tc_forward(B, F, P):
     # the fp32 SIMT path on the same inputs agrees with the TC path to bf16 accuracy as well
     y32, _ = ops.mobius_matvec_fwd(x.cuda(), M.cuda(), hvae.PoincareBall(c).c_value)
     assert ((y32 - y).abs().cpu() / scale.float()).max() < 1e-2
+    # forward-only single-pass variant (Gram-matrix row scale fused into the GEMM epilogue)
+    if P % 8 == 0:
+        yi = ops.mobius_matvec_tc_infer(x.cuda(), M.cuda(), hvae.PoincareBall(c).c_value)
+        torch.cuda.synchronize()
+        erri = ((yi.double().cpu() - ref).abs() / scale).max()
+        assert erri < 1e-2, erri
 
 
 @pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024)])
