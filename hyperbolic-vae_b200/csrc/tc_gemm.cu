@@ -38,6 +38,13 @@ constexpr uint32_t TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
 constexpr uint32_t COLC_BYTES = ACC_STAGES * BN * 16 + ACC_STAGES * BN * 4;  // per-column float4 constants + bias
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES;
+// A-resident schedule (K <= 512): the CTA keeps its 128 x K panel of A in smem for all n-tiles of the m-block and
+// streams only B tiles.  L2->SM traffic per flop halves (the 128x128 streaming schedule is L2-bound: ncu shows
+// lts throughput ~70 % at 26 % tensor-pipe activity).
+constexpr int ARES_KB = 8;                                  // up to 8 k-blocks of 64 -> K <= 512
+constexpr int ARES_STAGES = 4;                              // B ring
+constexpr uint32_t ARES_RING_BYTES = ARES_KB * TILE_A_BYTES + ARES_STAGES * TILE_B_BYTES;
+constexpr uint32_t SMEM_BYTES_ARES = ARES_RING_BYTES + 1024 + 256 + COLC_BYTES;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
 
 enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3 };
@@ -130,30 +137,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int EPI>
+template <int EPI, bool ARES>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params prm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle wants 1024-byte aligned tiles
-    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    constexpr int NST = ARES ? ARES_STAGES : STAGES;
+    const uint32_t bars = base + (ARES ? ARES_RING_BYTES : STAGES * STAGE_BYTES);
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
-    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+    auto empty_bar = [&](int s) { return bars + 8u * (NST + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * NST + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * NST + ACC_STAGES + s); };
+    const uint32_t afull_bar = bars + 8u * (2 * NST + 2 * ACC_STAGES);
+    const uint32_t aempty_bar = afull_bar + 8u;
+    const uint32_t tmem_slot = aempty_bar + 8u;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+    // tile addresses: streaming = [stage][A|B]; A-resident = [A panel: kb][B ring: stage]
+    auto a_tile = [&](int stage_or_kb) { return ARES ? base + (uint32_t)stage_or_kb * TILE_A_BYTES : base + (uint32_t)stage_or_kb * STAGE_BYTES; };
+    auto b_tile = [&](int stage) {
+        return ARES ? base + ARES_KB * TILE_A_BYTES + (uint32_t)stage * TILE_B_BYTES : base + (uint32_t)stage * STAGE_BYTES + TILE_A_BYTES;
+    };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
     const int64_t tiles = m_tiles * n_tiles;
     const int k_blocks = (int)((prm.K + BK - 1) / BK);
+    // work unit: one output tile (streaming) or one m-block with all its n-tiles (A-resident)
+    const int64_t units = ARES ? m_tiles : tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+        mbar_init(afull_bar, 1);
+        mbar_init(aempty_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -169,16 +188,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    const uint32_t sa = base + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(sa + TILE_A_BYTES, &map_b, full_bar(stage), kb * BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            uint32_t phase = 0, pphase = 0;
+            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const int64_t mt = ARES ? u : u / n_tiles;
+                const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+                const int m0 = (int)mt * BM;
+                if (ARES) {
+                    mbar_wait(aempty_bar, pphase ^ 1u);      // all MMAs of the previous m-block have retired
+                    mbar_expect_tx(afull_bar, (uint32_t)k_blocks * TILE_A_BYTES);
+                    for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(a_tile(kb), &map_a, afull_bar, kb * BK, m0);
+                    pphase ^= 1u;
+                }
+                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                    const int n0 = (int)nt * BN;
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), ARES ? TILE_B_BYTES : STAGE_BYTES);
+                        if (!ARES) tma_load_2d(a_tile(stage), &map_a, full_bar(stage), kb * BK, m0);
+                        tma_load_2d(b_tile(stage), &map_b, full_bar(stage), kb * BK, n0);
+                        if (++stage == NST) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
@@ -186,26 +215,34 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
-            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-                mbar_wait(tempty_bar(as), aphase ^ 1u);   // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
+            uint32_t phase = 0, aphase = 0, pphase = 0;
+            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+                if (ARES) {
+                    mbar_wait(afull_bar, pphase);
                     tc_fence_after();
-                    const uint32_t sa = base + stage * STAGE_BYTES;
-                    const uint64_t da = make_desc(sa), db = make_desc(sa + TILE_A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
-                    }
-                    umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    pphase ^= 1u;
                 }
-                umma_commit(tfull_bar(as));                 // accumulator complete
-                if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                    mbar_wait(tempty_bar(as), aphase ^ 1u);   // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint64_t da = make_desc(a_tile(ARES ? kb : stage)), db = make_desc(b_tile(stage));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+                            umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
+                        }
+                        umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+                        if (++stage == NST) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(tfull_bar(as));                 // accumulator complete
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+                }
+                if (ARES) umma_commit(aempty_bar);              // the A panel may be overwritten once these retire
             }
         }
     } else {
@@ -218,8 +255,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         int as = 0;
         uint32_t aphase = 0;
         constexpr int COLS = BN / CG;
-        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int64_t mt = t / n_tiles, nt = t % n_tiles;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+          const int64_t mt = ARES ? u : u / n_tiles;
+          const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+          for (int64_t nt = nt0; nt < nt1; ++nt) {
             const int64_t m = mt * BM + q * 32 + lane;
             const bool row_ok = m < prm.M;
             if (EPI == EPI_GYRO) {
@@ -333,6 +372,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+          }
         }
     }
     tc_fence_before();
@@ -447,12 +487,21 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     if (!make_map(&ma, A, prm.M, prm.K, BM) || !make_map(&mb, Bm, prm.N, prm.K, BN)) return HVAE_ELAUNCH;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaFuncSetAttribute(k_tc_gemm<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaFuncSetAttribute(k_tc_gemm<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_ARES);
         attr_set = true;
     }
-    const int64_t tiles = ((prm.M + BM - 1) / BM) * ((prm.N + BN - 1) / BN);
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    k_tc_gemm<EPI><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, prm);
+    const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
+    // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over, and enough m-blocks
+    const bool ares = prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
+    if (ares) {
+        const int grid = (int)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
+        k_tc_gemm<EPI, true><<<grid, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, prm);
+    } else {
+        const int64_t tiles = m_tiles * n_tiles;
+        const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+        k_tc_gemm<EPI, false><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, prm);
+    }
     return check_launch();
 }
 

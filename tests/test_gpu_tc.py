@@ -14,7 +14,8 @@ def _oball(c):
     return PoincareBall(c=c)
 
 
-@pytest.mark.parametrize("B,F,P", [(128, 64, 128), (256, 128, 256), (384, 256, 640), (1000, 512, 300), (4096, 512, 1024)])
+# the last shape has >= 148 m-blocks, K <= 512 and >= 4 n-tiles: it runs the A-resident schedule (ragged M and N)
+@pytest.mark.parametrize("B,F,P", [(128, 64, 128), (256, 128, 256), (384, 256, 640), (1000, 512, 300), (4096, 512, 1024), (19000, 512, 600)])
 def test_mobius_tc_forward(B, F, P):
     import hvae
     from hvae import ops
@@ -49,7 +50,7 @@ def test_mobius_tc_forward(B, F, P):
         assert erri < 1e-2, erri
 
 
-@pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024)])
+@pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024), (19000, 256, 520)])
 def test_gyroplane_tc_forward(B, D, P):
     import hvae
     from hvae import ops
