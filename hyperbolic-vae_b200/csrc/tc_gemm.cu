@@ -20,6 +20,7 @@
 // light second pass (k_mobius_rescale_rows); DESIGN.md lists the Gram-matrix single-pass variant as next.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "hvae_common.cuh"
 #include "gyro_pair.cuh"
@@ -37,14 +38,19 @@ constexpr int THREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue 
 constexpr uint32_t TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
 constexpr uint32_t COLC_BYTES = ACC_STAGES * BN * 16 + ACC_STAGES * BN * 4;  // per-column float4 constants + bias
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES;
+// per-warp 32x32 fp32 staging tile (row stride 36 floats): the accumulator arrives one ROW per lane, but a store
+// instruction should cover whole 128-byte lines (ncu on the direct per-lane stores: 16 of 32 bytes per sector used,
+// lg_throttle the top stall) -> transpose through smem so 8 lanes write one contiguous 128 B row segment.
+constexpr int STG_LD = 36;
+constexpr uint32_t STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES + STG_BYTES;
 // A-resident schedule (K <= 512): the CTA keeps its 128 x K panel of A in smem for all n-tiles of the m-block and
 // streams only B tiles.  L2->SM traffic per flop halves (the 128x128 streaming schedule is L2-bound: ncu shows
 // lts throughput ~70 % at 26 % tensor-pipe activity).
 constexpr int ARES_KB = 8;                                  // up to 8 k-blocks of 64 -> K <= 512
 constexpr int ARES_STAGES = 4;                              // B ring
 constexpr uint32_t ARES_RING_BYTES = ARES_KB * TILE_A_BYTES + ARES_STAGES * TILE_B_BYTES;
-constexpr uint32_t SMEM_BYTES_ARES = ARES_RING_BYTES + 1024 + 256 + COLC_BYTES;
+constexpr uint32_t SMEM_BYTES_ARES = ARES_RING_BYTES + 1024 + 256 + COLC_BYTES;  // (no room for the store staging)
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
 
 enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3 };
@@ -252,6 +258,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int et = threadIdx.x - 64;  // 0 .. 32*EPI_WARPS-1
         float4* colc = reinterpret_cast<float4*>(smem_raw + (bars + 256u - raw));            // [ACC_STAGES][BN]
         float* colb = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw) + ACC_STAGES * BN * 16);
+        float* stg = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw) + COLC_BYTES) + (warp - 2) * 32 * STG_LD;
         int as = 0;
         uint32_t aphase = 0;
         constexpr int COLS = BN / CG;
@@ -354,14 +361,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         }
                     }
                 }
-                if (EPI != EPI_ROWDOT && row_ok) {
-                    float* dst = prm.D + m * prm.N + n0;
-                    if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+                if (EPI != EPI_ROWDOT) {
+                    if (!ARES && n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+                        // stage: lane = row writes its 32 values; then 8 lanes cooperate on one 128-byte row segment
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-                        for (int i = 0; i < 32; ++i)
-                            if (n0 + i < prm.N) dst[i] = v[i];
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        __syncwarp();
+                        const int64_t mrow0 = mt * BM + q * 32;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = 4 * j + (lane >> 3), c4 = (lane & 7) * 4;
+                            const float4 t4 = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+                            if (mrow0 + r < prm.M) *reinterpret_cast<float4*>(prm.D + (mrow0 + r) * prm.N + n0 + c4) = t4;
+                        }
+                        __syncwarp();
+                    } else if (row_ok) {
+                        float* dst = prm.D + m * prm.N + n0;
+                        if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < prm.N) dst[i] = v[i];
+                        }
                     }
                 }
             }
@@ -493,7 +516,10 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     }
     const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
     // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over, and enough m-blocks
-    const bool ares = prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
+    // measured: not faster than streaming (the kernel is bound by the epilogue's stores, not by operand traffic), and it
+    // leaves no smem for the store staging -> opt-in only
+    static const bool want_ares = getenv("HVAE_TC_ARES") != nullptr;
+    const bool ares = want_ares && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
     if (ares) {
         const int grid = (int)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
         k_tc_gemm<EPI, true><<<grid, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, prm);
