@@ -345,10 +345,11 @@ inline int gyro_slabs(int64_t B, int64_t P) {
 }
 
 // G1: how many plane-chunks (gridDim.y) so that ~4 CTAs/SM are in flight
+constexpr int kGyroChunkGran = 8;  // plane-chunk granularity (a stage holds up to 32 planes, a chunk may be shorter)
 inline int gyro_x_chunks(int64_t B, int64_t P) {
     const int64_t rb = (B + kGyroBxThreads - 1) / kGyroBxThreads;
-    int64_t want = (4 * kNumSMs + rb - 1) / rb;
-    const int64_t maxc = (P + kGyroBxTJ - 1) / kGyroBxTJ;
+    int64_t want = (8 * kNumSMs + rb - 1) / rb;   // the pair math is a long dependent chain: aim for ~8 CTAs per SM
+    const int64_t maxc = (P + kGyroChunkGran - 1) / kGyroChunkGran;
     if (want > maxc) want = maxc;
     if (want < 1) want = 1;
     return (int)want;
@@ -415,7 +416,7 @@ int gyro_bwd_launch(const float* x, const float* p, const float* a, const float*
     float *CP = ws + L.cp, *CA = ws + L.ca, *wsum = ws + L.wsum, *wx = ws + L.wx, *wp = ws + L.wp, *wa = ws + L.wa,
           *wb = ws + L.wb;
     const int chunks = gyro_x_chunks(B, P);
-    const int ppc = (int)((((P + chunks - 1) / chunks) + kGyroBxTJ - 1) / kGyroBxTJ * kGyroBxTJ);
+    const int ppc = (int)((((P + chunks - 1) / chunks) + kGyroChunkGran - 1) / kGyroChunkGran * kGyroChunkGran);
     const int nch = (int)((P + ppc - 1) / ppc);
     float* dst = nch == 1 ? gx : wx;
     {

@@ -298,7 +298,7 @@ extern "C" int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, flo
     if (B < 0 || dim < 1 || dim > kMaxRadiusDim) return HVAE_ESHAPE;
     if (B == 0) return HVAE_OK;
     if (!sigma || !logZ) return HVAE_EARG;
-    k_hradius_lognorm<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sigma, logZ, dlogZ_dsigma, B, (int)dim,
+    k_hradius_lognorm<<<(unsigned)((B + 31) / 32), 32, 0, (cudaStream_t)stream>>>(sigma, logZ, dlogZ_dsigma, B, (int)dim,
                                                                                      (double)c);
     return check_launch();
 }
@@ -309,7 +309,7 @@ extern "C" int hvae_hradius_sample_f32(const float* sigma, float* r, int64_t S, 
     if (S == 0 || B == 0) return HVAE_OK;
     if (!sigma || !r) return HVAE_EARG;
     const int64_t n = S * B;
-    k_hradius_sample<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sigma, r, S, B, (int)dim, c, seed, offset,
+    k_hradius_sample<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(sigma, r, S, B, (int)dim, c, seed, offset,
                                                                                      offset_dev);
     return check_launch();
 }
@@ -320,7 +320,7 @@ extern "C" int hvae_hradius_rgrad_f32(const float* sigma, const float* r, float*
     if (S == 0 || B == 0) return HVAE_OK;
     if (!sigma || !r || !dr_dsigma) return HVAE_EARG;
     const int64_t n = S * B;
-    k_hradius_rgrad<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sigma, r, dr_dsigma, cdf, S, B, (int)dim,
+    k_hradius_rgrad<<<(unsigned)((n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(sigma, r, dr_dsigma, cdf, S, B, (int)dim,
                                                                                    (double)c);
     return check_launch();
 }

@@ -128,6 +128,15 @@ class RiemannianNormal(torch.distributions.Distribution):
                                     self.manifold.c_value)
         return ops.expmap_polar(self.loc, alpha, radius, self.manifold.c_value)
 
+    def kl_mc(self, z: Tensor, prior: "RiemannianNormal") -> Tensor:
+        """Monte-Carlo KL term log q(z) - log p(z) for z (S, B, D), q = self with per-row sigma (B,1) and an
+        origin-centred prior with scalar sigma — ONE fused kernel (forward) instead of two log_prob graphs.
+        Returns (S, B).  (The log|S^{D-1}| normalisers cancel.)"""
+        S, B, D = z.shape
+        return ops.rn_kl_fwd(ops._c(self.loc).view(B, D), ops._c(self.scale).view(B), ops._c(self.radius.log_normalizer).view(B),
+                             ops._c(z), ops._c(prior.scale).view(1), ops._c(prior.radius.log_normalizer).view(1),
+                             self.manifold.c_value)
+
     def log_prob(self, value: Tensor) -> Tensor:
         loc = self.loc.expand(value.shape)
         radius_sq = self.manifold.dist(loc, value, keepdim=True).pow(2)

@@ -258,9 +258,11 @@ class PvaeMnist(nn.Module):
       dec: GeodesicLayer(D,h) ReLU -> Linear(h,784) logits; Bernoulli likelihood (BCE with logits)
       loss = -E log p(x|z) + beta (log q(z|x) - log p(z)), summed over the batch."""
 
-    def __init__(self, latent_dim=10, hidden_dim=600, c=1.0, prior_std=1.0, beta=1.0, data_size=(1, 28, 28)):
+    def __init__(self, latent_dim=10, hidden_dim=600, c=1.0, prior_std=1.0, beta=1.0, data_size=(1, 28, 28), fused=True):
         super().__init__()
         from .distributions.riemannian_normal import RiemannianNormal  # noqa: F401
+
+        self.fused = fused
 
         self.data_size = torch.Size(data_size)
         n = self.data_size.numel()
@@ -293,7 +295,10 @@ class PvaeMnist(nn.Module):
         lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
         pz_scale = F.softplus(self._pz_logvar) / math.log(2) * self.prior_std
         p = RiemannianNormal(self._pz_mu, pz_scale, self.manifold)
-        kld = q.log_prob(zs).sum(-1) - p.log_prob(zs).sum(-1)
+        if self.fused:
+            kld = q.kl_mc(zs, p)  # one kernel: both log-densities and their difference
+        else:
+            kld = q.log_prob(zs).sum(-1) - p.log_prob(zs).sum(-1)
         recon = -lpx_z.mean(0).sum()
         kl = kld.mean(0).sum()
         return dict(loss_total=recon + self.beta * kl, recon_loss=recon, kl_loss=kl)

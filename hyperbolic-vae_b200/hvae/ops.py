@@ -890,3 +890,52 @@ def _gtc_backward(ctx, g):
 
 
 gyroplane_tc_fwd.register_autograd(_gtc_backward, setup_context=_gtc_setup)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused Monte-Carlo KL of two Riemannian normals (posterior vs origin prior)
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::rn_kl_fwd", mutates_args=())
+def rn_kl_fwd(mu: Tensor, sigma_q: Tensor, logz_q: Tensor, z: Tensor, sigma_p: Tensor, logz_p: Tensor, c: float) -> Tensor:
+    """mu (B,D); sigma_q, logz_q (B,); z (S,B,D); sigma_p, logz_p 1-element device tensors -> kl (S,B)"""
+    C.require_cuda(mu, sigma_q, logz_q, z, sigma_p, logz_p)
+    S, B, D = z.shape
+    kl = z.new_empty(S, B)
+    C.call("hvae_rn_kl_fwd_f32", C.ptr(mu), C.ptr(sigma_q), C.ptr(logz_q), C.ptr(z), C.ptr(sigma_p), C.ptr(logz_p), C.ptr(kl),
+           S, B, D, c, C.stream())
+    return kl
+
+
+@rn_kl_fwd.register_fake
+def _(mu, sigma_q, logz_q, z, sigma_p, logz_p, c):
+    return z.new_empty(z.shape[0], z.shape[1])
+
+
+@_op("hvae::rn_kl_bwd", mutates_args=())
+def rn_kl_bwd(mu: Tensor, sigma_q: Tensor, z: Tensor, sigma_p: Tensor, g: Tensor, c: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    C.require_cuda(mu, sigma_q, z, sigma_p, g)
+    S, B, D = z.shape
+    gmu, gs, glz, gz = torch.empty_like(mu), torch.empty_like(sigma_q), torch.empty_like(sigma_q), torch.empty_like(z)
+    C.call("hvae_rn_kl_bwd_f32", C.ptr(mu), C.ptr(sigma_q), C.ptr(z), C.ptr(sigma_p), C.ptr(g), C.ptr(gmu), C.ptr(gs),
+           C.ptr(glz), C.ptr(gz), S, B, D, c, C.stream())
+    return gmu, gs, glz, gz
+
+
+@rn_kl_bwd.register_fake
+def _(mu, sigma_q, z, sigma_p, g, c):
+    return torch.empty_like(mu), torch.empty_like(sigma_q), torch.empty_like(sigma_q), torch.empty_like(z)
+
+
+def _rk_setup(ctx, inputs, output):
+    mu, sigma_q, logz_q, z, sigma_p, logz_p, c = inputs
+    ctx.save_for_backward(mu, sigma_q, z, sigma_p)
+    ctx.c = c
+
+
+def _rk_backward(ctx, g):
+    mu, sigma_q, z, sigma_p = ctx.saved_tensors
+    gmu, gs, glz, gz = rn_kl_bwd(mu, sigma_q, z, sigma_p, _c(g), ctx.c)
+    return gmu, gs, glz, gz, None, None, None
+
+
+rn_kl_fwd.register_autograd(_rk_backward, setup_context=_rk_setup)

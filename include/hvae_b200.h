@@ -145,6 +145,16 @@ int hvae_expmap_polar_fwd_f32(const float* mu, const float* alpha, const float* 
 int hvae_expmap_polar_bwd_f32(const float* mu, const float* alpha, const float* r, const float* gz,
                               float* gmu, float* gr, int64_t S, int64_t B, int64_t D, float c, void* stream);
 
+/* ---- fused Monte-Carlo KL of RiemannianNormal(mu_b, sigma_b) against the origin prior RiemannianNormal(0, sigma_p)
+ * (pvae RiemannianNormal.log_prob x2, objective of training/old_pvae_train.py:53-58).  sigma_q, logz_q: (B,);
+ * sigma_p, logz_p: device scalars (no host sync); z: (S,B,D); kl: (S,B). */
+int hvae_rn_kl_fwd_f32(const float* mu, const float* sigma_q, const float* logz_q, const float* z,
+                       const float* sigma_p, const float* logz_p, float* kl, int64_t S, int64_t B, int64_t D,
+                       float c, void* stream);
+int hvae_rn_kl_bwd_f32(const float* mu, const float* sigma_q, const float* z, const float* sigma_p, const float* gkl,
+                       float* gmu, float* gsigma_q, float* glogz_q, float* gz, int64_t S, int64_t B, int64_t D,
+                       float c, void* stream);
+
 /* ---- K1-TC / K2-TC: tcgen05 (bf16 operands, fp32 accumulate) forward paths for GEMM-sized shapes --------------
  * Same math as hvae_mobius_matvec_fwd_f32 / hvae_gyroplane_fwd_f32 (a == p), operands rounded to bf16: the
  * "bf16 GEMM mode" of BASELINE.json (1e-2 tolerance).  K (= F or D) must be a multiple of 8. */

@@ -137,7 +137,8 @@ def test_riemannian_normal_injected_noise(D, c):
     assert_parity(sg.grad, o32[3], o64[3], what="RN gsigma", rtol=rtol_grad(kap, 5e-5), atol=2e-5, row_relative=False, slack_mult=2.0)
 
 
-def test_pvae_mnist_step_matches_oracle():
+@pytest.mark.parametrize("fused", [True, False])
+def test_pvae_mnist_step_matches_oracle(fused):
     """Config 2 at reduced width: same weights, same data, same injected (alpha, r)."""
     from hvae import models as HM
     from oracle import ref_port as R
@@ -171,7 +172,7 @@ def test_pvae_mnist_step_matches_oracle():
 
     L32, G32 = run_oracle(torch.float32)
     L64, G64 = run_oracle(torch.float64)
-    model = HM.PvaeMnist(latent_dim=D, hidden_dim=H, c=1.0)
+    model = HM.PvaeMnist(latent_dim=D, hidden_dim=H, c=1.0, fused=fused)
     sd_c = {k: v for k, v in sd.items() if not k.endswith("manifold.dim")}  # pvae's PoincareBall(dim, c) buffer
     missing, unexpected = model.load_state_dict(sd_c, strict=False)
     assert not unexpected and all("isp_c" in k for k in missing), (missing, unexpected)
