@@ -280,11 +280,27 @@ def run_ours(args, wl):
     for _ in range(max(args.warmup, 3)):
         ts.run()
     barrier()
-    with Clocks(local) as clk:
+    do_flush = os.environ.get("HVAE_BENCH_FLUSH", "1") != "0"
+    clocks_on = rank == 0 or os.environ.get("HVAE_BENCH_CLOCKS_ALL", "0") == "1"  # one nvidia-smi poller per node
+
+    class _NoClocks:
+        samples = []
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def summary(self):
+            return None
+
+    with (Clocks(local) if clocks_on else _NoClocks()) as clk:
         evs = []
         t_wall0 = time.perf_counter()
         for _ in range(args.steps):
-            flush.zero_()
+            if do_flush:
+                flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             ts.run()          # batch already resident in HBM
