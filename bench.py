@@ -312,15 +312,21 @@ def run_ours(args, wl):
         dev_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
 
         # ---- e2e: host batch -> pinned H2D -> TrainStep.run (public API) -> D2H loss, every step ------------
+        # Every step: one pinned H2D copy of that step's batch (prefetched on a copy stream while the previous step
+        # runs), the step, and a D2H read of its loss that the host waits for.
         for _ in range(3):
             loss_host.copy_(ts.run(x_host), non_blocking=True)
         barrier()
         e2e_steps = args.steps
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for _ in range(e2e_steps):
-            loss_host.copy_(ts.run(x_host), non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+        ts.prefetch(x_host)                                   # batch of step 0
+        for i in range(e2e_steps):
+            loss_dev = ts.run_prefetched()
+            if i + 1 < e2e_steps:
+                ts.prefetch(x_host)                           # batch of step i+1 streams in under step i
+            loss_host.copy_(loss_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()         # the caller reads the loss every step
         e.record()
         barrier()
         e2e_s = s.elapsed_time(e) * 1e-3
@@ -357,7 +363,7 @@ def run_ours(args, wl):
                        "l2": "256 MiB buffer written between timed steps (L2 flush)",
                        "trunk": "torch fp32 Linear (cuBLAS, TF32 off) — library code, not this repo's kernels"},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "samples/s",
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "mode": "hvae.train.TrainStep.run(host batch)"},
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "mode": "hvae.train.TrainStep prefetch()/run_prefetched(): H2D of step i+1 overlaps step i"},
             "gpu_launches": launches_per_step * (args.steps + e2e_steps),
             "gpu_launches_per_step": launches_per_step,
             "clocks": clk.summary(),

@@ -23,6 +23,10 @@ class TrainStep:
         self.bucket = FlatGradBucket(model.parameters())
         self.x = torch.empty_like(example_input)  # static input buffer (device)
         self.x.copy_(example_input)
+        self._stage = torch.empty_like(example_input)  # landing buffer of the asynchronous host->device prefetch
+        self._copy_stream = torch.cuda.Stream()
+        self._staged = None   # event: the prefetch into _stage has landed
+        self._consumed = None  # event: _stage has been copied into the static input
         self.loss = None
         self.graph = None
         for _ in range(3):
@@ -57,6 +61,29 @@ class TrainStep:
             self.graph = None
             sys.stderr.write("hvae.TrainStep: CUDA graph capture failed (%s); running eagerly\n" % (str(ex).splitlines()[0],))
             torch.cuda.synchronize()
+
+    def prefetch(self, x_host: torch.Tensor):
+        """Start the host->device copy of the NEXT batch on a side stream; it overlaps with the step in flight.
+        Pair with run_prefetched()."""
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)  # do not overwrite the landing buffer before the previous hand-over
+        with torch.cuda.stream(cs):
+            self._stage.copy_(x_host, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(cs)
+
+    def run_prefetched(self) -> torch.Tensor:
+        """One step on the batch handed over by prefetch()."""
+        if self._staged is None:
+            raise RuntimeError("TrainStep.run_prefetched() without a prefetch()")
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self.x.copy_(self._stage, non_blocking=True)  # device->device hand-over (a few microseconds)
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(cur)
+        self._staged = None
+        return self.run()
 
     def run(self, x: torch.Tensor = None) -> torch.Tensor:
         """One step. x: new batch (host pinned or device) copied into the static buffer, or None to reuse it.
