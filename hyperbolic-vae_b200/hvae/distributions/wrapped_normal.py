@@ -74,6 +74,11 @@ class WrappedNormal(torch.distributions.Distribution):
     def log_prob(self, x: Tensor) -> Tensor:
         """x: (S, *batch, D) (or missing the batch dims -> broadcast like the reference) -> (S, *batch, 1)"""
         D = int(self.event_shape[0])
+        if self._is_origin_prior() and x.dim() >= 2:
+            # origin prior with a scalar scale: every row of x is scored independently, any leading shape
+            xs = ops._c(x).view(1, -1, D)
+            lp = ops.wrapped_logprob_prior_fwd(xs, self._prior_sigma, self.manifold.c_value)
+            return lp.view(*x.shape[:-1], 1)
         loc_shape = torch.Size([x.shape[0], *self.batch_shape, D])
         if x.dim() < len(loc_shape):
             x = x.unsqueeze(1)
