@@ -245,15 +245,16 @@ k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const
     }
 }
 
-constexpr int kGyroBpThreads = 128;
+constexpr int kGyroBpThreads = 64;
 constexpr int kGyroBpTB = 32;  // rows per smem stage
+constexpr int kGyroBpSlabGran = 64;  // slab granularity in rows (finer than G1's 128-row blocks: more CTAs in flight)
 
 template <int D4, bool kAliased>
 __global__ void __launch_bounds__(kGyroBpThreads)
 k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
                   const float* __restrict__ CP, const float* __restrict__ CA, const float* __restrict__ wsum,
                   float* __restrict__ wp, float* __restrict__ wa, float* __restrict__ wb, int B, int D, int P_,
-                  int rows_per_slab /* multiple of 128 */) {
+                  int rows_per_slab /* multiple of kGyroBpSlabGran */) {
     constexpr int TJ = kGyroBpThreads;
     __shared__ float xs[kGyroBpTB][D4];
     const int tid = threadIdx.x;
@@ -295,7 +296,8 @@ k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, cons
     }
     if (j < P_) {
         float sdp2 = 0.0f, sdpa = 0.0f, sdan = 0.0f, sg = 0.0f;
-        for (int rb = bs / kGyroBxThreads; rb * kGyroBxThreads < be; ++rb) {
+        // the scalar sums live per 128-row block of G1: the slab that contains a block's first row takes it
+        for (int rb = (bs + kGyroBxThreads - 1) / kGyroBxThreads; rb * kGyroBxThreads < be; ++rb) {
             const float4 w = *reinterpret_cast<const float4*>(wsum + ((int64_t)rb * P_ + j) * 4);
             sdp2 += w.x; sdpa += w.y; sdan += w.z; sg += w.w;
         }
@@ -337,8 +339,8 @@ __global__ void k_gyro_reduce_slabs(const float* __restrict__ w, float* __restri
 // G2 slabs of rows (multiples of the 128-row blocks of G1)
 inline int gyro_slabs(int64_t B, int64_t P) {
     const int64_t jb = (P + kGyroBpThreads - 1) / kGyroBpThreads;
-    int64_t want = (4 * kNumSMs + jb - 1) / jb;
-    const int64_t maxs = (B + kGyroBxThreads - 1) / kGyroBxThreads;
+    int64_t want = (8 * kNumSMs + jb - 1) / jb;
+    const int64_t maxs = (B + kGyroBpSlabGran - 1) / kGyroBpSlabGran;
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     return (int)want;
@@ -427,7 +429,7 @@ int gyro_bwd_launch(const float* x, const float* p, const float* a, const float*
     }
     if (gp || ga || gbias) {
         const int slabs = gyro_slabs(B, P);
-        const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBxThreads - 1) / kGyroBxThreads * kGyroBxThreads);
+        const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBpSlabGran - 1) / kGyroBpSlabGran * kGyroBpSlabGran);
         const int nsl = (int)((B + rows_per_slab - 1) / rows_per_slab);
         dim3 grid((unsigned)((P + kGyroBpThreads - 1) / kGyroBpThreads), (unsigned)nsl);
         if (aliased) k_gyro_bwd_planes<D4, true><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);

@@ -25,50 +25,54 @@ __device__ __forceinline__ double log1p_erf(double x) {
     return log(erfcx(-x)) - x * x;
 }
 
-struct RadiusSeries {
-    double m;     // max_k of v_k
-    double S;     // sum_k s_k exp(v_k - m)          (Z-series, scaled)
-    double dS;    // d/ds of the unscaled series, scaled by exp(-m)
-};
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
-// v_k = logC_k + b_k^2 s^2/2 + log(1+erf(b_k s/sqrt2))
-__device__ __forceinline__ RadiusSeries radius_series(double s, double sc, int n, const double* __restrict__ logC) {
-    RadiusSeries R;
+// One WARP per row: lane l evaluates the series terms k = l, l+32, ...  (the float64 erf/erfcx/log/exp chain of one term
+// is ~1 us of latency; a thread-per-row loop over dim terms was pure latency: 16 us for B = 1).
+// v_k = logC_k + b_k^2 s^2/2 + log(1+erf(b_k s/sqrt2));  logZ = const + log s + m + log sum_k (-1)^k e^{v_k - m}
+__global__ void k_hradius_lognorm(const float* __restrict__ sigma, float* __restrict__ logZ, float* __restrict__ dlogZ,
+                                  int64_t B, int dim, double c) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= B) return;  // warp-uniform
+    const int n = dim - 1;
+    const double s = (double)sigma[row];
+    const double sc = sqrt(c);
+    const double lgd = lgamma((double)dim);
     double m = -1e300;
-    for (int k = 0; k <= n; ++k) {
+    for (int k = lane; k <= n; k += 32) {
         const double b = (n - 2 * k) * sc;
-        const double v = logC[k] + 0.5 * b * b * s * s + log1p_erf(b * s / kSqrt2);
+        const double v = lgd - lgamma((double)k + 1.0) - lgamma((double)(dim - k)) + 0.5 * b * b * s * s + log1p_erf(b * s / kSqrt2);
         m = fmax(m, v);
     }
+    m = warp_max_d(m);
     double S = 0.0, dS = 0.0;
-    for (int k = 0; k <= n; ++k) {
+    for (int k = lane; k <= n; k += 32) {
         const double b = (n - 2 * k) * sc;
         const double sg = (k & 1) ? -1.0 : 1.0;
-        const double v = logC[k] + 0.5 * b * b * s * s + log1p_erf(b * s / kSqrt2);
+        const double lc = lgd - lgamma((double)k + 1.0) - lgamma((double)(dim - k));
+        const double v = lc + 0.5 * b * b * s * s + log1p_erf(b * s / kSqrt2);
         const double e = exp(v - m);
         S += sg * e;
         // d/ds [C e^{b^2 s^2/2}(1+erf(b s/sqrt2))] = b^2 s (.) + C b sqrt(2/pi)
-        dS += sg * (b * b * s * e + exp(logC[k] - m) * b * kSqrt2OverPi);
+        dS += sg * (b * b * s * e + exp(lc - m) * b * kSqrt2OverPi);
     }
-    R.m = m; R.S = S; R.dS = dS;
-    return R;
-}
-
-__global__ void k_hradius_lognorm(const float* __restrict__ sigma, float* __restrict__ logZ, float* __restrict__ dlogZ,
-                                  int64_t B, int dim, double c) {
-    __shared__ double logC[kMaxRadiusDim];
-    const int n = dim - 1;
-    for (int k = threadIdx.x; k <= n; k += blockDim.x)
-        logC[k] = lgamma((double)dim) - lgamma((double)k + 1.0) - lgamma((double)(dim - k));
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    const double s = (double)sigma[i];
-    const double sc = sqrt(c);
-    const RadiusSeries R = radius_series(s, sc, n, logC);
-    const double lz = 0.5 * (log(3.14159265358979323846) - log(2.0)) + log(s) - n * (0.5 * log(c) + log(2.0)) + R.m + log(R.S);
-    logZ[i] = (float)lz;
-    if (dlogZ) dlogZ[i] = (float)(1.0 / s + R.dS / R.S);
+    S = warp_sum_d(S);
+    dS = warp_sum_d(dS);
+    if (lane == 0) {
+        const double lz = 0.5 * (log(3.14159265358979323846) - log(2.0)) + log(s) - n * (0.5 * log(c) + log(2.0)) + m + log(S);
+        logZ[row] = (float)lz;
+        if (dlogZ) dlogZ[row] = (float)(1.0 / s + dS / S);
+    }
 }
 
 // ---- Philox4x32-10 ------------------------------------------------------------------------------------
@@ -176,52 +180,49 @@ __global__ void k_hradius_sample(const float* __restrict__ sigma, float* __restr
     r_out[i] = r;
 }
 
-// dr/dsigma by implicit differentiation of F(r; sigma) = U.  float64.
+// dr/dsigma by implicit differentiation of F(r; sigma) = U.  float64, one warp per sample (lanes stride over terms).
 __global__ void k_hradius_rgrad(const float* __restrict__ sigma, const float* __restrict__ r_in, float* __restrict__ dr_ds,
                                 float* __restrict__ cdf, int64_t S, int64_t B, int dim, double c) {
-    __shared__ double logC[kMaxRadiusDim];
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= S * B) return;  // warp-uniform
     const int n = dim - 1;
-    for (int k = threadIdx.x; k <= n; k += blockDim.x)
-        logC[k] = lgamma((double)dim) - lgamma((double)k + 1.0) - lgamma((double)(dim - k));
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S * B) return;
     const double s = (double)sigma[i % B];
     const double r = (double)r_in[i];
     const double sc = sqrt(c);
+    const double lgd = lgamma((double)dim);
     double m = -1e300;
-    for (int k = 0; k <= n; ++k) {
+    for (int k = lane; k <= n; k += 32) {
         const double b = (n - 2 * k) * sc;
-        m = fmax(m, logC[k] + 0.5 * b * b * s * s);
+        m = fmax(m, lgd - lgamma((double)k + 1.0) - lgamma((double)(dim - k)) + 0.5 * b * b * s * s);
     }
-    double num = 0.0, den = 0.0, dnum = 0.0, dden = 0.0;
+    m = warp_max_d(m);
+    double num = 0.0, den = 0.0, dnum = 0.0, dden = 0.0, dfr = 0.0;
     const double gauss_r = -r * r / (2.0 * s * s);
-    for (int k = 0; k <= n; ++k) {
+    for (int k = lane; k <= n; k += 32) {
         const double b = (n - 2 * k) * sc;
         const double sg = (k & 1) ? -1.0 : 1.0;
-        const double w = exp(logC[k] + 0.5 * b * b * s * s - m);   // C e^{b^2 s^2/2}, scaled
-        const double w0 = exp(logC[k] - m);                        // C, scaled
+        const double lc = lgd - lgamma((double)k + 1.0) - lgamma((double)(dim - k));
+        const double w = exp(lc + 0.5 * b * b * s * s - m);   // C e^{b^2 s^2/2}, scaled
+        const double w0 = exp(lc - m);                        // C, scaled
         const double eA = erf((r - b * s * s) / (s * kSqrt2));
         const double eB = erf(b * s / kSqrt2);
         num += sg * w * (eA + eB);
         den += sg * w * (1.0 + eB);
         // d/ds: b^2 s w (.) + sqrt(2/pi) C [(-r/s^2 - b) e^{-r^2/2s^2 + r b} + b]
-        const double ex = exp(logC[k] + gauss_r + r * b - m);
+        const double ex = exp(lc + gauss_r + r * b - m);
         dnum += sg * (b * b * s * w * (eA + eB) + kSqrt2OverPi * ((-r / (s * s) - b) * ex + b * w0));
         dden += sg * (b * b * s * w * (1.0 + eB) + kSqrt2OverPi * b * w0);
+        dfr += sg * ex;   // rho(r) numerator: sum_k sg C e^{-r^2/2s^2 + r b}
     }
-    const double F = num / den;
-    const double dF_ds = (dnum - F * dden) / den;
-    // rho(r) = dF/dr = sum_k sg C e^{b^2 s^2/2} (2/sqrt(pi)) e^{-A^2} / (s sqrt2) / den
-    double dF_dr = 0.0;
-    for (int k = 0; k <= n; ++k) {
-        const double b = (n - 2 * k) * sc;
-        const double sg = (k & 1) ? -1.0 : 1.0;
-        dF_dr += sg * exp(logC[k] + gauss_r + r * b - m);
+    num = warp_sum_d(num); den = warp_sum_d(den); dnum = warp_sum_d(dnum); dden = warp_sum_d(dden); dfr = warp_sum_d(dfr);
+    if (lane == 0) {
+        const double F = num / den;
+        const double dF_ds = (dnum - F * dden) / den;
+        const double dF_dr = dfr * kSqrt2OverPi / s / den;
+        dr_ds[i] = (float)(-dF_ds / dF_dr);
+        if (cdf) cdf[i] = (float)F;
     }
-    dF_dr *= kSqrt2OverPi / s / den;
-    dr_ds[i] = (float)(-dF_ds / dF_dr);
-    if (cdf) cdf[i] = (float)F;
 }
 
 // ---- expmap_polar: z = project(mu (+) tanh(sc r/2) alpha/(sc |alpha|)) ----------------------------------------
@@ -298,7 +299,7 @@ extern "C" int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, flo
     if (B < 0 || dim < 1 || dim > kMaxRadiusDim) return HVAE_ESHAPE;
     if (B == 0) return HVAE_OK;
     if (!sigma || !logZ) return HVAE_EARG;
-    k_hradius_lognorm<<<(unsigned)((B + 31) / 32), 32, 0, (cudaStream_t)stream>>>(sigma, logZ, dlogZ_dsigma, B, (int)dim,
+    k_hradius_lognorm<<<(unsigned)((B + 3) / 4), 128, 0, (cudaStream_t)stream>>>(sigma, logZ, dlogZ_dsigma, B, (int)dim,
                                                                                      (double)c);
     return check_launch();
 }
@@ -320,7 +321,7 @@ extern "C" int hvae_hradius_rgrad_f32(const float* sigma, const float* r, float*
     if (S == 0 || B == 0) return HVAE_OK;
     if (!sigma || !r || !dr_dsigma) return HVAE_EARG;
     const int64_t n = S * B;
-    k_hradius_rgrad<<<(unsigned)((n + 31) / 32), 32, 0, (cudaStream_t)stream>>>(sigma, r, dr_dsigma, cdf, S, B, (int)dim,
+    k_hradius_rgrad<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(sigma, r, dr_dsigma, cdf, S, B, (int)dim,
                                                                                    (double)c);
     return check_launch();
 }

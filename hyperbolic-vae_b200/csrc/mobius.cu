@@ -341,23 +341,24 @@ k_mobius_bwd_x(const float* __restrict__ x, const float* __restrict__ M, const f
 constexpr int kMobGmThreads = 128;
 constexpr int kMobGmTB = 32;  // rows per smem stage of gmx
 
+template <int PC /* planes per CTA: 8, 16 or 32 */>
 __global__ void __launch_bounds__(kMobGmThreads)
 k_mobius_bwd_m(const float* __restrict__ x, const float* __restrict__ gmx, float* __restrict__ wM, int64_t B, int F, int P,
                int rows_per_slab) {
-    __shared__ float gs[kMobGmTB][kMobChunk];
+    __shared__ float gs[kMobGmTB][PC];
     const int f = blockIdx.x * kMobGmThreads + threadIdx.x;
-    const int j0 = blockIdx.y * kMobChunk;
-    const int jn = min(kMobChunk, P - j0);
+    const int j0 = blockIdx.y * PC;
+    const int jn = min(PC, P - j0);
     const int slab = blockIdx.z;
     const int64_t bs = (int64_t)slab * rows_per_slab;
     const int64_t be = min(B, bs + (int64_t)rows_per_slab);
-    float acc[kMobChunk];
+    float acc[PC];
 #pragma unroll
-    for (int j = 0; j < kMobChunk; ++j) acc[j] = 0.0f;
+    for (int j = 0; j < PC; ++j) acc[j] = 0.0f;
     for (int64_t b0 = bs; b0 < be; b0 += kMobGmTB) {
         __syncthreads();
-        for (int i = threadIdx.x; i < kMobGmTB * kMobChunk; i += kMobGmThreads) {
-            const int bb = i / kMobChunk, jj = i - bb * kMobChunk;
+        for (int i = threadIdx.x; i < kMobGmTB * PC; i += kMobGmThreads) {
+            const int bb = i / PC, jj = i - bb * PC;
             gs[bb][jj] = (b0 + bb < be && jj < jn) ? __ldg(gmx + (b0 + bb) * P + j0 + jj) : 0.0f;
         }
         __syncthreads();
@@ -366,7 +367,7 @@ k_mobius_bwd_m(const float* __restrict__ x, const float* __restrict__ gmx, float
             for (int bb = 0; bb < bn; ++bb) {
                 const float xv = __ldg(x + (b0 + bb) * F + f);
 #pragma unroll
-                for (int j = 0; j < kMobChunk; j += 4) {
+                for (int j = 0; j < PC; j += 4) {
                     const float4 g4 = *reinterpret_cast<const float4*>(&gs[bb][j]);
                     acc[j] = fmaf(g4.x, xv, acc[j]); acc[j + 1] = fmaf(g4.y, xv, acc[j + 1]);
                     acc[j + 2] = fmaf(g4.z, xv, acc[j + 2]); acc[j + 3] = fmaf(g4.w, xv, acc[j + 3]);
@@ -376,7 +377,7 @@ k_mobius_bwd_m(const float* __restrict__ x, const float* __restrict__ gmx, float
     }
     if (f < F) {
 #pragma unroll
-        for (int j = 0; j < kMobChunk; ++j)
+        for (int j = 0; j < PC; ++j)
             if (j < jn) wM[((int64_t)slab * P + j0 + j) * F + f] = acc[j];
     }
 }
@@ -389,8 +390,10 @@ __global__ void k_mob_reduce_slabs(const float* __restrict__ w, float* __restric
     out[i] = s;
 }
 
+inline int mob_pc(int64_t P) { return P <= 8 ? 8 : (P <= 16 ? 16 : 32); }
 inline int mob_slabs(int64_t B, int64_t F, int64_t P) {
-    const int64_t tiles = ((F + kMobGmThreads - 1) / kMobGmThreads) * ((P + kMobChunk - 1) / kMobChunk);
+    const int pc = mob_pc(P);
+    const int64_t tiles = ((F + kMobGmThreads - 1) / kMobGmThreads) * ((P + pc - 1) / pc);
     int64_t want = (4 * kNumSMs + tiles - 1) / tiles;
     const int64_t maxs = (B + kMobGmTB - 1) / kMobGmTB;
     if (want > maxs) want = maxs;
@@ -429,9 +432,11 @@ int mob_bwd_launch(const float* x, const float* M, const float* mx, const float*
     if (gM) {
         const int slabs = mob_slabs(B, F, P);
         const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kMobGmTB - 1) / kMobGmTB * kMobGmTB);
-        dim3 grid((unsigned)((F + kMobGmThreads - 1) / kMobGmThreads), (unsigned)((P + kMobChunk - 1) / kMobChunk),
-                  (unsigned)slabs);
-        k_mobius_bwd_m<<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
+        const int pc = mob_pc(P);
+        dim3 grid((unsigned)((F + kMobGmThreads - 1) / kMobGmThreads), (unsigned)((P + pc - 1) / pc), (unsigned)slabs);
+        if (pc == 8)       k_mobius_bwd_m<8><<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
+        else if (pc == 16) k_mobius_bwd_m<16><<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
+        else               k_mobius_bwd_m<32><<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
         const int64_t n = P * F;
         k_mob_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wM, gM, n, slabs);
     }
