@@ -1,0 +1,135 @@
+"""GPU: the rest of the drop-in API surface against the oracle — manifold helper methods, the free
+functions logdetexp / normdist2plane, over-parameterised Riemannian layers, sample-dim broadcasting, error behaviour."""
+import pytest
+import torch
+
+from util_parity import assert_parity, kappa, rtol_grad, rtol_val
+
+pytestmark = pytest.mark.gpu
+
+
+def _balls(c):
+    import hvae
+    from oracle.geoopt_min import PoincareBall as OBall
+
+    return hvae.PoincareBall(c), OBall(c)
+
+
+@pytest.mark.parametrize("c", [0.5, 1.0, 1.4])
+def test_manifold_helper_methods(c):
+    hb, ob = _balls(c)
+    assert hb.c_value == float(ob.c)
+    torch.manual_seed(1)
+    x = ob.expmap0(torch.randn(40, 6) * 0.4).detach()
+    y = ob.expmap0(torch.randn(40, 6) * 0.5).detach()
+    v = torch.randn(40, 6)
+    xc, yc, vc = x.cuda(), y.cuda(), v.cuda()
+    for name, a, b in (
+        ("lambda_x", hb.lambda_x(xc, keepdim=True), ob.lambda_x(x, keepdim=True)),
+        ("transp0", hb.transp0(yc, vc), ob.transp0(y, v)),
+        ("transp", hb.transp(xc, yc, vc), ob.transp(x, y, v)),
+        ("projx", hb.projx(xc * 3), ob.projx(x * 3)),
+        ("egrad2rgrad", hb.egrad2rgrad(xc, vc), ob.egrad2rgrad(x, v)),
+        ("inner", hb.inner(xc, vc, vc.flip(0)), ob.inner(x, v, v.flip(0))),
+        ("retr", hb.retr(xc, vc * 0.1), ob.retr(x, v * 0.1)),
+        ("dist", hb.dist(xc, yc, keepdim=True), ob.dist(x, y, keepdim=True)),
+    ):
+        torch.testing.assert_close(a.cpu(), torch.Tensor(b), rtol=2e-5, atol=1e-6, msg=name)
+    assert hb.origin(6, device="cuda").shape == (6,) and float(hb.origin(3, 4).abs().sum()) == 0.0
+    assert hb.check_point_on_manifold(xc) and not hb.check_point_on_manifold(xc * 10)
+    with pytest.raises(ValueError):
+        hb.assert_check_point_on_manifold(xc * 10)
+
+
+def test_free_functions_logdetexp_and_normdist2plane():
+    from hvae import manifolds as HM
+    from oracle import ref_port as R
+
+    hb, ob = _balls(1.0)
+    torch.manual_seed(2)
+    x = ob.expmap0(torch.randn(30, 5) * 0.4).detach()
+    y = ob.expmap0(torch.randn(30, 5) * 0.5).detach()
+    a = HM.logdetexp(hb, x.cuda(), y.cuda(), keepdim=True)
+    b = R.logdetexp(ob, x.double(), y.double(), keepdim=True)
+    torch.testing.assert_close(a.cpu().double(), b, rtol=2e-5, atol=2e-6)
+    # normdist2plane through the expanded layout GeodesicLayer uses (layers.py:98-121)
+    P = 7
+    pa = ob.expmap0(torch.randn(P, 5) * 0.3).detach()
+    pp = torch.randn(P, 5) * 0.4
+    xe = x.cuda().unsqueeze(-2).expand(30, P, 5)
+    out = HM.normdist2plane(hb, xe, pa.cuda(), pp.cuda(), signed=True, norm=True)
+    ref = R.normdist2plane(ob, x.unsqueeze(-2).expand(30, P, 5), pa, pp, signed=True, norm=True)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=5e-6)  # fp32 vs fp32, ill-conditioned pairs included
+    with pytest.raises(NotImplementedError):
+        HM.normdist2plane(hb, x.cuda(), pa.cuda()[0:1].expand(30, 5), pp.cuda()[0:1].expand(30, 5))
+
+
+@pytest.mark.parametrize("kind", ["mobius", "geodesic"])
+def test_over_param_layers(kind):
+    import hvae
+    from hvae import layers as HL
+    from oracle import ref_port as R
+    from oracle.geoopt_min import PoincareBall as OBall
+
+    torch.manual_seed(3)
+    c, Fin, Pout, B = 1.0, 12, 9, 50
+    o = (R.MobiusLayer if kind == "mobius" else R.GeodesicLayer)(Fin, Pout, OBall(c), over_param=True)
+    h = (HL.MobiusLayer if kind == "mobius" else HL.GeodesicLayer)(Fin, Pout, hvae.PoincareBall(c), over_param=True)
+    assert h._bias.shape == (Pout, Fin)
+    with torch.no_grad():
+        h._weight.copy_(o._weight)
+        h._bias.copy_(torch.Tensor(o._bias.detach()))
+    h = h.cuda()
+    ob = OBall(c)
+    x = (ob.expmap0(torch.randn(B, Fin) * 0.4).detach() if kind == "geodesic" else torch.randn(B, Fin))
+    g = torch.randn(B, Pout)
+    xo = x.clone().requires_grad_(True)
+    yo = o(xo)
+    yo.backward(g)
+    xh = x.cuda().requires_grad_(True)
+    yh = h(xh)
+    yh.backward(g.cuda())
+    torch.testing.assert_close(yh.cpu(), yo.detach(), rtol=3e-5, atol=3e-6)
+    torch.testing.assert_close(xh.grad.cpu(), xo.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(h._weight.grad.cpu(), o._weight.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(h._bias.grad.cpu(), torch.Tensor(o._bias.grad), rtol=1e-4, atol=1e-5)
+
+
+def test_wrapped_normal_sample_dims_and_softplus():
+    import hvae
+    from hvae.distributions import WrappedNormal
+    from oracle import ref_port as R
+    from oracle.geoopt_min import PoincareBall as OBall
+
+    torch.manual_seed(4)
+    c, B, D, S = 0.7, 20, 4, 3
+    ob = OBall(c)
+    mu = ob.expmap0(torch.randn(B, D) * 0.4).detach()
+    raw = torch.randn(B, D)
+    eps = torch.randn(S, B, D)
+    q_o = R.WrappedNormal(mu, raw, ob, softplus=True)
+    z_o = q_o.rsample(torch.Size([S]), eps=eps)
+    q_h = WrappedNormal(mu.cuda(), raw.cuda(), hvae.PoincareBall(c), softplus=True)
+    z_h = q_h.rsample(torch.Size([S]), eps=eps.cuda())
+    assert z_h.shape == (S, B, D)
+    torch.testing.assert_close(z_h.cpu(), z_o, rtol=3e-5, atol=3e-6)
+    lp_h = q_h.log_prob(z_h)
+    assert lp_h.shape == (S, B, 1)
+    torch.testing.assert_close(lp_h.cpu(), q_o.log_prob(z_o), rtol=3e-5, atol=3e-5)
+    assert q_h.rsample().shape == (B, D) and q_h.sample(torch.Size([2])).shape == (2, B, D)
+    assert q_h.batch_shape == (B,) and q_h.event_shape == (D,) and q_h.mean is q_h.loc
+    with pytest.raises(ValueError):
+        WrappedNormal((mu * 50).cuda(), raw.cuda(), hvae.PoincareBall(c), validate_args=True)
+
+
+def test_unknown_shapes_fail_loudly():
+    import hvae
+    from hvae import ops
+
+    ball = hvae.PoincareBall(1.0)
+    with pytest.raises(RuntimeError, match="shape"):
+        ops.expmap0(torch.randn(4, 2000, device="cuda"), ball.c_value)  # D > 1024 is not supported by the row kernels
+    with pytest.raises(RuntimeError, match="float32"):
+        ball.expmap0(torch.randn(4, 2, device="cuda", dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        ball.expmap0(torch.randn(4, 2, device="cuda"), dim=0)
