@@ -11,6 +11,7 @@
 // Larger P runs the same kernel in chunks of 32 planes (correct, not fast); the tcgen05 path is K1-TC.
 #include "hvae_common.cuh"
 #include "row_maps.cuh"
+#include "mobius_row.cuh"
 
 namespace hvae {
 
@@ -104,29 +105,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// per-row scalars of y = psi * mx (pre-projection), with derivative pieces
-struct MobRow {
-    float xn_raw, xn, mxn_raw, mxn, ax, at, kappa, theta, t, psi, ypn;
-    bool zero_row, hit;
-};
-
-__device__ __forceinline__ void mob_row_scalars(float x2, float mx2, bool all_zero, const Ball& ball, MobRow& r) {
-    r.xn_raw = sqrtf(x2);
-    r.xn = fmaxf(r.xn_raw, kMinNorm);
-    r.mxn_raw = sqrtf(mx2);
-    r.mxn = fmaxf(r.mxn_raw, kMinNorm);
-    r.ax = ball.sc * r.xn;
-    r.at = artanh_c(r.ax);                // artanh(clamp(sc xn)); artan_k = at/sc
-    r.kappa = r.at / r.xn;                // theta = sc * (mxn/xn * at/sc) = mxn * at / xn
-    r.theta = r.mxn / r.xn * r.at;
-    r.t = tanh_c(r.theta);
-    r.psi = ball.rsc * r.t / r.mxn;       // y = psi * mx
-    r.zero_row = all_zero;
-    const float yn = fmaxf(ball.rsc * r.t * (r.mxn_raw / r.mxn), kMinNorm);  // |y_pre| (= t/sc unless mxn was clamped)
-    r.ypn = yn;
-    r.hit = (!all_zero) && (yn > ball.maxnorm);
 }
 
 template <int EPLF, int R>
@@ -267,31 +245,7 @@ k_mobius_bwd_x(const float* __restrict__ x, const float* __restrict__ M, const f
         // per-row coefficients: gmx_j = alpha * gy_j + beta * mx_j ;  gx += gxn_coef * x
         float alpha[R], beta[R], gxc[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            MobRow rs;
-            mob_row_scalars(x2[r], mx2[r], !nz[r], ball, rs);
-            if (rs.zero_row) { alpha[r] = beta[r] = gxc[r] = 0.0f; continue; }
-            // projection backward on y_pre = psi*mx (norm ypn):  g' = s (g - (<g,ypre>/ypn^2) ypre)
-            float a_ = 1.0f, sub = 0.0f;  // g'_j = a_ * gy_j - sub * mx_j
-            float gdm_p = gdm[r];         // <g', mx>
-            if (rs.hit) {
-                const float s = ball.maxnorm / rs.ypn;
-                const float q = rs.psi * gdm[r] / (rs.ypn * rs.ypn);  // <g,ypre>/ypn^2, ypre = psi mx
-                a_ = s;
-                sub = s * q * rs.psi;
-                gdm_p = s * gdm[r] - sub * mx2[r];
-            }
-            // y_pre = psi(xn, mxn) mx
-            const float sech2 = (1.0f - rs.t * rs.t) * tanh_mask(rs.theta);
-            const float dpsi_dmxn = (sech2 * rs.kappa - rs.t / rs.mxn) * ball.rsc / rs.mxn;
-            // kappa'(xn) = (artanh'(sc xn) sc xn - artanh(sc xn)) / xn^2
-            const float dkappa = (artanh_grad(rs.ax) * rs.ax - rs.at) / (rs.xn * rs.xn);
-            const float dpsi_dxn = sech2 * dkappa * ball.rsc;
-            const float cm = (rs.mxn_raw >= kMinNorm) ? dpsi_dmxn * gdm_p / rs.mxn_raw : 0.0f;
-            alpha[r] = rs.psi * a_;
-            beta[r] = -rs.psi * sub + cm;
-            gxc[r] = (rs.xn_raw >= kMinNorm) ? dpsi_dxn * gdm_p / rs.xn_raw : 0.0f;
-        }
+        for (int r = 0; r < R; ++r) mob_bwd_coefs(x2[r], mx2[r], gdm[r], !nz[r], ball, alpha[r], beta[r], gxc[r]);
         for (int ch = 0; ch < nchunks; ++ch) {
             const int j0 = ch * kMobChunk;
             const int jn = min(kMobChunk, P - j0);

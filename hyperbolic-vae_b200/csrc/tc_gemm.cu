@@ -24,6 +24,7 @@
 
 #include "hvae_common.cuh"
 #include "gyro_pair.cuh"
+#include "mobius_row.cuh"
 
 namespace hvae {
 namespace tc {
@@ -59,6 +60,8 @@ struct Params {
     float* D;              // (M, N) row-major output
     int64_t M, N, K;
     const float* rowscale; // PLAIN: optional (M,)
+    const float* axpy_x;   // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
+    const float* axpy_coef;//        (M,)
     float* rowsq;          // PLAIN: optional [n_tiles][M] partial sums of acc^2
     const float* x2;       // GYRO: (M,) |x|^2
     const float* p2;       // GYRO: (N,) |p|^2
@@ -68,6 +71,7 @@ struct Params {
     float* rowdot;         // ROWDOT: [n_tiles][M] partial sums of acc * xrow
     const float* mxsq;     // MOBIUS: [q_tiles][M] partials of |mx_b|^2 (from the Gram row-dot pass)
     int q_tiles;
+    float* mxsq_out;       // MOBIUS: optional (M,) |mx_b|^2 as used by the epilogue (saved for the backward)
     Ball ball;             // MOBIUS
 };
 
@@ -290,6 +294,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int qt = 0; qt < prm.q_tiles; ++qt) mx2 += __ldg(prm.mxsq + (int64_t)qt * prm.M + m);
                 }
                 mx2 = fmaxf(mx2, 0.0f);
+                if (prm.mxsq_out && row_ok && nt == 0 && cg == 0) prm.mxsq_out[m] = mx2;
                 const Ball& bl = prm.ball;
                 const float xn = fmaxf(sqrt_fast(x2), kMinNorm);
                 const float mxn_raw = sqrt_fast(mx2), mxn = fmaxf(mxn_raw, kMinNorm);
@@ -372,12 +377,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int r = 4 * j + (lane >> 3), c4 = (lane & 7) * 4;
-                            const float4 t4 = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
-                            if (mrow0 + r < prm.M) *reinterpret_cast<float4*>(prm.D + (mrow0 + r) * prm.N + n0 + c4) = t4;
+                            float4 t4 = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+                            if (mrow0 + r < prm.M) {
+                                if (EPI == EPI_PLAIN && prm.axpy_x) {
+                                    const float cf = __ldg(prm.axpy_coef + mrow0 + r);
+                                    const float4 xv = __ldg(reinterpret_cast<const float4*>(prm.axpy_x + (mrow0 + r) * prm.N + n0 + c4));
+                                    t4.x = fmaf(cf, xv.x, t4.x); t4.y = fmaf(cf, xv.y, t4.y);
+                                    t4.z = fmaf(cf, xv.z, t4.z); t4.w = fmaf(cf, xv.w, t4.w);
+                                }
+                                *reinterpret_cast<float4*>(prm.D + (mrow0 + r) * prm.N + n0 + c4) = t4;
+                            }
                         }
                         __syncwarp();
                     } else if (row_ok) {
                         float* dst = prm.D + m * prm.N + n0;
+                        if (EPI == EPI_PLAIN && prm.axpy_x) {
+                            const float cf = __ldg(prm.axpy_coef + m);
+                            const float* xr = prm.axpy_x + m * prm.N + n0;
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < prm.N) v[i] = fmaf(cf, __ldg(xr + i), v[i]);
+                        }
                         if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -440,7 +459,7 @@ __global__ void k_rows_to_bf16(const float* __restrict__ in, __nv_bfloat16* __re
 // (R, C) fp32 row-major -> (C, R) bf16 row-major (32x32 smem tiles)
 __global__ void k_transpose_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C) {
     __shared__ float tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // row tiles on grid.x (may be > 65535)
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int r = r0 + i, c = c0 + threadIdx.x;
         tile[i][threadIdx.x] = (r < R && c < C) ? in[(int64_t)r * C + c] : 0.0f;
@@ -454,7 +473,8 @@ __global__ void k_transpose_to_bf16(const float* __restrict__ in, __nv_bfloat16*
 
 // Mobius pass 2: y_b = psi(|x_b|, |mx_b|) mx_b, projected.  one warp per row.
 __global__ void k_mobius_rescale_rows(const float* __restrict__ mx, const float* __restrict__ x2, const float* __restrict__ rowsq,
-                                      float* __restrict__ y, int64_t B, int64_t P, int n_tiles, Ball ball) {
+                                      float* __restrict__ y, float* __restrict__ mxsq_out, int64_t B, int64_t P, int n_tiles,
+                                      Ball ball) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -463,6 +483,7 @@ __global__ void k_mobius_rescale_rows(const float* __restrict__ mx, const float*
         for (int t = lane; t < n_tiles; t += 32) s += rowsq[(int64_t)t * B + b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (mxsq_out && lane == 0) mxsq_out[b] = s;
         const float xn = fmaxf(sqrtf(x2[b]), kMinNorm);
         const float mxn_raw = sqrtf(s), mxn = fmaxf(mxn_raw, kMinNorm);
         const float th = mxn / xn * artanh_c(ball.sc * xn);
@@ -472,6 +493,97 @@ __global__ void k_mobius_rescale_rows(const float* __restrict__ mx, const float*
         if (yn > ball.maxnorm) scale = scale / yn * ball.maxnorm;
         if (s == 0.0f) scale = 0.0f;  // all-zero mx row -> exact zero (geoopt's `cond`)
         for (int64_t j = lane; j < P; j += 32) y[b * P + j] = scale * mx[b * P + j];
+    }
+}
+
+// (R, C) bf16 row-major -> (C, R) bf16 row-major, 64x64 tiles, 4-byte accesses both ways (R, C even)
+__global__ void __launch_bounds__(256) k_transpose_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                        int64_t R, int64_t C) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t c0 = (int64_t)blockIdx.y * 64, r0 = (int64_t)blockIdx.x * 64;  // row tiles on grid.x
+    for (int i = ty; i < 64; i += 8) {
+        const int64_t r = r0 + i, c = c0 + 2 * tx;
+        __nv_bfloat162 v = __floats2bfloat162_rn(0.0f, 0.0f);
+        if (r < R && c < C) v = *reinterpret_cast<const __nv_bfloat162*>(in + r * C + c);
+        tile[i][2 * tx] = v.x;
+        tile[i][2 * tx + 1] = v.y;
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 8) {
+        const int64_t c = c0 + i, r = r0 + 2 * tx;
+        if (c < C && r < R) {
+            __nv_bfloat162 v;
+            v.x = tile[2 * tx][i];
+            v.y = tile[2 * tx + 1][i];
+            *reinterpret_cast<__nv_bfloat162*>(out + c * R + r) = v;
+        }
+    }
+}
+
+// Mobius backward, row pass (one warp per row): from the saved output y = s psi mx and |mx|^2 recover the coefficients of
+//   gmx_b = alpha_b gy_b + beta_b mx_b   (written as bf16, the A operand of both backward GEMMs)   and   gx_b += gxc_b x_b
+__global__ void __launch_bounds__(256)
+k_mobius_tc_bwd_rows(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mxsq,
+                     const float* __restrict__ gy, __nv_bfloat16* __restrict__ gmx16, float* __restrict__ gxc_out, int64_t B,
+                     int64_t F, int64_t P, Ball ball) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool v4 = (P & 3) == 0, f4 = (F & 3) == 0;
+    for (int64_t b = warp; b < B; b += nw) {
+        float x2 = 0.0f, gdy = 0.0f;
+        const float* xr = x + b * F;
+        if (f4) {
+            for (int64_t i = lane * 4; i < F; i += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xr + i));
+                x2 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            }
+        } else {
+            for (int64_t i = lane; i < F; i += 32) { const float a = __ldg(xr + i); x2 = fmaf(a, a, x2); }
+        }
+        const float* yr = y + b * P;
+        const float* gr = gy + b * P;
+        if (v4) {
+            for (int64_t i = lane * 4; i < P; i += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(yr + i));
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gr + i));
+                gdy += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+            }
+        } else {
+            for (int64_t i = lane; i < P; i += 32) gdy = fmaf(__ldg(yr + i), __ldg(gr + i), gdy);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+            gdy += __shfl_xor_sync(0xffffffffu, gdy, o);
+        }
+        const float mx2 = mxsq[b];
+        MobRow rs;
+        mob_row_scalars(x2, mx2, mx2 == 0.0f, ball, rs);
+        // y = sy * mx with sy = psi (times maxnorm/|y_pre| when the projection clipped the row)
+        float sy = rs.psi;
+        if (rs.hit) sy *= ball.maxnorm / rs.ypn;
+        const float inv = (rs.zero_row || sy == 0.0f) ? 0.0f : 1.0f / sy;
+        float alpha, beta, gxc;
+        mob_bwd_coefs(x2, mx2, gdy * inv, rs.zero_row || sy == 0.0f, ball, alpha, beta, gxc);
+        const float by = beta * inv;  // gmx = alpha gy + (beta / sy) y
+        __nv_bfloat16* dst = gmx16 + b * P;
+        if (v4) {
+            for (int64_t i = lane * 4; i < P; i += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(yr + i));
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gr + i));
+                __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(alpha, g.x, by * a.x), fmaf(alpha, g.y, by * a.y));
+                __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(alpha, g.z, by * a.z), fmaf(alpha, g.w, by * a.w));
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dst + i) = pk;
+            }
+        } else {
+            for (int64_t i = lane; i < P; i += 32) dst[i] = __float2bfloat16_rn(fmaf(alpha, __ldg(gr + i), by * __ldg(yr + i)));
+        }
+        if (lane == 0) gxc_out[b] = gxc;
     }
 }
 
@@ -551,10 +663,31 @@ static Ws ws_layout(int64_t B, int64_t K, int64_t P) {
     return w;
 }
 
+struct WsBwd {
+    size_t gmx16, gmxT16, mt16, xT16, gxc, total;
+};
+static WsBwd ws_bwd_layout(int64_t B, int64_t F, int64_t P) {
+    WsBwd w;
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return at; };
+    w.gmx16 = take((size_t)B * P * 2);
+    w.gmxT16 = take((size_t)B * P * 2);
+    w.mt16 = take((size_t)F * P * 2);
+    w.xT16 = take((size_t)F * B * 2);
+    w.gxc = take((size_t)B * 4);
+    w.total = o;
+    return w;
+}
+
 }  // namespace tc
 }  // namespace hvae
 
 using namespace hvae;
+
+extern "C" size_t hvae_mobius_tc_bwd_workspace_bytes(int64_t B, int64_t F, int64_t P) {
+    if (B <= 0 || F <= 0 || P <= 0) return 0;
+    return tc::ws_bwd_layout(B, F, P).total;
+}
 
 extern "C" size_t hvae_tc_workspace_bytes(int64_t B, int64_t K, int64_t P) {
     if (B <= 0 || K <= 0 || P <= 0) return 0;
@@ -566,8 +699,9 @@ static int tc_check(int64_t B, int64_t K, int64_t P) {
     return HVAE_OK;
 }
 
-extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, int64_t B, int64_t F,
-                                             int64_t P, float c, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, float* mxsq_out,
+                                             int64_t B, int64_t F, int64_t P, float c, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
     if (tc_check(B, F, P) != HVAE_OK) return HVAE_ESHAPE;
     if (!x || !M || !y || !workspace) return HVAE_EARG;
     const tc::Ws L = tc::ws_layout(B, F, P);
@@ -587,7 +721,7 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
         prm.D = mx_out; prm.M = B; prm.N = P; prm.K = F; prm.rowsq = rowsq;
         int rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
         if (rc != HVAE_OK) return rc;
-        tc::k_mobius_rescale_rows<<<kNumSMs * 8, 256, 0, s>>>(mx_out, x2, rowsq, y, B, P,
+        tc::k_mobius_rescale_rows<<<kNumSMs * 8, 256, 0, s>>>(mx_out, x2, rowsq, y, mxsq_out, B, P,
                                                               (int)((P + tc::BN - 1) / tc::BN) * tc::CG, make_ball(c));
         return check_launch();
     }
@@ -599,7 +733,7 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
     auto* g16 = (__nv_bfloat16*)(ws + L.g16);
     float* rowdot = (float*)(ws + L.rowdot);
     {
-        dim3 grid((unsigned)((F + 31) / 32), (unsigned)((P + 31) / 32)), block(32, 8);
+        dim3 grid((unsigned)((P + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
         tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(M, mt16, (int)P, (int)F);
     }
     {   // G = M^T M : (F, F), contraction over P
@@ -618,8 +752,55 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
     tc::Params prm{};
     prm.D = y; prm.M = B; prm.N = P; prm.K = F; prm.x2 = x2; prm.mxsq = rowdot;
     prm.q_tiles = (int)((F + tc::BN - 1) / tc::BN) * tc::CG;
+    prm.mxsq_out = mxsq_out;
     prm.ball = make_ball(c);
     return tc::launch_gemm<tc::EPI_MOBIUS>(a16, b16, prm, s);
+}
+
+// backward of y = mobius_matvec(M, x) on the tensor cores.  y and mxsq = |M x_b|^2 are the forward's outputs:
+// mx is recovered as y / (s psi), so the (B, P) pre-activation is never stored.
+//   gmx = alpha gy + beta mx  (row pass, bf16)   gx = gmx M + gxc x   (GEMM over P)   gM = gmx^T x   (GEMM over B)
+extern "C" int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, const float* y, const float* mxsq,
+                                             const float* gy, float* gx, float* gM, int64_t B, int64_t F, int64_t P, float c,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+    if (B <= 0 || F <= 0 || P <= 0 || (B % 8) != 0 || (F % 8) != 0 || (P % 8) != 0) return HVAE_ESHAPE;
+    if (!x || !M || !y || !mxsq || !gy || !workspace || (!gx && !gM)) return HVAE_EARG;
+    const tc::WsBwd L = tc::ws_bwd_layout(B, F, P);
+    if (workspace_bytes < L.total) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* gmx16 = (__nv_bfloat16*)(ws + L.gmx16);
+    auto* gmxT16 = (__nv_bfloat16*)(ws + L.gmxT16);
+    auto* mt16 = (__nv_bfloat16*)(ws + L.mt16);
+    auto* xT16 = (__nv_bfloat16*)(ws + L.xT16);
+    float* gxc = (float*)(ws + L.gxc);
+    tc::k_mobius_tc_bwd_rows<<<kNumSMs * 8, 256, 0, s>>>(x, y, mxsq, gy, gmx16, gxc, B, F, P, make_ball(c));
+    int rc = check_launch();
+    if (rc != HVAE_OK) return rc;
+    if (gx) {
+        dim3 grid((unsigned)((P + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+        tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(M, mt16, (int)P, (int)F);  // (P, F) -> (F, P)
+        tc::Params prm{};
+        prm.D = gx; prm.M = B; prm.N = F; prm.K = P; prm.axpy_x = x; prm.axpy_coef = gxc;
+        rc = tc::launch_gemm<tc::EPI_PLAIN>(gmx16, mt16, prm, s);
+        if (rc != HVAE_OK) return rc;
+    }
+    if (gM) {
+        if (B > 0x7fffffffLL) return HVAE_ESHAPE;
+        {
+            dim3 grid((unsigned)((B + 63) / 64), (unsigned)((P + 63) / 64));
+            tc::k_transpose_bf16<<<grid, 256, 0, s>>>(gmx16, gmxT16, B, P);  // (B, P) -> (P, B)
+        }
+        {
+            dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+            tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(x, xT16, (int)B, (int)F);  // (B, F) -> (F, B)
+        }
+        tc::Params prm{};
+        prm.D = gM; prm.M = P; prm.N = F; prm.K = B;
+        rc = tc::launch_gemm<tc::EPI_PLAIN>(gmxT16, xT16, prm, s);
+        if (rc != HVAE_OK) return rc;
+    }
+    return check_launch();
 }
 
 extern "C" int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,

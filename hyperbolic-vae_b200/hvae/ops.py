@@ -630,10 +630,10 @@ def mobius_matvec(x: Tensor, M: Tensor, c: float) -> Tensor:
     xr = _rows(x)
     if _tc_eligible(xr.shape[0], xr.shape[1], M.shape[0]):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or M.requires_grad)
-        if not needs_grad and M.shape[0] % 8 == 0:
-            y = mobius_matvec_tc_infer(xr, _c(M), c)
+        if M.shape[0] % 8 == 0 and (xr.shape[0] % 8 == 0 or not needs_grad):
+            y, _ = mobius_matvec_tc(xr, _c(M), c)       # single pass; tensor-core backward
         else:
-            y, _ = mobius_matvec_tc_fwd(xr, _c(M), c)
+            y, _ = mobius_matvec_tc_fwd(xr, _c(M), c)   # ragged shapes: two-pass forward, fp32 backward
     else:
         y, _ = mobius_matvec_fwd(xr, _c(M), c)
     return y.view(*lead, M.shape[0])
@@ -819,14 +819,15 @@ def _tc_eligible(B: int, K: int, P: int) -> bool:
 
 @_op("hvae::mobius_matvec_tc_fwd", mutates_args=())
 def mobius_matvec_tc_fwd(x: Tensor, M: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    """Two-pass variant (any P): the GEMM materialises mx, a light row pass rescales; backward = the fp32 kernels."""
     C.require_cuda(x, M)
     B, F = x.shape
     P = M.shape[0]
     y, mx = x.new_empty(B, P), x.new_empty(B, P)
     ws = _workspace(C.lib().hvae_tc_workspace_bytes(B, F, P), x.device)
-    C.call("hvae_mobius_matvec_tc_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), C.ptr(mx), B, F, P, c, C.ptr(ws), ws.numel(),
-           C.stream())
-    C.launch_count += 3
+    C.call("hvae_mobius_matvec_tc_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), C.ptr(mx), None, B, F, P, c, C.ptr(ws),
+           ws.numel(), C.stream())
+    C.launch_count += 4
     return y, mx
 
 
@@ -838,23 +839,56 @@ def _(x, M, c):
 mobius_matvec_tc_fwd.register_autograd(_mm_backward, setup_context=_mm_setup)  # backward: the fp32 kernels on the saved mx
 
 
-@_op("hvae::mobius_matvec_tc_infer", mutates_args=())
-def mobius_matvec_tc_infer(x: Tensor, M: Tensor, c: float) -> Tensor:
-    """Forward-only single-pass variant: |mx_b|^2 = x_b^T (M^T M) x_b from the Gram matrix, rescale + projection
-    fused into the main GEMM's epilogue (no mx is materialised, so there is nothing for a backward to use)."""
+@_op("hvae::mobius_matvec_tc", mutates_args=())
+def mobius_matvec_tc(x: Tensor, M: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    """Single-pass variant: |mx_b|^2 = x_b^T (M^T M) x_b from the Gram matrix, rescale + projection fused into the
+    main GEMM's epilogue; mx is never materialised.  Returns (y, |mx|^2) — all the tensor-core backward needs."""
     C.require_cuda(x, M)
     B, F = x.shape
     P = M.shape[0]
-    y = x.new_empty(B, P)
+    y, mxsq = x.new_empty(B, P), x.new_empty(B)
     ws = _workspace(C.lib().hvae_tc_workspace_bytes(B, F, P), x.device)
-    C.call("hvae_mobius_matvec_tc_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), None, B, F, P, c, C.ptr(ws), ws.numel(), C.stream())
-    C.launch_count += 6
-    return y
+    C.call("hvae_mobius_matvec_tc_fwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), None, C.ptr(mxsq), B, F, P, c, C.ptr(ws),
+           ws.numel(), C.stream())
+    C.launch_count += 7
+    return y, mxsq
 
 
-@mobius_matvec_tc_infer.register_fake
+@mobius_matvec_tc.register_fake
 def _(x, M, c):
-    return x.new_empty(x.shape[0], M.shape[0])
+    return x.new_empty(x.shape[0], M.shape[0]), x.new_empty(x.shape[0])
+
+
+@_op("hvae::mobius_matvec_tc_bwd", mutates_args=())
+def mobius_matvec_tc_bwd(x: Tensor, M: Tensor, y: Tensor, mxsq: Tensor, gy: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(x, M, y, mxsq, gy)
+    B, F = x.shape
+    P = M.shape[0]
+    gx, gM = torch.empty_like(x), torch.empty_like(M)
+    ws = _workspace(C.lib().hvae_mobius_tc_bwd_workspace_bytes(B, F, P), x.device)
+    C.call("hvae_mobius_matvec_tc_bwd_f32", C.ptr(x), C.ptr(M), C.ptr(y), C.ptr(mxsq), C.ptr(gy), C.ptr(gx), C.ptr(gM),
+           B, F, P, c, C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += 6
+    return gx, gM
+
+
+@mobius_matvec_tc_bwd.register_fake
+def _(x, M, y, mxsq, gy, c):
+    return torch.empty_like(x), torch.empty_like(M)
+
+
+def _mmtc_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], output[0], output[1])
+    ctx.c = inputs[2]
+
+
+def _mmtc_backward(ctx, gy, _g):
+    x, M, y, mxsq = ctx.saved_tensors
+    gx, gM = mobius_matvec_tc_bwd(x, M, y, mxsq, _c(gy), ctx.c)
+    return gx, gM, None
+
+
+mobius_matvec_tc.register_autograd(_mmtc_backward, setup_context=_mmtc_setup)
 
 
 @_op("hvae::gyroplane_tc_fwd", mutates_args=())

@@ -159,8 +159,19 @@ int hvae_rn_kl_bwd_f32(const float* mu, const float* sigma_q, const float* z, co
  * Same math as hvae_mobius_matvec_fwd_f32 / hvae_gyroplane_fwd_f32 (a == p), operands rounded to bf16: the
  * "bf16 GEMM mode" of BASELINE.json (1e-2 tolerance).  K (= F or D) must be a multiple of 8. */
 size_t hvae_tc_workspace_bytes(int64_t B, int64_t K, int64_t P);
-int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, int64_t B, int64_t F,
-                                  int64_t P, float c, void* workspace, size_t workspace_bytes, void* stream);
+/* mx_out (B,P) optional: when given, the pre-activation is materialised (two-pass); when NULL, |mx_b|^2 comes from the
+ * Gram matrix M^T M and the rescale + projection is fused into the GEMM epilogue (single pass, needs P % 8 == 0).
+ * mxsq_out (B,) optional: |M x_b|^2 as the forward used it, the only extra state the tensor-core backward needs. */
+int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, float* y, float* mx_out, float* mxsq_out, int64_t B,
+                                  int64_t F, int64_t P, float c, void* workspace, size_t workspace_bytes, void* stream);
+/* backward of the above on the tensor cores (autograd of geoopt mobius_matvec + project; reference call site
+ * geoopt/layers/stereographic.py MobiusLinear / pvae MobiusLayer.forward): mx is recovered from y and mxsq,
+ *   gmx = alpha gy + beta mx (bf16),  gx = gmx M + gxc x  (contraction over P),  gM = gmx^T x  (contraction over B).
+ * B, F, P multiples of 8.  gx or gM may be NULL. */
+size_t hvae_mobius_tc_bwd_workspace_bytes(int64_t B, int64_t F, int64_t P);
+int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, const float* y, const float* mxsq, const float* gy,
+                                  float* gx, float* gM, int64_t B, int64_t F, int64_t P, float c, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
                               int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -51,10 +51,16 @@ def main():
         out["mobius_tc_fwd"] = {"B": B, "F": F, "P": P, "ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / pk["bf16_tflops"],
                                 "alg_bytes": 4 * (B * F + P * F + B * P), "gbs_alg": 4 * (B * F + P * F + B * P) / t / 1e9,
                                 "note": "v1 = bf16 convert + GEMM(+|mx|^2 partials, fp32 mx out) + rescale pass: 3 passes over B*P fp32"}
-        t = timeit(lambda: ops.mobius_matvec_tc_infer(x, M, c))
+        t = timeit(lambda: ops.mobius_matvec_tc(x, M, c))
         out["mobius_tc_fwd_fused"] = {"B": B, "F": F, "P": P, "ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / pk["bf16_tflops"],
                                       "gbs_alg": 4 * (B * F + P * F + B * P) / t / 1e9, "frac_hbm": 4 * (B * F + P * F + B * P) / t / 1e9 / pk["hbm_gbs"],
                                       "note": "single pass over the output: Gram row scale + fused rescale epilogue (forward-only)"}
+        y, mxsq = ops.mobius_matvec_tc(x, M, c)
+        gy = torch.randn_like(y)
+        t = timeit(lambda: ops.mobius_matvec_tc_bwd(x, M, y, mxsq, gy, c))
+        out["mobius_tc_bwd"] = {"B": B, "F": F, "P": P, "ms": t * 1e3, "tflops": 2 * fl / t / 1e12, "frac_tensor": 2 * fl / t / 1e12 / pk["bf16_tflops"],
+                                "note": "row pass (bf16 gmx) + bf16 transpose + 2 GEMMs (gx over P with fused axpy, gM over B)"}
+        del y, gy
         t = timeit(lambda: ops.gyroplane_tc_fwd(x, pts, None, c, ops.GYRO_SIGNED))
         out["gyroplane_tc_fwd"] = {"B": B, "D": F, "P": P, "ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / pk["bf16_tflops"],
                                    "alg_bytes": 4 * (B * F + 2 * P * F + B * P), "gbs_alg": 4 * (B * F + 2 * P * F + B * P) / t / 1e9,

@@ -15,7 +15,7 @@ x = ops.expmap0(torch.randn(B, F, device=dev, generator=g) * 0.1, c)
 M = torch.randn(P, F, device=dev, generator=g) / F ** 0.5
 pts = ops.expmap0(torch.randn(P, F, device=dev, generator=g) * 0.03, c)
 for _ in range(2):
-    y = ops.mobius_matvec_tc_infer(x, M, c)
+    y, _ = ops.mobius_matvec_tc(x, M, c)
     o = ops.gyroplane_tc_fwd(x, pts, None, c, ops.GYRO_SIGNED)
 torch.cuda.synchronize()
 print("ok", float(y.abs().mean()), float(o.abs().mean()))

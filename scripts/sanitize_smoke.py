@@ -49,7 +49,7 @@ ops.set_gemm_mode("bf16")
 x = ball.expmap0(torch.randn(300, 72, device=dev) * 0.1)
 M = torch.randn(200, 72, device=dev) * 0.1
 ops.mobius_matvec_tc_fwd(x, M, c)
-ops.mobius_matvec_tc_infer(x, M, c)
+ops.mobius_matvec_tc(x, M, c)
 ops.gyroplane_tc_fwd(x, ball.expmap0(M), None, c, ops.GYRO_SIGNED)
 ops.set_gemm_mode("fp32")
 torch.cuda.synchronize()

@@ -44,10 +44,53 @@ def test_mobius_tc_forward(B, F, P):
     assert ((y32 - y).abs().cpu() / scale.float()).max() < 1e-2
     # forward-only single-pass variant (Gram-matrix row scale fused into the GEMM epilogue)
     if P % 8 == 0:
-        yi = ops.mobius_matvec_tc_infer(x.cuda(), M.cuda(), hvae.PoincareBall(c).c_value)
+        yi, mxsq = ops.mobius_matvec_tc(x.cuda(), M.cuda(), hvae.PoincareBall(c).c_value)
         torch.cuda.synchronize()
         erri = ((yi.double().cpu() - ref).abs() / scale).max()
         assert erri < 1e-2, erri
+        sq_ref = mx_ref.pow(2).sum(-1)
+        assert ((mxsq.double().cpu() - sq_ref).abs() / sq_ref).max() < 2e-2
+
+
+# tensor-core backward (row pass + two GEMMs) against float64 autograd of the oracle; includes rows clipped by the
+# projection (scale 3.0) and ragged tiles in every dimension
+@pytest.mark.parametrize("B,F,P,scale", [(128, 64, 128, 0.5), (256, 128, 256, 0.5), (1000, 512, 296, 0.5), (4096, 256, 1024, 0.5),
+                                          (512, 128, 384, 8.0), (19000, 512, 600, 0.5)])
+def test_mobius_tc_backward(B, F, P, scale):
+    import hvae
+    from hvae import ops
+    from oracle.geoopt_min.manifolds.stereographic import math as gm
+
+    torch.manual_seed(B + 7 * P)
+    c = 1.0
+    ob = _oball(c)
+    x = ob.expmap0(torch.randn(B, F) * 0.5 / F ** 0.5).detach()
+    M = torch.randn(P, F) / F ** 0.5 * 0.7 * scale
+    gy = torch.randn(B, P)
+    k = torch.tensor(-c, dtype=torch.float64)
+    xd, Md = x.double().requires_grad_(True), M.double().requires_grad_(True)
+    with gm.fp32_semantics():
+        ref = gm.project(gm.mobius_matvec(Md, xd, k=k), k=k)
+    ref.backward(gy.double())
+    ops.set_gemm_mode("bf16")
+    try:
+        xc, Mc = x.cuda().requires_grad_(True), M.cuda().requires_grad_(True)
+        y = ops.mobius_matvec(xc, Mc, hvae.PoincareBall(c).c_value)
+        y.backward(gy.cuda())
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode("fp32")
+    if scale > 1.0:
+        assert float((ref.norm(dim=-1) > 0.995).float().mean()) > 0.2  # the clipped branch is exercised
+    # bf16 operands: errors are relative to the row / matrix scale of each gradient (sums over P resp. B of rounded terms)
+    gx_ref, gM_ref = xd.grad, Md.grad
+    ex = (xc.grad.double().cpu() - gx_ref).norm(dim=-1) / gx_ref.norm(dim=-1).clamp_min(1e-12)
+    assert float(ex.max()) < 3e-2, float(ex.max())
+    assert float(ex.mean()) < 1e-2, float(ex.mean())
+    eM = (Mc.grad.double().cpu() - gM_ref).norm() / gM_ref.norm()
+    assert float(eM) < 1e-2, float(eM)
+    eMr = (Mc.grad.double().cpu() - gM_ref).norm(dim=-1) / gM_ref.norm(dim=-1).clamp_min(1e-12)
+    assert float(eMr.max()) < 3e-2, float(eMr.max())
 
 
 @pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024), (19000, 256, 520)])
