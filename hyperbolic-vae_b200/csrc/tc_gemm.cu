@@ -30,7 +30,7 @@ namespace hvae {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 64;   // BK * sizeof(bf16) = 128 B = one swizzle atom
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int UMMA_K = 16;
 constexpr int CG = 4;                        // epilogue column groups: 4*CG epilogue warps, each BN/CG columns
@@ -39,19 +39,15 @@ constexpr int THREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue 
 constexpr uint32_t TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
 constexpr uint32_t COLC_BYTES = ACC_STAGES * BN * 16 + ACC_STAGES * BN * 4;  // per-column float4 constants + bias
-// per-warp 32x32 fp32 staging tile (row stride 36 floats): the accumulator arrives one ROW per lane, but a store
-// instruction should cover whole 128-byte lines (ncu on the direct per-lane stores: 16 of 32 bytes per sector used,
-// lg_throttle the top stall) -> transpose through smem so 8 lanes write one contiguous 128 B row segment.
-constexpr int STG_LD = 36;
-constexpr uint32_t STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES + STG_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES;
 // A-resident schedule (K <= 512): the CTA keeps its 128 x K panel of A in smem for all n-tiles of the m-block and
 // streams only B tiles.  L2->SM traffic per flop halves (the 128x128 streaming schedule is L2-bound: ncu shows
 // lts throughput ~70 % at 26 % tensor-pipe activity).
 constexpr int ARES_KB = 8;                                  // up to 8 k-blocks of 64 -> K <= 512
-constexpr int ARES_STAGES = 4;                              // B ring
+constexpr int ARES_STAGES = 5;                              // B ring
 constexpr uint32_t ARES_RING_BYTES = ARES_KB * TILE_A_BYTES + ARES_STAGES * TILE_B_BYTES;
-constexpr uint32_t SMEM_BYTES_ARES = ARES_RING_BYTES + 1024 + 256 + COLC_BYTES;  // (no room for the store staging)
+constexpr uint32_t SMEM_BYTES_ARES = ARES_RING_BYTES + 1024 + 256 + COLC_BYTES;
+static_assert(SMEM_BYTES <= 232448 && SMEM_BYTES_ARES <= 232448, "exceeds the 227 KB per-CTA shared memory");
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
 
 enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3 };
@@ -59,7 +55,8 @@ enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3 };
 struct Params {
     float* D;              // (M, N) row-major output
     int64_t M, N, K;
-    const float* rowscale; // PLAIN: optional (M,)
+    int dbg;               // experiments only (HVAE_TC_DBG): 1 = skip the global stores, 2 = skip the whole drain
+    const float* rowscale; // PLAIN: optional (M,); MOBIUS: required (M,)
     const float* axpy_x;   // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
     const float* axpy_coef;//        (M,)
     float* rowsq;          // PLAIN: optional [n_tiles][M] partial sums of acc^2
@@ -69,10 +66,6 @@ struct Params {
     GyroParams gp;
     const float* xrow;     // ROWDOT: (M, N) fp32 rows dotted with the accumulator rows
     float* rowdot;         // ROWDOT: [n_tiles][M] partial sums of acc * xrow
-    const float* mxsq;     // MOBIUS: [q_tiles][M] partials of |mx_b|^2 (from the Gram row-dot pass)
-    int q_tiles;
-    float* mxsq_out;       // MOBIUS: optional (M,) |mx_b|^2 as used by the epilogue (saved for the backward)
-    Ball ball;             // MOBIUS
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,6 +138,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16 lanes x (4 repeats of 256 bits): 16 registers; issue both halves, then wait once
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the asm takes the loaded registers as in/out operands so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(float (&a)[16], float (&b)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]),
+                   "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]), "+f"(b[0]),
+                   "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]), "+f"(b[8]), "+f"(b[9]),
+                   "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15])
+                 :
+                 : "memory");
 }
 
 template <int EPI, bool ARES>
@@ -257,159 +273,168 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
     } else {
         // ===== epilogue: warp w owns TMEM lane quarter (w % 4) and column group (w - 2) / 4 =====
+        // The accumulator is read with the 16x256b shape: for each 8-column repeat i, lane t holds columns
+        // 8i + 2(t%4) + {0,1} of rows t/4 and t/4 + 8 of a 16-row half.  Four neighbouring lanes own one contiguous
+        // 32-byte sector of an output row, so the global stores leave sector-complete straight from registers, with
+        // no shared-memory transpose: smem bandwidth is what bounds this kernel (UMMA operand reads + TMA writes
+        // already take the SM's 128 B/clk; measured, the staged version's store phase added to the mainloop
+        // time instead of hiding under it).
         const int q = warp & 3;
         const int cg = (warp - 2) >> 2;
         const int et = threadIdx.x - 64;  // 0 .. 32*EPI_WARPS-1
         float4* colc = reinterpret_cast<float4*>(smem_raw + (bars + 256u - raw));            // [ACC_STAGES][BN]
         float* colb = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw) + ACC_STAGES * BN * 16);
-        float* stg = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw) + COLC_BYTES) + (warp - 2) * 32 * STG_LD;
+        const int lr = lane >> 2, lc = (lane & 3) * 2;  // row inside an 8-row group, first column inside a repeat
+        const bool n_even = (prm.N & 1) == 0;
         int as = 0;
         uint32_t aphase = 0;
         constexpr int COLS = BN / CG;
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
           const int64_t mt = ARES ? u : u / n_tiles;
           const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+          // this thread's 4 rows: k = 2h + g -> row 16h + 8g + lr of the warp's 32-row quarter
+          int64_t mr[4];
+          bool ok[4];
+          float rs[4], x2r[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+              mr[k] = mt * BM + q * 32 + 16 * (k >> 1) + 8 * (k & 1) + lr;
+              ok[k] = mr[k] < prm.M;
+              rs[k] = 1.0f;
+              x2r[k] = 0.0f;
+              if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && ok[k]) rs[k] = __ldg(prm.rowscale + mr[k]);
+              if (EPI == EPI_GYRO && ok[k]) x2r[k] = __ldg(prm.x2 + mr[k]);
+          }
           for (int64_t nt = nt0; nt < nt1; ++nt) {
-            const int64_t m = mt * BM + q * 32 + lane;
-            const bool row_ok = m < prm.M;
+            float accr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (EPI == EPI_GYRO) {
-                // per-column constants of this tile: {|p|^2, 1 - c|p|^2, c^2 |p|^2, |p|} (+ bias), once per tile
+                // per-column constants of this tile: {|p|^2, u, v, |p|} (+ bias), once per tile.  u, v: see the lean path
                 if (et < BN) {
                     const int64_t n = nt * BN + et;
                     const float p2 = (n < prm.N) ? __ldg(prm.p2 + n) : 0.0f;
-                    const float c = prm.gp.c;
-                    colc[as * BN + et] = make_float4(p2, 1.0f - c * p2, c * c * p2, sqrt_fast(p2));
+                    const float c = prm.gp.c, pn = sqrtf(p2);
+                    const float rcol = 2.0f * prm.gp.sc / ((1.0f - c * p2) * pn + kMinNorm);
+                    colc[as * BN + et] = make_float4(p2, rcol * (1.0f + c * p2), rcol * p2, pn);
                     colb[as * BN + et] = (prm.bias && n < prm.N) ? __ldg(prm.bias + n) : 0.0f;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-            }
-            float rs = 1.0f, x2 = 0.0f, acc_row = 0.0f;
-            if (EPI == EPI_PLAIN && prm.rowscale && row_ok) rs = __ldg(prm.rowscale + m);
-            if (EPI == EPI_GYRO && row_ok) x2 = __ldg(prm.x2 + m);
-            if (EPI == EPI_MOBIUS) {
-                // y = psi(|x|, |mx|) mx with |mx|^2 from the Gram pass; projection folded into the scale
-                float mx2 = 0.0f;
-                if (row_ok) {
-                    x2 = __ldg(prm.x2 + m);
-                    for (int qt = 0; qt < prm.q_tiles; ++qt) mx2 += __ldg(prm.mxsq + (int64_t)qt * prm.M + m);
-                }
-                mx2 = fmaxf(mx2, 0.0f);
-                if (prm.mxsq_out && row_ok && nt == 0 && cg == 0) prm.mxsq_out[m] = mx2;
-                const Ball& bl = prm.ball;
-                const float xn = fmaxf(sqrt_fast(x2), kMinNorm);
-                const float mxn_raw = sqrt_fast(mx2), mxn = fmaxf(mxn_raw, kMinNorm);
-                const float th = mxn * rcpf(xn) * artanh_c(bl.sc * xn);
-                const float tt = tanh_c(th);
-                rs = bl.rsc * tt * rcpf(mxn);
-                const float yn = fmaxf(bl.rsc * tt * (mxn_raw * rcpf(mxn)), kMinNorm);
-                if (yn > bl.maxnorm) rs = rs * rcpf(yn) * bl.maxnorm;
-                if (mx2 == 0.0f) rs = 0.0f;
             }
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
 #pragma unroll 1
             for (int cb = cg * COLS; cb < (cg + 1) * COLS; cb += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb), v);
+                if (prm.dbg & 2) break;
+                float v[2][16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb), v[0]);
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(as * BN + cb), v[1]);
+                tmem_ld_wait(v[0], v[1]);
                 const int64_t n0 = nt * BN + cb;
-                if (EPI == EPI_PLAIN) {
+                // element (k = 2h + g, i, e): v[h][4i + 2g + e]  <->  row mr[k], column n0 + 8i + lc + e
+                if (EPI == EPI_PLAIN || EPI == EPI_MOBIUS) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        acc_row = fmaf(v[i], v[i], acc_row);  // out-of-range columns are TMA zero-filled -> contribute 0
-                        v[i] *= rs;
-                    }
-                } else if (EPI == EPI_MOBIUS) {
+                    for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= rs;
-                } else if (EPI == EPI_ROWDOT) {
-                    if (row_ok) {
-                        const float* xr = prm.xrow + m * prm.N + n0;
-                        if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + i));
-                                acc_row = fmaf(v[i], xv.x, fmaf(v[i + 1], xv.y, fmaf(v[i + 2], xv.z, fmaf(v[i + 3], xv.w, acc_row))));
+                            for (int e = 0; e < 2; ++e) {
+                                float& t = v[k >> 1][4 * i + 2 * (k & 1) + e];
+                                if (EPI == EPI_PLAIN) accr[k] = fmaf(t, t, accr[k]);  // out-of-range columns are zero-filled
+                                t *= rs[k];
                             }
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (n0 + i < prm.N) acc_row = fmaf(v[i], __ldg(xr + i), acc_row);
+                } else if (EPI == EPI_ROWDOT) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!ok[k]) continue;
+                        const float* xr = prm.xrow + mr[k] * prm.N + n0 + lc;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int64_t col = n0 + 8 * i + lc;
+                            const float t0 = v[k >> 1][4 * i + 2 * (k & 1)], t1 = v[k >> 1][4 * i + 2 * (k & 1) + 1];
+                            if (n_even && col + 2 <= prm.N) {
+                                const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + 8 * i));
+                                accr[k] = fmaf(t0, xv.x, fmaf(t1, xv.y, accr[k]));
+                            } else {
+                                if (col < prm.N) accr[k] = fmaf(t0, __ldg(xr + 8 * i), accr[k]);
+                                if (col + 1 < prm.N) accr[k] = fmaf(t1, __ldg(xr + 8 * i + 1), accr[k]);
+                            }
                         }
                     }
                 } else {
+                    // geoopt signed distance with a == p (the decoder's configuration).  With z = (-p) (+) x,
+                    //   <z, p> = (Bc <x,p> - A |p|^2) / den   and   1 - c|z|^2 = Bc (1 - c|x|^2) / den     (Bc = 1 - c|p|^2)
+                    // so den cancels and asinh's argument separates into row and column factors around <x,p>:
+                    //   y = 2 sqrt(c) [<x,p>(1 + c|p|^2) - |p|^2 (1 + c|x|^2)] / (Bc |p| (1 - c|x|^2)) = px a_b u_j - w_b v_j
+                    // (3 FMA-pipe ops + asinh per output; the clamps of the reference only bind for |p| ~ 1e-15, kept via
+                    // the + MIN_NORM in u, v).  Other flag combinations take the general pair function.
                     const bool lean = (prm.gp.flags & ~(uint32_t)HVAE_GYRO_SIGNED) == 0u && (prm.gp.flags & HVAE_GYRO_SIGNED);
-                    const float c = prm.gp.c, two_c = 2.0f * c, sc2 = 2.0f * prm.gp.sc, rsc = prm.gp.rsc;
-                    const float rowA0 = fmaf(c, x2, 1.0f);
-                    if (lean) {
-                        // geoopt signed distance, a == p (the decoder's configuration): ~25 FMA + 4 MUFU per output
+                    const float rsc = prm.gp.rsc;
+                    float ar[4], wr[4];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float4 cc = colc[as * BN + cb + i];  // {p2, Bc, c^2 p2, |p|}  (smem broadcast)
-                            const float px = v[i];
-                            const float A = fmaf(-two_c, px, rowA0);
-                            const float den = fmaxf(fmaf(cc.z, x2, fmaf(-two_c, px, 1.0f)), kMinNorm);
-                            const float rden = rcpf(den);
-                            const float N1 = fmaf(cc.y, px, -A * cc.x);
-                            const float N2 = fmaxf(fmaf(A, fmaf(A, cc.x, -2.0f * cc.y * px), cc.y * cc.y * x2), 0.0f);
-                            const float da = N1 * rden;
-                            const float dn2 = fmaxf(N2 * rden * rden, kMinNorm);
-                            const float w = (1.0f - c * dn2) * cc.w;
-                            const float denom = copysignf(fabsf(w) + kMinNorm, w);
-                            const float y = sc2 * da * rcpf(denom);
-                            v[i] = fmaf(asinh_fast(y), rsc, colb[as * BN + cb + i]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float4 cc = colc[as * BN + cb + i];
-                            GyroPairCtx k;
-                            v[i] = gyro_pair_fwd(v[i], v[i], x2, cc.x, cc.x, cc.w, prm.gp, k) + colb[as * BN + cb + i];
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        ar[k] = 1.0f / fmaxf(1.0f - prm.gp.c * x2r[k], 1e-30f);
+                        wr[k] = ar[k] * (1.0f + prm.gp.c * x2r[k]);
                     }
-                }
-                if (EPI != EPI_ROWDOT) {
-                    if (!ARES && n0 + 32 <= prm.N && (prm.N & 3) == 0) {
-                        // stage: lane = row writes its 32 values; then 8 lanes cooperate on one 128-byte row segment
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(stg + lane * STG_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        __syncwarp();
-                        const int64_t mrow0 = mt * BM + q * 32;
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = 4 * j + (lane >> 3), c4 = (lane & 7) * 4;
-                            float4 t4 = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
-                            if (mrow0 + r < prm.M) {
-                                if (EPI == EPI_PLAIN && prm.axpy_x) {
-                                    const float cf = __ldg(prm.axpy_coef + mrow0 + r);
-                                    const float4 xv = __ldg(reinterpret_cast<const float4*>(prm.axpy_x + (mrow0 + r) * prm.N + n0 + c4));
-                                    t4.x = fmaf(cf, xv.x, t4.x); t4.y = fmaf(cf, xv.y, t4.y);
-                                    t4.z = fmaf(cf, xv.z, t4.z); t4.w = fmaf(cf, xv.w, t4.w);
+                        for (int e = 0; e < 2; ++e) {
+                            const float4 cc = colc[as * BN + cb + 8 * i + lc + e];  // {p2, u, v, |p|}
+                            const float bb = colb[as * BN + cb + 8 * i + lc + e];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float& t = v[k >> 1][4 * i + 2 * (k & 1) + e];
+                                if (lean) {
+                                    const float y = fmaf(t * ar[k], cc.y, -cc.z * wr[k]);
+                                    t = fmaf(asinh_fast(y), rsc, bb);
+                                } else {
+                                    GyroPairCtx kk;
+                                    t = gyro_pair_fwd(t, t, x2r[k], cc.x, cc.x, cc.w, prm.gp, kk) + bb;
                                 }
-                                *reinterpret_cast<float4*>(prm.D + (mrow0 + r) * prm.N + n0 + c4) = t4;
                             }
                         }
-                        __syncwarp();
-                    } else if (row_ok) {
-                        float* dst = prm.D + m * prm.N + n0;
-                        if (EPI == EPI_PLAIN && prm.axpy_x) {
-                            const float cf = __ldg(prm.axpy_coef + m);
-                            const float* xr = prm.axpy_x + m * prm.N + n0;
-                            for (int i = 0; i < 32; ++i)
-                                if (n0 + i < prm.N) v[i] = fmaf(cf, __ldg(xr + i), v[i]);
-                        }
-                        if (n0 + 32 <= prm.N && (prm.N & 3) == 0) {
+                }
+                if (EPI != EPI_ROWDOT && (prm.dbg & 1)) {
+                    float t = 0.0f;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        } else {
-                            for (int i = 0; i < 32; ++i)
-                                if (n0 + i < prm.N) dst[i] = v[i];
+                    for (int i = 0; i < 16; ++i) t += v[0][i] + v[1][i];
+                    if (t == 123.456f) prm.D[0] = t;
+                } else if (EPI != EPI_ROWDOT) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!ok[k]) continue;
+                        const float cf = (EPI == EPI_PLAIN && prm.axpy_x) ? __ldg(prm.axpy_coef + mr[k]) : 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int64_t col = n0 + 8 * i + lc;
+                            const int64_t off = mr[k] * prm.N + col;
+                            float2 t2 = make_float2(v[k >> 1][4 * i + 2 * (k & 1)], v[k >> 1][4 * i + 2 * (k & 1) + 1]);
+                            if (n_even && col + 2 <= prm.N) {
+                                if (EPI == EPI_PLAIN && prm.axpy_x) {
+                                    const float2 xv = __ldg(reinterpret_cast<const float2*>(prm.axpy_x + off));
+                                    t2.x = fmaf(cf, xv.x, t2.x);
+                                    t2.y = fmaf(cf, xv.y, t2.y);
+                                }
+                                *reinterpret_cast<float2*>(prm.D + off) = t2;
+                            } else {
+                                if (col < prm.N) prm.D[off] = (EPI == EPI_PLAIN && prm.axpy_x) ? fmaf(cf, __ldg(prm.axpy_x + off), t2.x) : t2.x;
+                                if (col + 1 < prm.N)
+                                    prm.D[off + 1] = (EPI == EPI_PLAIN && prm.axpy_x) ? fmaf(cf, __ldg(prm.axpy_x + off + 1), t2.y) : t2.y;
+                            }
                         }
                     }
                 }
             }
-            // per-(row, n-tile, column-group) partials: [ (nt*CG + cg) ][M]
-            if (EPI == EPI_PLAIN && prm.rowsq && row_ok) prm.rowsq[(nt * CG + cg) * prm.M + m] = acc_row;
-            if (EPI == EPI_ROWDOT && row_ok) prm.rowdot[(nt * CG + cg) * prm.M + m] = acc_row;
+            // per-(row, n-tile, column-group) partials: [ (nt*CG + cg) ][M]; the 4 lanes of a row combine first
+            if ((EPI == EPI_PLAIN && prm.rowsq) || EPI == EPI_ROWDOT) {
+                float* dstp = (EPI == EPI_PLAIN) ? prm.rowsq : prm.rowdot;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a = accr[k];
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    if ((lane & 3) == 0 && ok[k]) dstp[(nt * CG + cg) * prm.M + mr[k]] = a;
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -469,6 +494,28 @@ __global__ void k_transpose_to_bf16(const float* __restrict__ in, __nv_bfloat16*
         const int c = c0 + i, r = r0 + threadIdx.x;
         if (c < C && r < R) out[(int64_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
     }
+}
+
+// Single-pass Mobius: per-row scale of y = rs * mx (psi, times maxnorm/|y_pre| when the projection clips) from the
+// Gram-pass partials of |mx_b|^2; a thread per row.  Kept out of the GEMM epilogue: there it sat on every tile's
+// critical path (q_tiles dependent loads + artanh/tanh before the accumulator could be drained).
+__global__ void k_mobius_rowscale(const float* __restrict__ x2, const float* __restrict__ mxsq_part, int q_tiles,
+                                  float* __restrict__ rs_out, float* __restrict__ mxsq_out, int64_t B, Ball bl) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float mx2 = 0.0f;
+    for (int qt = 0; qt < q_tiles; ++qt) mx2 += __ldg(mxsq_part + (int64_t)qt * B + b);
+    mx2 = fmaxf(mx2, 0.0f);
+    if (mxsq_out) mxsq_out[b] = mx2;
+    const float xn = fmaxf(sqrtf(x2[b]), kMinNorm);
+    const float mxn_raw = sqrtf(mx2), mxn = fmaxf(mxn_raw, kMinNorm);
+    const float th = mxn / xn * artanh_c(bl.sc * xn);
+    const float tt = tanh_c(th);
+    float rs = bl.rsc * tt / mxn;
+    const float yn = fmaxf(bl.rsc * tt * (mxn_raw / mxn), kMinNorm);
+    if (yn > bl.maxnorm) rs = rs / yn * bl.maxnorm;
+    if (mx2 == 0.0f) rs = 0.0f;
+    rs_out[b] = rs;
 }
 
 // Mobius pass 2: y_b = psi(|x_b|, |mx_b|) mx_b, projected.  one warp per row.
@@ -617,7 +664,10 @@ static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, i
 }
 
 template <int EPI>
-static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm, cudaStream_t s) {
+static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm_in, cudaStream_t s) {
+    Params prm = prm_in;
+    static const int dbg = getenv("HVAE_TC_DBG") ? atoi(getenv("HVAE_TC_DBG")) : 0;
+    prm.dbg = dbg;
     CUtensorMap ma, mb;
     if (!make_map(&ma, A, prm.M, prm.K, BM) || !make_map(&mb, Bm, prm.N, prm.K, BN)) return HVAE_ELAUNCH;
     static bool attr_set = false;
@@ -628,10 +678,9 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     }
     const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
     // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over, and enough m-blocks
-    // measured: not faster than streaming (the kernel is bound by the epilogue's stores, not by operand traffic), and it
-    // leaves no smem for the store staging -> opt-in only
-    static const bool want_ares = getenv("HVAE_TC_ARES") != nullptr;
-    const bool ares = want_ares && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
+    // (not for the gyroplane epilogue: measured slower there, its per-tile column-constant exchange serialises the n-tiles)
+    static const bool want_ares = getenv("HVAE_TC_NO_ARES") == nullptr;
+    const bool ares = want_ares && EPI != EPI_GYRO && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
     if (ares) {
         const int grid = (int)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
         k_tc_gemm<EPI, true><<<grid, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, prm);
@@ -749,11 +798,11 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
         int rc = tc::launch_gemm<tc::EPI_ROWDOT>(a16, g16, prm, s);
         if (rc != HVAE_OK) return rc;
     }
+    float* rs = (float*)(ws + L.rowsq);  // (B,) row scale; the rowsq slot is unused on this path
+    tc::k_mobius_rowscale<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(x2, rowdot, (int)((F + tc::BN - 1) / tc::BN) * tc::CG, rs,
+                                                                      mxsq_out, B, make_ball(c));
     tc::Params prm{};
-    prm.D = y; prm.M = B; prm.N = P; prm.K = F; prm.x2 = x2; prm.mxsq = rowdot;
-    prm.q_tiles = (int)((F + tc::BN - 1) / tc::BN) * tc::CG;
-    prm.mxsq_out = mxsq_out;
-    prm.ball = make_ball(c);
+    prm.D = y; prm.M = B; prm.N = P; prm.K = F; prm.rowscale = rs;
     return tc::launch_gemm<tc::EPI_MOBIUS>(a16, b16, prm, s);
 }
 
