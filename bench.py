@@ -361,7 +361,7 @@ def run_ours(args, wl):
             "config": {"workload": "cfg2: " + wl["desc"], "batch_per_gpu": B, "latent_dim": wl["latent"], "hidden": wl["hidden"],
                        "curvature": wl["c"], "parallelism": "dp%d" % world, "cuda_graph": graph_on,
                        "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                       "trunk": "torch fp32 Linear (cuBLAS, TF32 off) — library code, not this repo's kernels"},
+                       "trunk": "hvae.layers.Linear -> tcgen05 split-bf16 GEMM (3 pieces, 6 products, chunked fp32 accumulation): fp32-accurate, own kernel"},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "samples/s",
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "mode": "hvae.train.TrainStep prefetch()/run_prefetched(): H2D of step i+1 overlaps step i"},
             "gpu_launches": launches_per_step * (args.steps + e2e_steps),

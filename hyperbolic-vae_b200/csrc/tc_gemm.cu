@@ -47,14 +47,26 @@ constexpr int ARES_KB = 8;                                  // up to 8 k-blocks 
 constexpr int ARES_STAGES = 5;                              // B ring
 constexpr uint32_t ARES_RING_BYTES = ARES_KB * TILE_A_BYTES + ARES_STAGES * TILE_B_BYTES;
 constexpr uint32_t SMEM_BYTES_ARES = ARES_RING_BYTES + 1024 + 256 + COLC_BYTES;
+static_assert(BN / CG == 32, "EPI_X3 assumes one 32-column chunk per epilogue warp");
 static_assert(SMEM_BYTES <= 232448 && SMEM_BYTES_ARES <= 232448, "exceeds the 227 KB per-CTA shared memory");
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
 
-enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3 };
+enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_X3 = 4 };
+// EPI_X3 (fp32 emulation): the tensor core adds into its fp32 accumulator with truncation, a bias that grows with the
+// length of the accumulation chain (measured 6e-6 relative at K = 4096).  So the MMA warp hands the accumulator over
+// every X3_CHUNK k-blocks (512 contraction elements) and the epilogue warps sum the chunks in registers with
+// round-to-nearest fp32 adds; the two TMEM stages pipeline chunk i+1 under the drain of chunk i.
+constexpr int X3_CHUNK = 8;
 
 struct Params {
     float* D;              // (M, N) row-major output
     int64_t M, N, K;
+    // multi-piece contraction (fp32 emulation): the K loop runs over npairs (A piece, B piece) column offsets of kbp
+    // k-blocks each; npairs == 0 -> one piece of ceil(K / BK) k-blocks.  splits > 1: split-K, unit (tile, s) writes
+    // its partial tile to D + s * M * N.
+    int npairs, kbp, splits;
+    int a_off[6], b_off[6];
+    int relu;              // PLAIN: bias (per column, via `bias`) then optional ReLU
     int dbg;               // experiments only (HVAE_TC_DBG): 1 = skip the global stores, 2 = skip the whole drain
     const float* rowscale; // PLAIN: optional (M,); MOBIUS: required (M,)
     const float* axpy_x;   // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
@@ -188,9 +200,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
     const int64_t tiles = m_tiles * n_tiles;
-    const int k_blocks = (int)((prm.K + BK - 1) / BK);
+    const int kbp = prm.npairs ? prm.kbp : (int)((prm.K + BK - 1) / BK);      // k-blocks per piece pair
+    const int k_blocks = prm.npairs ? prm.npairs * kbp : kbp;                // whole contraction
+    const int S = (!ARES && prm.splits > 1) ? prm.splits : 1;
     // work unit: one output tile (streaming) or one m-block with all its n-tiles (A-resident)
-    const int64_t units = ARES ? m_tiles : tiles;
+    const int64_t units = ARES ? m_tiles : tiles * S;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -216,8 +230,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             int stage = 0;
             uint32_t phase = 0, pphase = 0;
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-                const int64_t mt = ARES ? u : u / n_tiles;
-                const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+                const int64_t tile = ARES ? u : u / S;
+                const int sp = ARES ? 0 : (int)(u % S);
+                const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
+                const int64_t mt = ARES ? u : tile / n_tiles;
+                const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
                 const int m0 = (int)mt * BM;
                 if (ARES) {
                     mbar_wait(aempty_bar, pphase ^ 1u);      // all MMAs of the previous m-block have retired
@@ -227,11 +244,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 }
                 for (int64_t nt = nt0; nt < nt1; ++nt) {
                     const int n0 = (int)nt * BN;
-                    for (int kb = 0; kb < k_blocks; ++kb) {
+                    for (int f = kb0; f < kb1; ++f) {
+                        int ka = f * BK, kbo = f * BK;
+                        if (prm.npairs) {
+                            const int pr = f / kbp, kk = f - pr * kbp;
+                            ka = prm.a_off[pr] + kk * BK;
+                            kbo = prm.b_off[pr] + kk * BK;
+                        }
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         mbar_expect_tx(full_bar(stage), ARES ? TILE_B_BYTES : STAGE_BYTES);
-                        if (!ARES) tma_load_2d(a_tile(stage), &map_a, full_bar(stage), kb * BK, m0);
-                        tma_load_2d(b_tile(stage), &map_b, full_bar(stage), kb * BK, n0);
+                        if (!ARES) tma_load_2d(a_tile(stage), &map_a, full_bar(stage), ka, m0);
+                        tma_load_2d(b_tile(stage), &map_b, full_bar(stage), kbo, n0);
                         if (++stage == NST) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -243,24 +266,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0, pphase = 0;
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-                const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+                const int64_t tile = ARES ? u : u / S;
+                const int sp = ARES ? 0 : (int)(u % S);
+                const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
+                const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
                 if (ARES) {
                     mbar_wait(afull_bar, pphase);
                     tc_fence_after();
                     pphase ^= 1u;
                 }
-                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                const int chk = (EPI == EPI_X3) ? X3_CHUNK : (kb1 - kb0);
+                for (int64_t nt = nt0; nt < nt1; ++nt)
+                  for (int c0 = kb0; c0 < kb1; c0 += chk) {
+                    const int c1 = (c0 + chk < kb1) ? c0 + chk : kb1;
                     mbar_wait(tempty_bar(as), aphase ^ 1u);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                    for (int kb = 0; kb < k_blocks; ++kb) {
+                    for (int kb = c0; kb < c1; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint64_t da = make_desc(a_tile(ARES ? kb : stage)), db = make_desc(b_tile(stage));
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-                            umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
+                            umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)(((kb - c0) | k) != 0));
                         }
                         umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
                         if (++stage == NST) { stage = 0; phase ^= 1u; }
@@ -290,8 +319,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint32_t aphase = 0;
         constexpr int COLS = BN / CG;
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-          const int64_t mt = ARES ? u : u / n_tiles;
-          const int64_t nt0 = ARES ? 0 : u % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+          const int64_t tile = ARES ? u : u / S;
+          const int sp = ARES ? 0 : (int)(u % S);
+          const int64_t mt = ARES ? u : tile / n_tiles;
+          const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+          float* __restrict__ Dout = prm.D + (int64_t)sp * prm.M * prm.N;   // split-K: partial tile of slice sp
+          const bool fin = (EPI == EPI_PLAIN) && S == 1 && (prm.bias != nullptr || prm.relu);
           // this thread's 4 rows: k = 2h + g -> row 16h + 8g + lr of the warp's 32-row quarter
           int64_t mr[4];
           bool ok[4];
@@ -305,6 +338,59 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && ok[k]) rs[k] = __ldg(prm.rowscale + mr[k]);
               if (EPI == EPI_GYRO && ok[k]) x2r[k] = __ldg(prm.x2 + mr[k]);
           }
+          if (EPI == EPI_X3) {
+              // chunked accumulation: sum the accumulator hand-overs of this unit in registers, then finish + store
+              const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
+              float acc[2][16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[0][i] = acc[1][i] = 0.0f;
+              const int cb = cg * COLS;  // COLS == 32: one column chunk per warp
+              for (int c0 = kb0; c0 < kb1; c0 += X3_CHUNK) {
+                  mbar_wait(tfull_bar(as), aphase);
+                  tc_fence_after();
+                  float v[2][16];
+                  tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb), v[0]);
+                  tmem_ld16(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(as * BN + cb), v[1]);
+                  tmem_ld_wait(v[0], v[1]);
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(tempty_bar(as));
+                  if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { acc[0][i] += v[0][i]; acc[1][i] += v[1][i]; }
+              }
+              const int64_t n0 = nt0 * BN + cb;
+              const bool fin3 = S == 1;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                      const int64_t col = n0 + 8 * i + lc + e;
+                      const float bb = (fin3 && prm.bias && col < prm.N) ? __ldg(prm.bias + col) : 0.0f;
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                          float& t = acc[k >> 1][4 * i + 2 * (k & 1) + e];
+                          t += bb;
+                          if (fin3 && prm.relu) t = fmaxf(t, 0.0f);
+                      }
+                  }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                  if (!ok[k]) continue;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                      const int64_t col = n0 + 8 * i + lc;
+                      const int64_t off = mr[k] * prm.N + col;
+                      const float2 t2 = make_float2(acc[k >> 1][4 * i + 2 * (k & 1)], acc[k >> 1][4 * i + 2 * (k & 1) + 1]);
+                      if (n_even && col + 2 <= prm.N) {
+                          *reinterpret_cast<float2*>(Dout + off) = t2;
+                      } else {
+                          if (col < prm.N) Dout[off] = t2.x;
+                          if (col + 1 < prm.N) Dout[off + 1] = t2.y;
+                      }
+                  }
+              }
+          } else
           for (int64_t nt = nt0; nt < nt1; ++nt) {
             float accr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (EPI == EPI_GYRO) {
@@ -399,26 +485,42 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int i = 0; i < 16; ++i) t += v[0][i] + v[1][i];
                     if (t == 123.456f) prm.D[0] = t;
                 } else if (EPI != EPI_ROWDOT) {
+                    if (fin) {
+                        // dense-layer epilogue: per-column bias, optional ReLU
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int64_t col = n0 + 8 * i + lc + e;
+                                const float bb = (prm.bias && col < prm.N) ? __ldg(prm.bias + col) : 0.0f;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float& t = v[k >> 1][4 * i + 2 * (k & 1) + e];
+                                    t += bb;
+                                    if (prm.relu) t = fmaxf(t, 0.0f);
+                                }
+                            }
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (!ok[k]) continue;
-                        const float cf = (EPI == EPI_PLAIN && prm.axpy_x) ? __ldg(prm.axpy_coef + mr[k]) : 0.0f;
+                        const bool axpy = (EPI == EPI_PLAIN) && prm.axpy_x != nullptr;
+                        const float cf = axpy ? __ldg(prm.axpy_coef + mr[k]) : 0.0f;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int64_t col = n0 + 8 * i + lc;
                             const int64_t off = mr[k] * prm.N + col;
                             float2 t2 = make_float2(v[k >> 1][4 * i + 2 * (k & 1)], v[k >> 1][4 * i + 2 * (k & 1) + 1]);
                             if (n_even && col + 2 <= prm.N) {
-                                if (EPI == EPI_PLAIN && prm.axpy_x) {
+                                if (axpy) {
                                     const float2 xv = __ldg(reinterpret_cast<const float2*>(prm.axpy_x + off));
                                     t2.x = fmaf(cf, xv.x, t2.x);
                                     t2.y = fmaf(cf, xv.y, t2.y);
                                 }
-                                *reinterpret_cast<float2*>(prm.D + off) = t2;
+                                *reinterpret_cast<float2*>(Dout + off) = t2;
                             } else {
-                                if (col < prm.N) prm.D[off] = (EPI == EPI_PLAIN && prm.axpy_x) ? fmaf(cf, __ldg(prm.axpy_x + off), t2.x) : t2.x;
-                                if (col + 1 < prm.N)
-                                    prm.D[off + 1] = (EPI == EPI_PLAIN && prm.axpy_x) ? fmaf(cf, __ldg(prm.axpy_x + off + 1), t2.y) : t2.y;
+                                if (col < prm.N) Dout[off] = axpy ? fmaf(cf, __ldg(prm.axpy_x + off), t2.x) : t2.x;
+                                if (col + 1 < prm.N) Dout[off + 1] = axpy ? fmaf(cf, __ldg(prm.axpy_x + off + 1), t2.y) : t2.y;
                             }
                         }
                     }
@@ -634,6 +736,72 @@ k_mobius_tc_bwd_rows(const float* __restrict__ x, const float* __restrict__ y, c
     }
 }
 
+// ---- fp32 emulation ("x3"): v = hi + mid + lo with three bf16 pieces (24 mantissa bits) -----------------------------
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);   // exact
+    m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);  // exact
+    l = __float2bfloat16_rn(r2);
+}
+
+// (R, K) fp32 -> (R, 3*Kp) bf16, piece t in columns [t*Kp, t*Kp + K), zero padding up to Kp (Kp % 64 == 0)
+__global__ void __launch_bounds__(256) k_split3_rows(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t R,
+                                                     int64_t K, int64_t Kp) {
+    const int64_t half = Kp >> 1;  // pairs of columns per row
+    const int64_t n = R * half;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / half, c = (i - r * half) * 2;
+        float a = 0.0f, b = 0.0f;
+        if (c < K) a = __ldg(in + r * K + c);
+        if (c + 1 < K) b = __ldg(in + r * K + c + 1);
+        __nv_bfloat162 h, m, l;
+        split3(a, h.x, m.x, l.x);
+        split3(b, h.y, m.y, l.y);
+        __nv_bfloat16* o = out + r * 3 * Kp + c;
+        *reinterpret_cast<__nv_bfloat162*>(o) = h;
+        *reinterpret_cast<__nv_bfloat162*>(o + Kp) = m;
+        *reinterpret_cast<__nv_bfloat162*>(o + 2 * Kp) = l;
+    }
+}
+
+// (R, C) fp32 -> (C, 3*Rp) bf16: transposed, the contraction runs over the rows of the input.  32x32 smem tiles.
+__global__ void __launch_bounds__(256) k_split3_transposed(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                           int64_t R, int64_t C, int64_t Rp) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;  // r0 covers [0, Rp)
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < R && c < C) ? __ldg(in + r * C + c) : 0.0f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t c = c0 + i, r = r0 + tx;
+        if (c < C && r < Rp) {
+            __nv_bfloat16 h, m, l;
+            split3(tile[tx][i], h, m, l);
+            __nv_bfloat16* o = out + c * 3 * Rp + r;
+            o[0] = h;
+            o[Rp] = m;
+            o[2 * Rp] = l;
+        }
+    }
+}
+
+// split-K fix-up: C = sum_s part[s] (+ bias per column) (ReLU)
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, const float* __restrict__ bias,
+                                                       float* __restrict__ C, int64_t M, int64_t N, int S, int relu) {
+    const int64_t n = M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float a = 0.0f;
+        for (int s = 0; s < S; ++s) a += part[(int64_t)s * n + i];
+        if (bias) a += __ldg(bias + i % N);
+        if (relu) a = fmaxf(a, 0.0f);
+        C[i] = a;
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -680,12 +848,12 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over, and enough m-blocks
     // (not for the gyroplane epilogue: measured slower there, its per-tile column-constant exchange serialises the n-tiles)
     static const bool want_ares = getenv("HVAE_TC_NO_ARES") == nullptr;
-    const bool ares = want_ares && EPI != EPI_GYRO && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
+    const bool ares = want_ares && EPI != EPI_GYRO && prm.npairs == 0 && prm.splits <= 1 && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
     if (ares) {
         const int grid = (int)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
         k_tc_gemm<EPI, true><<<grid, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, prm);
     } else {
-        const int64_t tiles = m_tiles * n_tiles;
+        const int64_t tiles = m_tiles * n_tiles * (prm.splits > 1 ? prm.splits : 1);
         const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
         k_tc_gemm<EPI, false><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, prm);
     }
@@ -872,4 +1040,99 @@ extern "C" int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const f
     const Ball b = make_ball(c);
     prm.gp.c = b.c; prm.gp.sc = b.sc; prm.gp.rsc = b.rsc; prm.gp.maxnorm = b.maxnorm; prm.gp.flags = flags;
     return tc::launch_gemm<tc::EPI_GYRO>(a16, b16, prm, s);
+}
+
+// ---- fp32-accurate GEMM on the tensor cores (trunk dense layers; SURVEY 8f "next") ----------------------------------
+namespace hvae { namespace tc {
+constexpr int X3_MAX_SPLITS = 8;
+static int64_t x3_kp(int64_t K) { return (K + BK - 1) / BK * BK; }
+static int x3_pick_splits(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int64_t T = 6 * (x3_kp(K) / BK);
+    const double t_kb = 0.16e-6;  // one 128x128x64 k-block of the mainloop
+    double best = 1e30;
+    int bs = 1;
+    const int cand[6] = {1, 2, 3, 4, 6, 8};
+    for (int ci = 0; ci < 6; ++ci) {
+        const int S = cand[ci];
+        if (S > 1 && T / S < 8) break;
+        const int64_t waves = (tiles * S + kNumSMs - 1) / kNumSMs;
+        double t = (double)waves * (double)((T + S - 1) / S) * t_kb;
+        if (S > 1) t += 3e-6 + (double)(S + 1) * (double)M * (double)N * 4.0 / 3.0e12;
+        if (t < best * 0.97) { best = t; bs = S; }
+    }
+    return bs;
+}
+struct WsX3 { size_t a, b, part, total; };
+static WsX3 ws_x3_layout(int64_t M, int64_t N, int64_t K) {
+    WsX3 w;
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return at; };
+    const int64_t Kp = x3_kp(K);
+    w.a = take((size_t)M * 3 * Kp * 2);
+    w.b = take((size_t)N * 3 * Kp * 2);
+    w.part = take((size_t)X3_MAX_SPLITS * M * N * 4);
+    w.total = o;
+    return w;
+}
+}}  // namespace hvae::tc
+
+extern "C" size_t hvae_gemm_x3_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return tc::ws_x3_layout(M, N, K).total;
+}
+
+extern "C" int hvae_gemm_x3_num_launches(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return 3 + (tc::x3_pick_splits(M, N, K) > 1 ? 1 : 0);
+}
+
+// C (M, N) = opA (M, K) . opB (N, K)^T  (+ bias[n]) (ReLU), fp32 in / fp32 out, ~fp32 accuracy:
+// each operand is split into three bf16 pieces and the six piece products down to 2^-16 relative are accumulated
+// (smallest first) in the fp32 TMEM accumulator by ONE tcgen05 GEMM whose K loop walks the (A piece, B piece) pairs.
+// a_trans / b_trans: the operand is stored (K, M) / (K, N) instead of (M, K) / (N, K).
+extern "C" int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int b_trans, const float* bias, int relu,
+                                float* C, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) return HVAE_ESHAPE;
+    if (!A || !B || !C || !workspace) return HVAE_EARG;
+    const tc::WsX3 L = tc::ws_x3_layout(M, N, K);
+    if (workspace_bytes < L.total) return HVAE_EARG;
+    const int64_t Kp = tc::x3_kp(K);
+    if (3 * Kp > 0x7fffffffLL) return HVAE_ESHAPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* a16 = (__nv_bfloat16*)(ws + L.a);
+    auto* b16 = (__nv_bfloat16*)(ws + L.b);
+    float* part = (float*)(ws + L.part);
+    auto split = [&](const float* src, int trans, __nv_bfloat16* dst, int64_t rows) {
+        if (!trans) {
+            const int64_t n = rows * (Kp / 2);
+            const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
+            tc::k_split3_rows<<<grid, 256, 0, s>>>(src, dst, rows, K, Kp);
+        } else {  // stored (K, rows)
+            dim3 grid((unsigned)(Kp / 32), (unsigned)((rows + 31) / 32));
+            tc::k_split3_transposed<<<grid, 256, 0, s>>>(src, dst, K, rows, Kp);
+        }
+    };
+    split(A, a_trans, a16, M);
+    split(B, b_trans, b16, N);
+    const int S = tc::x3_pick_splits(M, N, K);
+    tc::Params prm{};
+    prm.M = M; prm.N = N; prm.K = 3 * Kp;
+    prm.npairs = 6; prm.kbp = (int)(Kp / tc::BK); prm.splits = S;
+    // pieces: 0 = hi, 1 = mid, 2 = lo; smallest products first
+    const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};
+    for (int i = 0; i < 6; ++i) { prm.a_off[i] = (int)(pa[i] * Kp); prm.b_off[i] = (int)(pb[i] * Kp); }
+    if (S == 1) {
+        prm.D = C; prm.bias = bias; prm.relu = relu;
+        return tc::launch_gemm<tc::EPI_X3>(a16, b16, prm, s);
+    }
+    prm.D = part;
+    int rc = tc::launch_gemm<tc::EPI_X3>(a16, b16, prm, s);
+    if (rc != HVAE_OK) return rc;
+    const int64_t n = M * N;
+    const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
+    tc::k_splitk_reduce<<<grid, 256, 0, s>>>(part, bias, C, M, N, S, relu);
+    return check_launch();
 }

@@ -149,3 +149,12 @@ class Distance2StereographicHyperplanes(Distance2PoincareHyperplanes):
 
     def __init__(self, plane_shape: int, num_planes: int, signed=True, squared=False, *, ball: PoincareBall, std=1.0):
         super().__init__(plane_shape, num_planes, bias=False, signed=signed, squared=squared, ball=ball, std=std)
+
+
+class Linear(nn.Linear):
+    """torch.nn.Linear (same parameters, same state_dict keys) whose GEMM-sized CUDA fp32 calls run on the tensor-core
+    fp32-accurate GEMM (ops.linear); everything else defers to torch.  reference: the nn.Linear trunk layers of
+    hyperbolic_vae/models/*.py and pvae's Enc/Dec."""
+
+    def forward(self, input):
+        return ops.linear(input, self.weight, self.bias)

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .distributions.wrapped_normal import WrappedNormal
-from .layers import Distance2PoincareHyperplanes, Distance2StereographicHyperplanes, ExpMap0, GeodesicLayer, MobiusLayer
+from .layers import Distance2PoincareHyperplanes, Distance2StereographicHyperplanes, ExpMap0, GeodesicLayer, Linear, MobiusLayer
 from .manifolds import PoincareBall
 
 
@@ -70,12 +70,12 @@ class ModelA(nn.Module, _LatentMixin):
         self.beta, self.latent_dim, self.prior_scale, self.fused = beta, latent_dim, prior_scale, fused
         self.manifold = PoincareBall(c=manifold_curvature)
         n = data_shape.numel()
-        self.encoder = nn.Sequential(nn.Flatten(), nn.Linear(n, 64), nn.GELU(), nn.Linear(64, 16), nn.GELU())
-        self.mu = nn.Sequential(nn.Linear(16, latent_dim), ExpMap0(self.manifold))
-        self.scale = nn.Sequential(nn.Linear(16, latent_dim), nn.Softplus())
+        self.encoder = nn.Sequential(nn.Flatten(), Linear(n, 64), nn.GELU(), Linear(64, 16), nn.GELU())
+        self.mu = nn.Sequential(Linear(16, latent_dim), ExpMap0(self.manifold))
+        self.scale = nn.Sequential(Linear(16, latent_dim), nn.Softplus())
         self.decoder = nn.Sequential(
             Distance2StereographicHyperplanes(latent_dim, 16, ball=self.manifold),
-            nn.GELU(), nn.Linear(16, 64), nn.GELU(), nn.Linear(64, n), nn.Sigmoid(),
+            nn.GELU(), Linear(16, 64), nn.GELU(), Linear(64, n), nn.Sigmoid(),
             nn.Unflatten(dim=-1, unflattened_size=data_shape),
         )
 
@@ -104,14 +104,14 @@ class ImageVAEHyperbolic(nn.Module):
         )
         feat = 32 * (w // 8) * (h // 8)
         if encoder_last_layer_module == "linear":
-            self.mu = nn.Linear(feat, latent_dim)
+            self.mu = Linear(feat, latent_dim)
         elif encoder_last_layer_module == "mobius":
             self.mu = MobiusLayer(feat, latent_dim, self.manifold)
         else:
             raise ValueError(f"encoder_last_layer_module {encoder_last_layer_module} not supported")
-        self.log_var = nn.Linear(feat, latent_dim)
+        self.log_var = Linear(feat, latent_dim)
         if decoder_first_layer_module == "linear":
-            first = nn.Linear(latent_dim, feat)
+            first = Linear(latent_dim, feat)
         elif decoder_first_layer_module == "geodesic":
             first = GeodesicLayer(latent_dim, feat, self.manifold)
         elif decoder_first_layer_module == "mobius":
@@ -170,12 +170,12 @@ class ModelC(nn.Module, _LatentMixin):
         n = torch.Size(input_data_shape).numel()
         self.beta, self.latent_dim, self.prior_scale, self.fused = beta, latent_dim, 1.0, fused
         self.manifold = PoincareBall(c=manifold_curvature)
-        self.encoder = nn.Sequential(nn.Linear(n, hidden_layer_dim), nn.GELU())
-        self.mu = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), ExpMap0(self.manifold))
-        self.scale = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), nn.Softplus())
+        self.encoder = nn.Sequential(Linear(n, hidden_layer_dim), nn.GELU())
+        self.mu = nn.Sequential(Linear(hidden_layer_dim, latent_dim), ExpMap0(self.manifold))
+        self.scale = nn.Sequential(Linear(hidden_layer_dim, latent_dim), nn.Softplus())
         self.decoder = nn.Sequential(
             Distance2StereographicHyperplanes(latent_dim, hidden_layer_dim, ball=self.manifold),
-            nn.GELU(), nn.Linear(hidden_layer_dim, n), nn.Sigmoid(),
+            nn.GELU(), Linear(hidden_layer_dim, n), nn.Sigmoid(),
         )
 
     def loss(self, x, eps=None):
@@ -196,9 +196,9 @@ class ModelOneB(nn.Module, _LatentMixin):
         self.latent_manifold = PoincareBall(latent_curvature)
         self.prior_scale, self.beta, self.kl_loss_method = prior_scale, beta, kl_loss_method
         self.last_activation, self.loss_recon_method = last_activation, loss_recon_method
-        self.encoder = nn.Sequential(*([] if len(input_size) == 1 else [nn.Flatten()]), nn.Linear(n, hidden_layer_dim), nn.GELU())
-        self.mu = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), ExpMap0(self.latent_manifold))
-        self.scale = nn.Sequential(nn.Linear(hidden_layer_dim, latent_dim), nn.Softplus())
+        self.encoder = nn.Sequential(*([] if len(input_size) == 1 else [nn.Flatten()]), Linear(n, hidden_layer_dim), nn.GELU())
+        self.mu = nn.Sequential(Linear(hidden_layer_dim, latent_dim), ExpMap0(self.latent_manifold))
+        self.scale = nn.Sequential(Linear(hidden_layer_dim, latent_dim), nn.Softplus())
         tail = [] if len(input_size) == 1 else [nn.Unflatten(1, input_size)]
         if last_activation == "sigmoid":
             tail.append(nn.Sigmoid())
@@ -206,7 +206,7 @@ class ModelOneB(nn.Module, _LatentMixin):
             tail.append(nn.Softplus())
         self.decoder = nn.Sequential(
             Distance2PoincareHyperplanes(latent_dim, hidden_layer_dim, ball=self.latent_manifold),
-            nn.GELU(), nn.Linear(hidden_layer_dim, n), *tail,
+            nn.GELU(), Linear(hidden_layer_dim, n), *tail,
         )
 
     @property
@@ -268,11 +268,11 @@ class PvaeMnist(nn.Module):
         n = self.data_size.numel()
         self.manifold = PoincareBall(c)
         self.beta, self.prior_std, self.latent_dim = beta, prior_std, latent_dim
-        self.enc = nn.Sequential(nn.Linear(n, hidden_dim), nn.ReLU())
+        self.enc = nn.Sequential(Linear(n, hidden_dim), nn.ReLU())
         self.fc21 = MobiusLayer(hidden_dim, latent_dim, self.manifold)
-        self.fc22 = nn.Linear(hidden_dim, 1)
+        self.fc22 = Linear(hidden_dim, 1)
         self.dec0 = GeodesicLayer(latent_dim, hidden_dim, self.manifold)
-        self.fc31 = nn.Linear(hidden_dim, n)
+        self.fc31 = Linear(hidden_dim, n)
         self._pz_mu = nn.Parameter(torch.zeros(1, latent_dim), requires_grad=False)
         self._pz_logvar = nn.Parameter(torch.zeros(1, 1), requires_grad=False)
 

@@ -973,3 +973,91 @@ def _rk_backward(ctx, g):
 
 
 rn_kl_fwd.register_autograd(_rk_backward, setup_context=_rk_setup)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Trunk dense layers: fp32-accurate GEMM on the tensor cores (three-way bf16 split, six products)
+# ---------------------------------------------------------------------------------------------------
+_trunk_mode = "x3"
+
+
+def set_trunk_mode(mode: str):
+    """'x3' (default): hvae.layers.Linear runs on the tcgen05 split-bf16 GEMM (fp32 accuracy, fp32 in/out);
+    'torch': it defers to torch.nn.functional.linear (cuBLAS fp32 FMA kernels)."""
+    global _trunk_mode
+    if mode not in ("x3", "torch"):
+        raise ValueError(mode)
+    _trunk_mode = mode
+
+
+def get_trunk_mode() -> str:
+    return _trunk_mode
+
+
+def trunk_x3_eligible(x: Tensor, weight: Tensor) -> bool:
+    return (_trunk_mode == "x3" and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and x.numel() // x.shape[-1] >= 128 and weight.shape[0] >= 64 and weight.shape[1] >= 64)
+
+
+@_op("hvae::gemm_x3", mutates_args=())
+def gemm_x3(A: Tensor, a_trans: bool, B: Tensor, b_trans: bool, bias: Optional[Tensor], relu: bool) -> Tensor:
+    """C (M,N) = opA (M,K) . opB (N,K)^T (+ bias) (ReLU); *_trans: the operand is stored (K,M) / (K,N)."""
+    C.require_cuda(A, B)
+    K, M = (A.shape[0], A.shape[1]) if a_trans else (A.shape[1], A.shape[0])
+    Kb, N = (B.shape[0], B.shape[1]) if b_trans else (B.shape[1], B.shape[0])
+    if K != Kb:
+        raise RuntimeError("gemm_x3: contraction mismatch %d vs %d" % (K, Kb))
+    out = A.new_empty(M, N)
+    ws = _workspace(C.lib().hvae_gemm_x3_workspace_bytes(M, N, K), A.device)
+    C.call("hvae_gemm_x3_f32", C.ptr(A), int(a_trans), C.ptr(B), int(b_trans), C.ptr(bias), int(relu), C.ptr(out), M, N, K,
+           C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += C.lib().hvae_gemm_x3_num_launches(M, N, K)
+    return out
+
+
+@gemm_x3.register_fake
+def _(A, a_trans, B, b_trans, bias, relu):
+    M = A.shape[1] if a_trans else A.shape[0]
+    N = B.shape[1] if b_trans else B.shape[0]
+    return A.new_empty(M, N)
+
+
+@_op("hvae::linear_x3", mutates_args=())
+def linear_x3_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    return gemm_x3(x, False, weight, False, bias, False)
+
+
+@linear_x3_fwd.register_fake
+def _(x, weight, bias):
+    return x.new_empty(x.shape[0], weight.shape[0])
+
+
+def _lx3_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+
+
+def _lx3_backward(ctx, gy):
+    x, weight = ctx.saved_tensors
+    gy = _c(gy)
+    gx = gw = gb = None
+    if ctx.needs_input_grad[0]:
+        gx = gemm_x3(gy, False, weight, True, None, False)   # (M, in) = gy (M, out) . W (out, in): contraction over out
+    if ctx.needs_input_grad[1]:
+        gw = gemm_x3(gy, True, x, True, None, False)         # (out, in) = gy^T (out, M) . x (M, in): contraction over M
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        gb = gy.sum(0)
+    return gx, gw, gb
+
+
+linear_x3_fwd.register_autograd(_lx3_backward, setup_context=_lx3_setup)
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """torch.nn.functional.linear semantics; the tensor-core fp32 path for GEMM-sized CUDA inputs."""
+    if trunk_x3_eligible(x, weight):
+        lead = x.shape[:-1]
+        y = linear_x3_fwd(_rows(x), _c(weight), None if bias is None else _c(bias))
+        return y.view(*lead, weight.shape[0])
+    return torch.nn.functional.linear(x, weight, bias)

@@ -175,6 +175,17 @@ int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, const float* y
 int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
                               int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fp32-accurate dense GEMM on the tensor cores: the Euclidean trunk layers either side of the hyperbolic path
+ * (reference: nn.Linear in hyperbolic_vae/models/vae_hyperbolic_*.py encoders/decoders and pvae Enc/Dec).
+ *   C (M,N) = opA (M,K) . opB (N,K)^T  (+ bias[n]) (ReLU)
+ * a_trans / b_trans != 0: the operand is stored (K,M) / (K,N).  Every fp32 operand is split into three bf16 pieces
+ * (24 mantissa bits) and the six piece products down to 2^-16 are accumulated in fp32 (cf. cuBLAS BF16x9): the error
+ * against a float64 product is that of an fp32 FMA GEMM (tests/test_gpu_trunk.py), so the 1e-5 budget holds. */
+size_t hvae_gemm_x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int hvae_gemm_x3_num_launches(int64_t M, int64_t N, int64_t K);
+int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int b_trans, const float* bias, int relu, float* C,
+                     int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
