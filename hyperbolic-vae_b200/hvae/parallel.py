@@ -7,8 +7,10 @@ parameter-gradient sum.  Loss reductions decide the scale rule:
   batch-SUM losses (model B: models/vae_hyperbolic.py:216,219)  -> SUM, no rescale reproduces 1-GPU grads;
   batch-MEAN losses (models A/C: ...gyroplane_decoder.py:151)   -> each rank's mean is over its shard, so
                                                                    SUM then divide by world size (AVG).
-The payload is 0.2-4 MB: latency-bound on NVLink 5/NVSwitch, so a single collective (NCCL picks NVLS/tree)
-is the right shape; there is no compute-then-collective kernel on this path to fuse with.
+The payload is 0.2-4 MB: latency-bound on NVLink 5/NVSwitch.  The bucket can be cut into an EARLY segment (the
+parameters whose gradients autograd finishes first — the decoder tail) and the rest: the early segment's all-reduce
+is issued from a gradient hook on a side stream and runs under the remaining backward; the rest follows at the end
+(`TrainStep` picks the cut from the observed completion order of the first warm-up backward).
 """
 from __future__ import annotations
 
@@ -22,10 +24,15 @@ class FlatGradBucket:
     """Owns one contiguous buffer; every parameter's .grad is a view into it, so backward writes straight
     into the bucket and the all-reduce needs no gather/scatter copies."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        if not self.params:
+    def __init__(self, params: Iterable[torch.nn.Parameter], early: Iterable[torch.nn.Parameter] = ()):
+        """early: parameters to place first in the buffer (one contiguous segment [0, split))."""
+        ps = [p for p in params if p.requires_grad]
+        if not ps:
             raise ValueError("no trainable parameters")
+        early_ids = [id(p) for p in early]
+        first = [p for i in early_ids for p in ps if id(p) == i]
+        self.params: List[torch.nn.Parameter] = first + [p for p in ps if id(p) not in set(early_ids)]
+        self.n_early = len(first)
         dev, dt = self.params[0].device, self.params[0].dtype
         total = 0
         self.offsets = []
@@ -34,6 +41,7 @@ class FlatGradBucket:
                 raise ValueError("FlatGradBucket needs all parameters on one device/dtype")
             self.offsets.append(total)
             total += (p.numel() + 31) // 32 * 32  # keep every view 128-byte aligned
+        self.split = self.offsets[self.n_early] if 0 < self.n_early < len(self.params) else 0
         self.buffer = torch.zeros(total, device=dev, dtype=dt)
         for p, off in zip(self.params, self.offsets):
             p.grad = self.buffer[off:off + p.numel()].view_as(p)
@@ -50,8 +58,23 @@ class FlatGradBucket:
     def nbytes(self) -> int:
         return self.buffer.numel() * self.buffer.element_size()
 
+    @staticmethod
+    def _active(group=None) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def all_reduce_segment(self, which: str, average: bool, group=None):
+        """SUM (or AVG) all-reduce of the 'early' ([0, split)) or 'late' ([split, end)) segment on the current stream."""
+        if not self._active(group):
+            return
+        seg = self.buffer[:self.split] if which == "early" else self.buffer[self.split:]
+        if seg.numel() == 0:
+            return
+        dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            seg.div_(dist.get_world_size(group))
+
     def all_reduce(self, average: bool, group=None, async_op: bool = False):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if not self._active(group):
             return None
         work = dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if average:

@@ -8,9 +8,11 @@ The reference's equivalents of this call are LightningModule.training_step -> lo
 """
 from __future__ import annotations
 
+import os
 import sys
 
 import torch
+import torch.distributed as dist
 
 from .parallel import FlatGradBucket
 
@@ -21,6 +23,11 @@ class TrainStep:
         self.model, self.loss_key, self.loss_kwargs = model, loss_key, loss_kwargs
         self.average = average_grads
         self.bucket = FlatGradBucket(model.parameters())
+        self._hooks, self._order, self._fired = [], [], 0
+        self._side = torch.cuda.Stream()
+        self._early_launched = False
+        self.overlap = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                        and os.environ.get("HVAE_DP_OVERLAP", "1") != "0")
         self.x = torch.empty_like(example_input)  # static input buffer (device)
         self.x.copy_(example_input)
         self._stage = torch.empty_like(example_input)  # landing buffer of the asynchronous host->device prefetch
@@ -29,17 +36,62 @@ class TrainStep:
         self._consumed = None  # event: _stage has been copied into the static input
         self.loss = None
         self.graph = None
+        if self.overlap:
+            self._plan_overlap()
         for _ in range(3):
             self.loss = self._step()
         torch.cuda.synchronize()
         if use_graph:
             self._capture()
 
+    # ---- data-parallel overlap: the early segment's all-reduce runs under the rest of the backward -------------
+    def _plan_overlap(self, early_fraction: float = 0.35):
+        """Observe one backward: the order in which parameter gradients complete.  The first parameters to finish
+        (>= early_fraction of the payload) become the bucket's early segment; a hook on them launches that segment's
+        all-reduce on a side stream as soon as the last of them has accumulated."""
+        order = []
+        hs = [p.register_post_accumulate_grad_hook(lambda p_, order=order: order.append(p_)) for p in self.bucket.params]
+        self.bucket.zero_()
+        self.model.loss(self.x, **self.loss_kwargs)[self.loss_key].backward()
+        torch.cuda.synchronize()
+        for h in hs:
+            h.remove()
+        total = sum(p.numel() for p in order)
+        early, acc = [], 0
+        for p in order[:-1]:  # keep at least one parameter late
+            early.append(p)
+            acc += p.numel()
+            if acc >= early_fraction * total:
+                break
+        if not early or acc > 0.9 * total:
+            self.overlap = False
+            return
+        self.bucket = FlatGradBucket(self.bucket.params, early=early)
+        self._n_early = len(early)
+
+        def hook(_p):
+            self._fired += 1
+            if self._fired == self._n_early:
+                cur = torch.cuda.current_stream()
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    self.bucket.all_reduce_segment("early", self.average)
+                self._early_launched = True
+
+        self._hooks = [p.register_post_accumulate_grad_hook(hook) for p in early]
+
     def _step(self):
         self.bucket.zero_()
+        self._fired, self._early_launched = 0, False
         out = self.model.loss(self.x, **self.loss_kwargs)
         out[self.loss_key].backward()
-        self.bucket.all_reduce(average=self.average)
+        if self.overlap:
+            if not self._early_launched:  # (a parameter without gradient this step): reduce it here instead
+                self.bucket.all_reduce_segment("early", self.average)
+            self.bucket.all_reduce_segment("late", self.average)
+            torch.cuda.current_stream().wait_stream(self._side)
+        else:
+            self.bucket.all_reduce(average=self.average)
         return out[self.loss_key].detach()
 
     def _capture(self):

@@ -21,10 +21,26 @@ def _worker(rank, world, port, reduction, out_q):
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     x = torch.randn(10, 6)
     lo, hi = shard_rows(10, rank, world)
-    bucket = FlatGradBucket(model.parameters())
+    params = list(model.parameters())
+    if reduction == "segments":
+        # the overlap layout: the decoder-tail parameters (first to finish in backward) lead the buffer; the two
+        # segment all-reduces together must equal the single one.  Report in the canonical parameter order.
+        bucket = FlatGradBucket(params, early=params[2:])
+        assert bucket.n_early == 2 and 0 < bucket.split < bucket.buffer.numel()
+        assert [id(p) for p in bucket.params] == [id(p) for p in params[2:] + params[:2]]
+    else:
+        bucket = FlatGradBucket(params)
     bucket.zero_()
     y = model(x[lo:hi]).pow(2).sum(-1)
-    (y.sum() if reduction == "sum" else y.mean()).backward()
+    (y.mean() if reduction == "mean" else y.sum()).backward()
+    if reduction == "segments":
+        bucket.all_reduce_segment("early", average=False)
+        bucket.all_reduce_segment("late", average=False)
+        flat = torch.cat([torch.cat([p.grad.flatten(), torch.zeros((-p.numel()) % 32)]) for p in params])
+        out_q.put((rank, flat))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if reduction == "sum":
         bucket.all_reduce(average=False)
     else:
@@ -41,7 +57,7 @@ def _single(reduction):
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     x = torch.randn(10, 6)
     y = model(x).pow(2).sum(-1)
-    (y.sum() if reduction == "sum" else y.mean()).backward()
+    (y.mean() if reduction == "mean" else y.sum()).backward()
     return torch.cat([(torch.cat([p.grad.flatten(), torch.zeros((-p.numel()) % 32)])) for p in model.parameters()])
 
 
@@ -66,6 +82,10 @@ def test_dp_sum_loss_matches_single_process():
 
 def test_dp_mean_loss_matches_single_process():
     _run("mean", 29512)
+
+
+def test_dp_early_late_segments_match_single_process():
+    _run("segments", 29513)
 
 
 def test_shard_rows_cover_batch():
