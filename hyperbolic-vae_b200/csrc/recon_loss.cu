@@ -1,0 +1,101 @@
+// Reconstruction-loss head of the decoders: Bernoulli negative log-likelihood with logits, summed over the feature
+// axis of every (sample, row):   nll[s,b] = sum_n  max(l,0) - l x + log1p(exp(-|l|)),   l = logits[s,b,n], x = x[b,n]
+// reference: torch.distributions.Bernoulli(logits).log_prob(x).sum(-1) in the pvae objective
+// (hyperbolic_vae/training/old_pvae_train.py:53-58) and F.binary_cross_entropy_with_logits in
+// hyperbolic_vae/models/vae_hyperbolic_gyroplane_decoder.py loss_recon (SURVEY 8f "recon-loss heads").
+// torch runs this as ~6 elementwise + reduce kernels forward and ~6 backward over (B, 784) tensors; here one warp
+// walks one row once per direction.  HBM-bound: forward 8N + 4 bytes per row, backward 12N + 4.
+#include "hvae_common.cuh"
+
+namespace hvae {
+
+__device__ __forceinline__ float bce_term(float l, float x) {
+    return fmaxf(l, 0.0f) - l * x + log1pf(expf(-fabsf(l)));
+}
+__device__ __forceinline__ float sigmoid_acc(float l) {
+    const float e = expf(-fabsf(l));
+    const float s = 1.0f / (1.0f + e);     // sigmoid(|l|)
+    return l >= 0.0f ? s : e * s;           // sigmoid(-|l|) = e / (1 + e)
+}
+
+__global__ void __launch_bounds__(256)
+k_bce_logits_rows_fwd(const float* __restrict__ logits, const float* __restrict__ x, float* __restrict__ nll, int64_t S,
+                      int64_t B, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool v4 = (N & 3) == 0;
+    for (int64_t row = warp; row < S * B; row += nw) {
+        const float* lr = logits + row * N;
+        const float* xr = x + (row % B) * N;
+        float acc = 0.0f;
+        if (v4) {
+            for (int64_t i = lane * 4; i < N; i += 128) {
+                const float4 l = __ldg(reinterpret_cast<const float4*>(lr + i));
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+                acc += (bce_term(l.x, t.x) + bce_term(l.y, t.y)) + (bce_term(l.z, t.z) + bce_term(l.w, t.w));
+            }
+        } else {
+            for (int64_t i = lane; i < N; i += 32) acc += bce_term(__ldg(lr + i), __ldg(xr + i));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) nll[row] = acc;
+    }
+}
+
+// glogits[s,b,n] = gnll[s,b] * (sigmoid(l) - x)
+__global__ void __launch_bounds__(256)
+k_bce_logits_rows_bwd(const float* __restrict__ logits, const float* __restrict__ x, const float* __restrict__ gnll,
+                      float* __restrict__ glogits, int64_t S, int64_t B, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool v4 = (N & 3) == 0;
+    for (int64_t row = warp; row < S * B; row += nw) {
+        const float* lr = logits + row * N;
+        const float* xr = x + (row % B) * N;
+        float* gr = glogits + row * N;
+        const float g = __ldg(gnll + row);
+        if (v4) {
+            for (int64_t i = lane * 4; i < N; i += 128) {
+                const float4 l = __ldg(reinterpret_cast<const float4*>(lr + i));
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+                float4 o;
+                o.x = g * (sigmoid_acc(l.x) - t.x);
+                o.y = g * (sigmoid_acc(l.y) - t.y);
+                o.z = g * (sigmoid_acc(l.z) - t.z);
+                o.w = g * (sigmoid_acc(l.w) - t.w);
+                *reinterpret_cast<float4*>(gr + i) = o;
+            }
+        } else {
+            for (int64_t i = lane; i < N; i += 32) gr[i] = g * (sigmoid_acc(__ldg(lr + i)) - __ldg(xr + i));
+        }
+    }
+}
+
+}  // namespace hvae
+
+using namespace hvae;
+
+static unsigned bce_grid(int64_t rows) {
+    const int64_t want = (rows + 7) / 8;  // 8 warps per CTA
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+extern "C" int hvae_bce_logits_rows_fwd_f32(const float* logits, const float* x, float* nll, int64_t S, int64_t B, int64_t N,
+                                            void* stream) {
+    if (S <= 0 || B <= 0 || N <= 0) return HVAE_ESHAPE;
+    if (!logits || !x || !nll) return HVAE_EARG;
+    k_bce_logits_rows_fwd<<<bce_grid(S * B), 256, 0, (cudaStream_t)stream>>>(logits, x, nll, S, B, N);
+    return check_launch();
+}
+
+extern "C" int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const float* gnll, float* glogits, int64_t S,
+                                            int64_t B, int64_t N, void* stream) {
+    if (S <= 0 || B <= 0 || N <= 0) return HVAE_ESHAPE;
+    if (!logits || !x || !gnll || !glogits) return HVAE_EARG;
+    k_bce_logits_rows_bwd<<<bce_grid(S * B), 256, 0, (cudaStream_t)stream>>>(logits, x, gnll, glogits, S, B, N);
+    return check_launch();
+}

@@ -65,6 +65,7 @@ struct Params {
     // k-blocks each; npairs == 0 -> one piece of ceil(K / BK) k-blocks.  splits > 1: split-K, unit (tile, s) writes
     // its partial tile to D + s * M * N.
     int npairs, kbp, splits;
+    int a_mn, b_mn;        // operand stored contraction-major-OUTER: buffer rows = contraction index, columns = M / N index
     int a_off[6], b_off[6];
     int relu;              // PLAIN: bias (per column, via `bias`) then optional ReLU
     int dbg;               // experiments only (HVAE_TC_DBG): 1 = skip the global stores, 2 = skip the whole drain
@@ -122,15 +123,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
     return d;
 }
+// MN-major, 128B-swizzled operand tile, loaded as two TMA boxes {64 MN elements (128 B), 64 contraction rows}: a
+// contraction row is 128 B, 8-row groups are 1024 B apart (SBO), the second 64-wide MN block sits 8192 B later (LBO).
+// One UMMA consumes 16 contraction rows = 2048 B, so the k-step advance is whole swizzle atoms.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset: between 64-element MN blocks
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: between 8-row contraction groups
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -253,8 +266,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         }
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         mbar_expect_tx(full_bar(stage), ARES ? TILE_B_BYTES : STAGE_BYTES);
-                        if (!ARES) tma_load_2d(a_tile(stage), &map_a, full_bar(stage), ka, m0);
-                        tma_load_2d(b_tile(stage), &map_b, full_bar(stage), kbo, n0);
+                        if (!ARES) {
+                            if (prm.a_mn) {  // piece offset moves to the MN coordinate, the k-block to the row coordinate
+                                const int kk = ka - (prm.npairs ? prm.a_off[f / kbp] : 0), mn = m0 + (prm.npairs ? prm.a_off[f / kbp] : 0);
+                                tma_load_2d(a_tile(stage), &map_a, full_bar(stage), mn, kk);
+                                tma_load_2d(a_tile(stage) + 8192u, &map_a, full_bar(stage), mn + 64, kk);
+                            } else {
+                                tma_load_2d(a_tile(stage), &map_a, full_bar(stage), ka, m0);
+                            }
+                        }
+                        if (prm.b_mn) {
+                            const int kk = kbo - (prm.npairs ? prm.b_off[f / kbp] : 0), mn = n0 + (prm.npairs ? prm.b_off[f / kbp] : 0);
+                            tma_load_2d(b_tile(stage), &map_b, full_bar(stage), mn, kk);
+                            tma_load_2d(b_tile(stage) + 8192u, &map_b, full_bar(stage), mn + 64, kk);
+                        } else {
+                            tma_load_2d(b_tile(stage), &map_b, full_bar(stage), kbo, n0);
+                        }
                         if (++stage == NST) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -265,6 +292,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0, pphase = 0;
+            const uint32_t idesc = kIdesc | (prm.a_mn ? (1u << 15) : 0u) | (prm.b_mn ? (1u << 16) : 0u);
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
                 const int64_t tile = ARES ? u : u / S;
                 const int sp = ARES ? 0 : (int)(u % S);
@@ -285,11 +313,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int kb = c0; kb < c1; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint64_t da = make_desc(a_tile(ARES ? kb : stage)), db = make_desc(b_tile(stage));
+                        const uint64_t da = prm.a_mn ? make_desc_mn(a_tile(stage)) : make_desc(a_tile(ARES ? kb : stage));
+                        const uint64_t db = prm.b_mn ? make_desc_mn(b_tile(stage)) : make_desc(b_tile(stage));
+                        // k-step advance in the (addr >> 4) field: K-major 16 bf16 = 32 B inside the swizzle atom (+2);
+                        // MN-major 16 contraction rows = 2048 B (+128)
+                        const uint64_t sa = prm.a_mn ? 128u : 2u, sb = prm.b_mn ? 128u : 2u;
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-                            umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (uint32_t)(((kb - c0) | k) != 0));
+                            umma(tmem_d, da + sa * (uint64_t)k, db + sb * (uint64_t)k, idesc, (uint32_t)(((kb - c0) | k) != 0));
                         }
                         umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
                         if (++stage == NST) { stage = 0; phase ^= 1u; }
@@ -831,13 +862,20 @@ static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, i
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// buffer shapes (rows, cols) of the two operands: by default (M, K) and (N, K); an MN-major operand (prm.a_mn / b_mn) is a
+// (contraction, >= M or N) buffer fetched in {64, 64} boxes
+struct OperandShapes { int64_t a_rows = -1, a_cols = -1, b_rows = -1, b_cols = -1; };
+
 template <int EPI>
-static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm_in, cudaStream_t s) {
+static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm_in, cudaStream_t s,
+                       OperandShapes sh = OperandShapes()) {
     Params prm = prm_in;
     static const int dbg = getenv("HVAE_TC_DBG") ? atoi(getenv("HVAE_TC_DBG")) : 0;
     prm.dbg = dbg;
     CUtensorMap ma, mb;
-    if (!make_map(&ma, A, prm.M, prm.K, BM) || !make_map(&mb, Bm, prm.N, prm.K, BN)) return HVAE_ELAUNCH;
+    const int64_t ar = sh.a_rows >= 0 ? sh.a_rows : prm.M, ac = sh.a_cols >= 0 ? sh.a_cols : prm.K;
+    const int64_t br = sh.b_rows >= 0 ? sh.b_rows : prm.N, bc = sh.b_cols >= 0 ? sh.b_cols : prm.K;
+    if (!make_map(&ma, A, ar, ac, prm.a_mn ? 64 : BM) || !make_map(&mb, Bm, br, bc, prm.b_mn ? 64 : BN)) return HVAE_ELAUNCH;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_tc_gemm<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
@@ -848,7 +886,7 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over, and enough m-blocks
     // (not for the gyroplane epilogue: measured slower there, its per-tile column-constant exchange serialises the n-tiles)
     static const bool want_ares = getenv("HVAE_TC_NO_ARES") == nullptr;
-    const bool ares = want_ares && EPI != EPI_GYRO && prm.npairs == 0 && prm.splits <= 1 && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
+    const bool ares = want_ares && EPI != EPI_GYRO && prm.npairs == 0 && prm.splits <= 1 && !prm.a_mn && !prm.b_mn && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
     if (ares) {
         const int grid = (int)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
         k_tc_gemm<EPI, true><<<grid, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, prm);
@@ -1076,6 +1114,69 @@ static WsX3 ws_x3_layout(int64_t M, int64_t N, int64_t K) {
     return w;
 }
 }}  // namespace hvae::tc
+
+// ---- pre-split operands: split once, use in several GEMMs (forward, dgrad, wgrad) -------------------------------------
+extern "C" size_t hvae_split3_bytes(int64_t rows, int64_t cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    return (size_t)rows * 3 * (size_t)tc::x3_kp(cols) * 2;
+}
+
+// src (rows, cols) fp32 -> dst (rows, 3*Cp) bf16, Cp = cols rounded up to 64; piece t in columns [t*Cp, t*Cp + cols)
+extern "C" int hvae_split3_f32(const float* src, void* dst, int64_t rows, int64_t cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return HVAE_ESHAPE;
+    if (!src || !dst) return HVAE_EARG;
+    const int64_t Cp = tc::x3_kp(cols);
+    const int64_t n = rows * (Cp / 2);
+    const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
+    tc::k_split3_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, cols, Cp);
+    return check_launch();
+}
+
+extern "C" size_t hvae_gemm_x3s_workspace_bytes(int64_t M, int64_t N) {
+    if (M <= 0 || N <= 0) return 0;
+    return (size_t)tc::X3_MAX_SPLITS * M * N * 4 + 256;
+}
+extern "C" int hvae_gemm_x3s_num_launches(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return 1 + (tc::x3_pick_splits(M, N, K) > 1 ? 1 : 0);
+}
+
+// C (M, N) = opA (M, K) . opB (N, K)^T (+ bias[n]) (ReLU) on operands already split by hvae_split3_f32.
+//   a_mn == 0: As is the split of an (M, K) matrix (contraction contiguous);
+//   a_mn != 0: As is the split of a  (K, M) matrix (the contraction runs over its ROWS) - no transpose is made, the
+//              tensor core reads the tile MN-major.  Same for Bs / b_mn with N.
+extern "C" int hvae_gemm_x3s_f32(const void* As, int a_mn, const void* Bs, int b_mn, const float* bias, int relu, float* C,
+                                 int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) return HVAE_ESHAPE;
+    if (!As || !Bs || !C) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t Kp = tc::x3_kp(K), Mp = tc::x3_kp(M), Np = tc::x3_kp(N);
+    const int S = tc::x3_pick_splits(M, N, K);
+    if (S > 1 && (!workspace || workspace_bytes < (size_t)S * M * N * 4)) return HVAE_EARG;
+    tc::Params prm{};
+    prm.M = M; prm.N = N; prm.K = 3 * Kp;
+    prm.npairs = 6; prm.kbp = (int)(Kp / tc::BK); prm.splits = S;
+    prm.a_mn = a_mn ? 1 : 0; prm.b_mn = b_mn ? 1 : 0;
+    const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};  // 0 = hi, 1 = mid, 2 = lo; smallest products first
+    for (int i = 0; i < 6; ++i) {
+        prm.a_off[i] = (int)(pa[i] * (a_mn ? Mp : Kp));
+        prm.b_off[i] = (int)(pb[i] * (b_mn ? Np : Kp));
+    }
+    tc::OperandShapes sh;
+    if (a_mn) { sh.a_rows = K; sh.a_cols = 3 * Mp; } else { sh.a_rows = M; sh.a_cols = 3 * Kp; }
+    if (b_mn) { sh.b_rows = K; sh.b_cols = 3 * Np; } else { sh.b_rows = N; sh.b_cols = 3 * Kp; }
+    if (S == 1) {
+        prm.D = C; prm.bias = bias; prm.relu = relu;
+        return tc::launch_gemm<tc::EPI_X3>((const __nv_bfloat16*)As, (const __nv_bfloat16*)Bs, prm, s, sh);
+    }
+    prm.D = (float*)workspace;
+    int rc = tc::launch_gemm<tc::EPI_X3>((const __nv_bfloat16*)As, (const __nv_bfloat16*)Bs, prm, s, sh);
+    if (rc != HVAE_OK) return rc;
+    const int64_t n = M * N;
+    const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
+    tc::k_splitk_reduce<<<grid, 256, 0, s>>>((const float*)workspace, bias, C, M, N, S, relu);
+    return check_launch();
+}
 
 extern "C" size_t hvae_gemm_x3_workspace_bytes(int64_t M, int64_t N, int64_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;

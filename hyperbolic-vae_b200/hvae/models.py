@@ -292,7 +292,10 @@ class PvaeMnist(nn.Module):
         q = RiemannianNormal(mu, sigma, self.manifold)
         zs = q.rsample(torch.Size([1]), alpha=alpha, r=r)  # (1,B,D)
         logits = self.decode(zs)
-        lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
+        if self.fused:
+            lpx_z = -ops.bernoulli_nll_rows(logits, x.view(B, -1))  # one row kernel per direction
+        else:
+            lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
         pz_scale = F.softplus(self._pz_logvar) / math.log(2) * self.prior_std
         p = RiemannianNormal(self._pz_mu, pz_scale, self.manifold)
         if self.fused:

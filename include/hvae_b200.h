@@ -175,12 +175,30 @@ int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, const float* y
 int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
                               int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- reconstruction-loss head: Bernoulli NLL with logits, summed over the feature axis (reference:
+ * Bernoulli(logits).log_prob(x).sum(-1) in training/old_pvae_train.py:53-58; F.binary_cross_entropy_with_logits in
+ * models/vae_hyperbolic_gyroplane_decoder.py).  logits (S,B,N), x (B,N) broadcast over S, nll / gnll (S,B). */
+int hvae_bce_logits_rows_fwd_f32(const float* logits, const float* x, float* nll, int64_t S, int64_t B, int64_t N,
+                                 void* stream);
+int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const float* gnll, float* glogits, int64_t S,
+                                 int64_t B, int64_t N, void* stream);
+
 /* ---- fp32-accurate dense GEMM on the tensor cores: the Euclidean trunk layers either side of the hyperbolic path
  * (reference: nn.Linear in hyperbolic_vae/models/vae_hyperbolic_*.py encoders/decoders and pvae Enc/Dec).
  *   C (M,N) = opA (M,K) . opB (N,K)^T  (+ bias[n]) (ReLU)
  * a_trans / b_trans != 0: the operand is stored (K,M) / (K,N).  Every fp32 operand is split into three bf16 pieces
  * (24 mantissa bits) and the six piece products down to 2^-16 are accumulated in fp32 (cf. cuBLAS BF16x9): the error
  * against a float64 product is that of an fp32 FMA GEMM (tests/test_gpu_trunk.py), so the 1e-5 budget holds. */
+/* Split once, multiply several times (a dense layer uses each split in forward, dgrad and wgrad):
+ *   hvae_split3_f32: src (rows, cols) fp32 -> dst (rows, 3*Cp) bf16, Cp = cols rounded up to 64 (hvae_split3_bytes).
+ *   hvae_gemm_x3s_f32: the GEMM above on split operands.  a_mn / b_mn != 0: that operand is the split of a (K, M) /
+ *   (K, N) matrix - the contraction runs over its rows and the tensor core reads it MN-major, no transpose is made. */
+size_t hvae_split3_bytes(int64_t rows, int64_t cols);
+int hvae_split3_f32(const float* src, void* dst, int64_t rows, int64_t cols, void* stream);
+size_t hvae_gemm_x3s_workspace_bytes(int64_t M, int64_t N);
+int hvae_gemm_x3s_num_launches(int64_t M, int64_t N, int64_t K);
+int hvae_gemm_x3s_f32(const void* As, int a_mn, const void* Bs, int b_mn, const float* bias, int relu, float* C,
+                      int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream);
 size_t hvae_gemm_x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int hvae_gemm_x3_num_launches(int64_t M, int64_t N, int64_t K);
 int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int b_trans, const float* bias, int relu, float* C,

@@ -51,6 +51,37 @@ def test_gemm_x3_matches_fp32_accuracy(M, N, K, ta, tb):
     assert torch.equal(outr, out.clamp_min(0))
 
 
+# pre-split operands, every combination of K-major / MN-major reads (the backward GEMMs of a dense layer use the
+# forward's splits MN-major instead of transposing), with ragged sizes and split-K shapes
+@pytest.mark.parametrize("M,N,K", [(4096, 784, 600), (600, 784, 4096), (257, 130, 77), (128, 64, 64), (1000, 601, 333)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_x3s_operand_majors(M, N, K, a_mn, b_mn):
+    from hvae import ops
+
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    ref = A.double() @ B.double().t() + bias.double()
+    As = ops.split3(A.t().contiguous() if a_mn else A)
+    Bs = ops.split3(B.t().contiguous() if b_mn else B)
+    out = ops.gemm_x3s(As, a_mn, Bs, b_mn, bias, False, M, N, K)
+    torch.cuda.synchronize()
+    e = _rel(out, ref)
+    assert e < 2e-6, e
+
+
+def test_split3_is_exact_to_24_bits():
+    from hvae import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(300, 100, device="cuda") * torch.rand(300, 1, device="cuda").mul(20).sub(10).exp()
+    s = ops.split3(x).float().view(300, 3, 128)
+    assert torch.equal(s[:, :, 100:], torch.zeros_like(s[:, :, 100:]))
+    rec = s[:, 0, :100].double() + s[:, 1, :100].double() + s[:, 2, :100].double()
+    assert float(((rec - x.double()).abs() / x.double().abs()).max()) < 2.0 ** -23
+
+
 def test_linear_layer_forward_backward():
     from hvae import layers, ops
 
@@ -81,3 +112,56 @@ def test_linear_layer_forward_backward():
     small = layers.Linear(16, 8).cuda()
     xs = torch.randn(4, 16, device="cuda")
     assert torch.equal(small(xs), torch.nn.functional.linear(xs, small.weight, small.bias))
+
+
+@pytest.mark.parametrize("S,B,N", [(1, 4096, 784), (3, 17, 10), (2, 5, 1)])
+def test_bernoulli_nll_rows(S, B, N):
+    from hvae import ops
+
+    torch.manual_seed(S + B + N)
+    logits = (torch.randn(S, B, N, device="cuda") * 6).requires_grad_(True)  # includes |l| > 15 (saturated sigmoid)
+    x = torch.rand(B, N, device="cuda")
+    g = torch.randn(S, B, device="cuda")
+    out = ops.bernoulli_nll_rows(logits, x)
+    out.backward(g)
+    ld = logits.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(ld, x.double().expand(S, B, N), reduction="none").sum(-1)
+    ref.backward(g.double())
+    assert float(((out.double() - ref).abs() / ref.abs()).max()) < 1e-5   # 1e-5 relative, fp32 sums over N terms
+    gscale = ld.grad.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30)
+    assert float(((logits.grad.double() - ld.grad).abs() / gscale).max()) < 1e-5
+
+
+def test_cfg2_step_fused_heads_match_torch_heads():
+    """config-2 shapes: the step with the tensor-core trunk + fused loss head against the same model on torch's
+    fp32 Linear / BCE kernels (same noise): loss within 1e-5; parameter gradients within 1e-4 in norm (two fp32
+    GEMM implementations differ by ~1e-6, which flips the ReLU mask of the few pre-activations that close to zero)."""
+    import hvae
+    from hvae import models, ops
+
+    torch.manual_seed(0)
+    B = 4096
+    x = torch.rand(B, 1, 28, 28, device="cuda")
+    model = models.PvaeMnist().cuda()
+    alpha = torch.randn(1, B, 10, device="cuda")
+    mu, sigma = model.encode(x)
+    from hvae.distributions.riemannian_normal import RiemannianNormal
+
+    r = RiemannianNormal(mu, sigma, model.manifold).radius.sample(torch.Size([1])).detach()
+    res = {}
+    for mode in ("ours", "torch"):
+        model.zero_grad(set_to_none=True)
+        model.fused = mode == "ours"
+        ops.set_trunk_mode("x3" if mode == "ours" else "torch")
+        try:
+            out = model.loss(x, alpha=alpha, r=r)
+            out["loss_total"].backward()
+        finally:
+            ops.set_trunk_mode("x3")
+            model.fused = True
+        res[mode] = (out["loss_total"].detach().double(), {n: p.grad.detach().double().clone() for n, p in model.named_parameters() if p.grad is not None})
+    la, lb = res["ours"][0], res["torch"][0]
+    assert abs(float(la - lb)) / abs(float(lb)) < 1e-5
+    for n, gb in res["torch"][1].items():
+        ga = res["ours"][1][n]
+        assert float((ga - gb).norm() / gb.norm().clamp_min(1e-30)) < 1e-4, n
