@@ -174,6 +174,21 @@ def kernel_roofline(wl, device, pk, pk_kind):
         "gyroplane_fwd": (lambda: ops.gyroplane_fwd(z, Mg, bpt, None, c, FL), 4 * (B * D + 2 * H * D + B * H)),
         "gyroplane_bwd": (lambda: ops.gyroplane_bwd(z, Mg, bpt, gout, c, FL, False), 4 * (B * H + 2 * B * D + 4 * H * D)),
     }
+    # trunk dense layers: the five fp32-accurate tensor-core GEMMs of one step (enc fwd, dec fwd, dec dgrad, dec wgrad,
+    # enc wgrad), timed as GEMM launches on pre-split operands.  Algorithmic flops = 2 M N K of the fp32 product; the
+    # kernel executes 6x that in bf16 (three-way split, six piece products).
+    n_in = int(torch.Size(wl["data"]).numel())
+    gemms = [(B, H, n_in), (B, n_in, H), (B, H, n_in), (n_in, H, B), (H, n_in, B)]
+    tc_ops = []
+    for (m_, n_, k_) in gemms:
+        a_s = ops.split3(torch.randn(m_, k_, device=device, generator=g))
+        b_s = ops.split3(torch.randn(n_, k_, device=device, generator=g))
+        tc_ops.append((a_s, b_s, m_, n_, k_))
+
+    def run_gemms():
+        for a_s, b_s, m_, n_, k_ in tc_ops:
+            ops.gemm_x3s(a_s, False, b_s, False, None, False, m_, n_, k_)
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     res = {}
     for name, (fn, nbytes) in cases.items():
@@ -191,13 +206,37 @@ def kernel_roofline(wl, device, pk, pk_kind):
         ts.sort()
         t = sum(ts[2:-2]) / len(ts[2:-2])
         res[name] = {"seconds": t, "bytes": nbytes, "gbs": nbytes / t / 1e9}
+    for _ in range(3):
+        run_gemms()
+    ts = []
+    for _ in range(20):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        run_gemms()
+        e.record()
+        e.synchronize()
+        ts.append(s.elapsed_time(e) * 1e-3)
+    ts.sort()
+    t_g = sum(ts[2:-2]) / len(ts[2:-2])
+    fl = sum(2.0 * m_ * n_ * k_ for (m_, n_, k_) in gemms)
+    n_g = sum(C.lib().hvae_gemm_x3s_num_launches(m_, n_, k_) for (m_, n_, k_) in gemms)
     top = max(res, key=lambda k: res[k]["seconds"])
     r = res[top]
-    roof = {"bound": "hbm", "kernel": top, "achieved": r["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": r["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
-            "launch_us": r["seconds"] * 1e6, "algorithmic_bytes": r["bytes"],
-            "note": "cfg2 sizes (~10 MB per kernel) are launch/latency-bound; large-row rooflines in kernel_rooflines"}
+    hbm_roof = {"bound": "hbm", "kernel": top, "achieved": r["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": r["gbs"] / pk["hbm_gbs"], "launch_us": r["seconds"] * 1e6, "algorithmic_bytes": r["bytes"],
+                "note": "cfg2 sizes (~10 MB per kernel) are launch/latency-bound; large-row rooflines in kernel_rooflines"}
+    # the dominant kernel of the step is the trunk GEMM (5 launches, ~1/3 of the step): tensor-bound
+    roof = {"bound": "tensor", "kernel": "k_tc_gemm<EPI_X3> (trunk dense layers, fp32-accurate split-bf16 GEMM)",
+            "achieved": fl / t_g / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t_g / 1e12 / pk["bf16_tflops"],
+            "traffic": None, "peak_source": pk_kind, "launch_us": t_g / 5 * 1e6, "launches_per_step": n_g,
+            "algorithmic_flops_per_step": fl, "executed_bf16_tflops": 6.0 * fl / t_g / 1e12,
+            "executed_frac": 6.0 * fl / t_g / 1e12 / pk["bf16_tflops"],
+            "note": "achieved = algorithmic fp32 flops (2MNK summed over the step's five GEMMs) / their launch time; the "
+                    "kernel executes 6x as many bf16 flops (executed_*). Largest HBM-bound own kernel in hbm_kernel.",
+            "hbm_kernel": hbm_roof}
     others = {k: {"us": v["seconds"] * 1e6, "gbs": v["gbs"]} for k, v in res.items()}
+    others["trunk_gemm_x3_5launches"] = {"us": t_g * 1e6, "tflops_algorithmic": fl / t_g / 1e12}
     # large-row HBM rooflines of the row kernels (inputs >> L2)
     big = {}
     for D_ in (2, 16, 64):

@@ -65,6 +65,8 @@ struct Params {
     // k-blocks each; npairs == 0 -> one piece of ceil(K / BK) k-blocks.  splits > 1: split-K, unit (tile, s) writes
     // its partial tile to D + s * M * N.
     int npairs, kbp, splits;
+    int share;             // X3: piece-sharing schedule (K-major operands): a stage holds the hi/mid/lo tiles of A and B for one
+                           // k-position (96 KB) and the six piece products are issued from it
     int a_mn, b_mn;        // operand stored contraction-major-OUTER: buffer rows = contraction index, columns = M / N index
     int a_off[6], b_off[6];
     int relu;              // PLAIN: bias (per column, via `bias`) then optional ReLU
@@ -237,7 +239,66 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 0) {
+    // X3 piece-sharing schedule: 2 stages x 6 tiles [A hi, A mid, A lo, B hi, B mid, B lo]; shared-memory traffic per
+    // k-position drops from 6 x (32 KB fill + 32 KB operand reads) to 96 KB fill + 192 KB reads (the cta_group::1 mainloop
+    // is bound by shared-memory bandwidth: a 128x128x16 MMA reads 8 KB per 64 cycles, the SM's whole 128 B/clk)
+    constexpr uint32_t X3_STAGE_BYTES = 6 * TILE_A_BYTES;
+    auto x3_tile = [&](int stage, int t) { return base + (uint32_t)stage * X3_STAGE_BYTES + (uint32_t)t * TILE_A_BYTES; };
+    const bool share = (EPI == EPI_X3) && !ARES && prm.share;
+    const int units_k = share ? kbp : k_blocks;  // what split-K divides: k-positions or flattened (pair, k-block)
+
+    if (warp == 0 && share) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int piece = kbp * BK;  // column stride between pieces
+            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const int64_t tile = u / S;
+                const int sp = (int)(u % S);
+                const int p0 = (int)((int64_t)sp * kbp / S), p1 = (int)((int64_t)(sp + 1) * kbp / S);
+                const int m0 = (int)(tile / n_tiles) * BM, n0 = (int)(tile % n_tiles) * BN;
+                for (int kk = p0; kk < p1; ++kk) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), X3_STAGE_BYTES);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        tma_load_2d(x3_tile(stage, t), &map_a, full_bar(stage), t * piece + kk * BK, m0);
+                        tma_load_2d(x3_tile(stage, 3 + t), &map_b, full_bar(stage), t * piece + kk * BK, n0);
+                    }
+                    if (++stage == 2) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1 && share) {
+        if (lane == 0) {
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sp = (int)(u % S);
+                const int p0 = (int)((int64_t)sp * kbp / S), p1 = (int)((int64_t)(sp + 1) * kbp / S);
+                for (int kk = p0; kk < p1; ++kk) {
+                    mbar_wait(tempty_bar(as), aphase ^ 1u);   // one accumulator hand-over per k-position (24 MMAs)
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    // pieces 0 = hi, 1 = mid, 2 = lo; smallest products first
+                    constexpr int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};
+#pragma unroll
+                    for (int pr = 0; pr < 6; ++pr) {
+                        const uint64_t da = make_desc(x3_tile(stage, pa[pr])), db = make_desc(x3_tile(stage, 3 + pb[pr]));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (uint32_t)((pr | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));
+                    umma_commit(tfull_bar(as));
+                    if (++stage == 2) { stage = 0; phase ^= 1u; }
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0;
@@ -371,12 +432,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           if (EPI == EPI_X3) {
               // chunked accumulation: sum the accumulator hand-overs of this unit in registers, then finish + store
-              const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
+              const int kb0 = (int)((int64_t)sp * units_k / S), kb1 = (int)((int64_t)(sp + 1) * units_k / S);
+              const int cstep = share ? 1 : X3_CHUNK;
               float acc[2][16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) acc[0][i] = acc[1][i] = 0.0f;
               const int cb = cg * COLS;  // COLS == 32: one column chunk per warp
-              for (int c0 = kb0; c0 < kb1; c0 += X3_CHUNK) {
+              for (int c0 = kb0; c0 < kb1; c0 += cstep) {
                   mbar_wait(tfull_bar(as), aphase);
                   tc_fence_after();
                   float v[2][16];
@@ -1157,6 +1219,7 @@ extern "C" int hvae_gemm_x3s_f32(const void* As, int a_mn, const void* Bs, int b
     prm.M = M; prm.N = N; prm.K = 3 * Kp;
     prm.npairs = 6; prm.kbp = (int)(Kp / tc::BK); prm.splits = S;
     prm.a_mn = a_mn ? 1 : 0; prm.b_mn = b_mn ? 1 : 0;
+    prm.share = (!a_mn && !b_mn && !getenv("HVAE_X3_NOSHARE")) ? 1 : 0;
     const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};  // 0 = hi, 1 = mid, 2 = lo; smallest products first
     for (int i = 0; i < 6; ++i) {
         prm.a_off[i] = (int)(pa[i] * (a_mn ? Mp : Kp));
@@ -1222,6 +1285,7 @@ extern "C" int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int
     tc::Params prm{};
     prm.M = M; prm.N = N; prm.K = 3 * Kp;
     prm.npairs = 6; prm.kbp = (int)(Kp / tc::BK); prm.splits = S;
+    prm.share = getenv("HVAE_X3_NOSHARE") ? 0 : 1;
     // pieces: 0 = hi, 1 = mid, 2 = lo; smallest products first
     const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};
     for (int i = 0; i < 6; ++i) { prm.a_off[i] = (int)(pa[i] * Kp); prm.b_off[i] = (int)(pb[i] * Kp); }

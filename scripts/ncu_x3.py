@@ -1,0 +1,19 @@
+"""Tiny driver for the ncu capture of the trunk GEMM (k_tc_gemm<EPI_X3>): the five GEMMs of one config-2 step on
+pre-split operands, twice (the second round is the one to capture: --launch-skip = launches of round one)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "hyperbolic-vae_b200")):
+    sys.path.insert(0, p)
+import torch
+from hvae import ops
+
+dev = torch.device("cuda")
+B, H, n_in = 4096, 600, 784
+g = torch.Generator(device=dev).manual_seed(0)
+gemms = [(B, H, n_in), (B, n_in, H), (B, H, n_in), (n_in, H, B), (H, n_in, B)]
+tc_ops = [(ops.split3(torch.randn(m, k, device=dev, generator=g)), ops.split3(torch.randn(n, k, device=dev, generator=g)), m, n, k) for m, n, k in gemms]
+for _ in range(2):
+    for a, b, m, n, k in tc_ops:
+        out = ops.gemm_x3s(a, False, b, False, None, False, m, n, k)
+torch.cuda.synchronize()
+print("ok", float(out.abs().mean()))
