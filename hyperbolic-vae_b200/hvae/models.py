@@ -276,6 +276,25 @@ class PvaeMnist(nn.Module):
         self._pz_mu = nn.Parameter(torch.zeros(1, latent_dim), requires_grad=False)
         self._pz_logvar = nn.Parameter(torch.zeros(1, 1), requires_grad=False)
 
+    def _prior(self):
+        """RiemannianNormal(0, softplus(logvar)/ln2 * prior_std).  The reference rebuilds it (softplus + the float64
+        normaliser series) every step; its parameters are frozen (requires_grad=False), so the built object is cached
+        and rebuilt only when they change (tensor version counters) or start requiring grad."""
+        from .distributions.riemannian_normal import RiemannianNormal
+
+        lv, mu = self._pz_logvar, self._pz_mu
+        frozen = not (lv.requires_grad or mu.requires_grad)
+        key = (lv._version, mu._version, lv.data_ptr(), mu.data_ptr(), self.prior_std)
+        cache = getattr(self, "_prior_cache", None)
+        if frozen and cache is not None and cache[0] == key:
+            return cache[1]
+        with torch.set_grad_enabled(not frozen):
+            p = RiemannianNormal(mu, F.softplus(lv) / math.log(2) * self.prior_std, self.manifold)
+        capturing = lv.is_cuda and torch.cuda.is_current_stream_capturing()
+        if frozen and not capturing:
+            self._prior_cache = (key, p)
+        return p
+
     def encode(self, x):
         e = self.enc(x.view(x.shape[0], -1))
         mu = self.manifold.expmap0(self.fc21(e))
@@ -296,8 +315,7 @@ class PvaeMnist(nn.Module):
             lpx_z = -ops.bernoulli_nll_rows(logits, x.view(B, -1))  # one row kernel per direction
         else:
             lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
-        pz_scale = F.softplus(self._pz_logvar) / math.log(2) * self.prior_std
-        p = RiemannianNormal(self._pz_mu, pz_scale, self.manifold)
+        p = self._prior()
         if self.fused:
             kld = q.kl_mc(zs, p)  # one kernel: both log-densities and their difference
         else:

@@ -1060,6 +1060,23 @@ def _(As, a_mn, Bs, b_mn, bias, relu, M, N, K):
     return torch.empty(M, N, dtype=torch.float32, device=As.device)
 
 
+@_op("hvae::colsum", mutates_args=())
+def colsum(x: Tensor) -> Tensor:
+    """(R, C) -> (C,) column sums (a dense layer's bias gradient); deterministic two-pass kernel."""
+    C.require_cuda(x)
+    R, Cn = x.shape
+    out = x.new_empty(Cn)
+    ws = _workspace(C.lib().hvae_colsum_workspace_bytes(Cn), x.device)
+    C.call("hvae_colsum_f32", C.ptr(x), C.ptr(out), R, Cn, C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += 2
+    return out
+
+
+@colsum.register_fake
+def _(x):
+    return x.new_empty(x.shape[1])
+
+
 @_op("hvae::linear_x3", mutates_args=())
 def linear_x3_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     return gemm_x3(x, False, weight, False, bias, False)
@@ -1088,7 +1105,7 @@ def _lx3_backward(ctx, gy):
     if ctx.needs_input_grad[1]:
         gw = gemm_x3(gy, True, x, True, None, False)         # (out, in) = gy^T (out, M) . x (M, in): contraction over M
     if ctx.has_bias and ctx.needs_input_grad[2]:
-        gb = gy.sum(0)
+        gb = colsum(gy)
     return gx, gw, gb
 
 

@@ -183,6 +183,11 @@ int hvae_bce_logits_rows_fwd_f32(const float* logits, const float* x, float* nll
 int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const float* gnll, float* glogits, int64_t S,
                                  int64_t B, int64_t N, void* stream);
 
+/* column sums of a row-major (R, C) matrix: the bias gradient of a dense layer (autograd of nn.Linear's bias). */
+size_t hvae_colsum_workspace_bytes(int64_t C);
+int hvae_colsum_f32(const float* x, float* out, int64_t R, int64_t C, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* ---- fp32-accurate dense GEMM on the tensor cores: the Euclidean trunk layers either side of the hyperbolic path
  * (reference: nn.Linear in hyperbolic_vae/models/vae_hyperbolic_*.py encoders/decoders and pvae Enc/Dec).
  *   C (M,N) = opA (M,K) . opB (N,K)^T  (+ bias[n]) (ReLU)

@@ -165,3 +165,14 @@ def test_cfg2_step_fused_heads_match_torch_heads():
     for n, gb in res["torch"][1].items():
         ga = res["ours"][1][n]
         assert float((ga - gb).norm() / gb.norm().clamp_min(1e-30)) < 1e-4, n
+
+
+@pytest.mark.parametrize("R,C", [(4096, 784), (1000, 77), (5, 3), (33, 600)])
+def test_colsum(R, C):
+    from hvae import ops
+
+    torch.manual_seed(R + C)
+    x = torch.randn(R, C, device="cuda")
+    ref = x.double().sum(0)
+    out = ops.colsum(x)
+    assert float((out.double() - ref).abs().max()) < 1e-5 * float(x.double().abs().sum(0).max())
