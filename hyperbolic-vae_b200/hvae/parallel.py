@@ -14,6 +14,7 @@ is issued from a gradient hook on a side stream and runs under the remaining bac
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List
 
 import torch
@@ -24,8 +25,11 @@ class FlatGradBucket:
     """Owns one contiguous buffer; every parameter's .grad is a view into it, so backward writes straight
     into the bucket and the all-reduce needs no gather/scatter copies."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], early: Iterable[torch.nn.Parameter] = ()):
-        """early: parameters to place first in the buffer (one contiguous segment [0, split))."""
+    def __init__(self, params: Iterable[torch.nn.Parameter], early: Iterable[torch.nn.Parameter] = (), symmetric: bool = None):
+        """early: parameters to place first in the buffer (one contiguous segment [0, split)).
+        symmetric: allocate the buffer in symmetric (peer-addressable) memory and all-reduce it with the repo's own
+        NVLink kernel (hvae_allreduce_p2p_f32) instead of NCCL.  Default: on for CUDA buckets of an initialised
+        multi-rank NCCL job unless HVAE_DP_P2P=0; construction is then a collective call (every rank, same order)."""
         ps = [p for p in params if p.requires_grad]
         if not ps:
             raise ValueError("no trainable parameters")
@@ -42,9 +46,41 @@ class FlatGradBucket:
             self.offsets.append(total)
             total += (p.numel() + 31) // 32 * 32  # keep every view 128-byte aligned
         self.split = self.offsets[self.n_early] if 0 < self.n_early < len(self.params) else 0
-        self.buffer = torch.zeros(total, device=dev, dtype=dt)
+        if symmetric is None:
+            symmetric = (dev.type == "cuda" and dt == torch.float32 and self._active() and dist.get_backend() == "nccl"
+                         and os.environ.get("HVAE_DP_P2P", "1") != "0")
+        self._symm = None
+        if symmetric:
+            self.buffer, self._symm = self._alloc_symmetric(total, dev)
+        if self._symm is None:
+            self.buffer = torch.zeros(total, device=dev, dtype=dt)
         for p, off in zip(self.params, self.offsets):
             p.grad = self.buffer[off:off + p.numel()].view_as(p)
+
+    @staticmethod
+    def _alloc_symmetric(total: int, dev):
+        """-> (buffer, handle) in torch symmetric memory, or (None, None) when peers cannot map each other."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            from . import _cabi as C
+
+            need = 4 * (64 + 2 * C.lib().hvae_allreduce_p2p_slots(dist.get_world_size()))
+            if symm.get_signal_pad_size() < need:
+                symm.set_signal_pad_size(need)
+            buf = symm.empty(total, dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            buf.zero_()
+            ok = torch.ones(1, device=dev)
+        except Exception as ex:  # no P2P mapping on this node: fall back to NCCL on every rank together
+            import sys
+
+            sys.stderr.write("hvae.parallel: symmetric memory unavailable (%s); using NCCL\n" % (str(ex).splitlines()[0],))
+            buf, hdl, ok = None, None, torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same path
+        if float(ok) < 1.0:
+            return None, None
+        return buf, hdl
 
     def zero_(self):
         self.buffer.zero_()
@@ -66,15 +102,33 @@ class FlatGradBucket:
         """SUM (or AVG) all-reduce of the 'early' ([0, split)) or 'late' ([split, end)) segment on the current stream."""
         if not self._active(group):
             return
-        seg = self.buffer[:self.split] if which == "early" else self.buffer[self.split:]
-        if seg.numel() == 0:
+        lo, hi = (0, self.split) if which == "early" else (self.split, self.buffer.numel())
+        if hi <= lo:
             return
+        if self._symm is not None:
+            self._p2p(lo, hi - lo, 0 if which == "early" else 1, average)
+            return
+        seg = self.buffer[lo:hi]
         dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=group)
         if average:
             seg.div_(dist.get_world_size(group))
 
+    def _p2p(self, offset: int, n: int, site: int, average: bool):
+        """The repo's own all-reduce kernel over NVLink peer memory (csrc/allreduce_p2p.cu) on the current stream.
+        site: which of the two disjoint signal-pad slot ranges to use (calls that may overlap in time need their own)."""
+        from . import _cabi as C
+
+        h = self._symm
+        W = h.world_size
+        base = 64 + site * C.lib().hvae_allreduce_p2p_slots(W)
+        C.call("hvae_allreduce_p2p_f32", h.buffer_ptrs_dev, h.signal_pad_ptrs_dev, h.rank, W, offset, n, base,
+               1.0 / W if average else 1.0, C.stream())
+
     def all_reduce(self, average: bool, group=None, async_op: bool = False):
         if not self._active(group):
+            return None
+        if self._symm is not None:
+            self._p2p(0, self.buffer.numel(), 1, average)
             return None
         work = dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if average:

@@ -26,8 +26,12 @@ class TrainStep:
         self._hooks, self._order, self._fired = [], [], 0
         self._side = torch.cuda.Stream()
         self._early_launched = False
+        # NCCL path: overlap the early gradient segment's collective with the rest of the backward.  With the bucket in
+        # symmetric memory the exchange is ONE peer-memory kernel at the end of the step instead (measured at 2 GPUs:
+        # 674 us/step against 693 us for overlapped NCCL and 712 us for a single NCCL all-reduce; 636 us without any
+        # exchange) - its barriers spin, so it is not run concurrently with compute.
         self.overlap = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-                        and os.environ.get("HVAE_DP_OVERLAP", "1") != "0")
+                        and self.bucket._symm is None and os.environ.get("HVAE_DP_OVERLAP", "1") != "0")
         self.x = torch.empty_like(example_input)  # static input buffer (device)
         self.x.copy_(example_input)
         self._stage = torch.empty_like(example_input)  # landing buffer of the asynchronous host->device prefetch
@@ -66,7 +70,7 @@ class TrainStep:
         if not early or acc > 0.9 * total:
             self.overlap = False
             return
-        self.bucket = FlatGradBucket(self.bucket.params, early=early)
+        self.bucket = FlatGradBucket(self.bucket.params, early=early)  # (a collective when the bucket is symmetric)
         self._n_early = len(early)
 
         def hook(_p):

@@ -183,6 +183,15 @@ int hvae_bce_logits_rows_fwd_f32(const float* logits, const float* x, float* nll
 int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const float* gnll, float* glogits, int64_t S,
                                  int64_t B, int64_t N, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (the reference is single-device:
+ * training/trainer_mnist.py:19).  buf_ptrs_dev / pad_ptrs_dev: DEVICE arrays of `world` pointers - every rank's copy of
+ * the flat gradient bucket and of a zero-initialised uint32 signal pad, as mapped into THIS rank's address space
+ * (symmetric memory).  Sums elements [offset, offset+n) across ranks in place (fixed rank order: identical bits on all
+ * ranks), scaled by `scale`; one kernel per rank, barriers on the pad slots [pad_slot_base, + hvae_allreduce_p2p_slots). */
+int hvae_allreduce_p2p_slots(int world);
+int hvae_allreduce_p2p_f32(const void* buf_ptrs_dev, const void* pad_ptrs_dev, int rank, int world, int64_t offset,
+                           int64_t n, int pad_slot_base, float scale, void* stream);
+
 /* column sums of a row-major (R, C) matrix: the bias gradient of a dense layer (autograd of nn.Linear's bias). */
 size_t hvae_colsum_workspace_bytes(int64_t C);
 int hvae_colsum_f32(const float* x, float* out, int64_t R, int64_t C, void* workspace, size_t workspace_bytes,
