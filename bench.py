@@ -146,6 +146,14 @@ def build_model(wl, device):
     return m
 
 
+def x3_traffic():
+    """DRAM bytes per launch of the trunk GEMM from the committed ncu --set full capture (mean of the five launches)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_x3_traffic.json")))["traffic_bytes_per_launch_mean"]
+    except Exception:
+        return None
+
+
 def kernel_roofline(wl, device, pk, pk_kind):
     """Time each own kernel of the cfg2 step alone (CUDA events per launch, L2 flushed between launches) and
     report the dominant one against the HBM roofline.  Algorithmic bytes per SURVEY.md §8(d)."""
@@ -232,7 +240,7 @@ def kernel_roofline(wl, device, pk, pk_kind):
     roof = {"bound": "tensor", "kernel": "k_tc_gemm<EPI_X3> (trunk dense layers, fp32-accurate split-bf16 GEMM)",
             "achieved": 6.0 * fl / t_g / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": 6.0 * fl / t_g / 1e12 / pk["bf16_tflops"],
-            "traffic": None, "peak_source": pk_kind, "launch_us": t_g / 5 * 1e6, "launches_per_step": n_g,
+            "traffic": x3_traffic(), "peak_source": pk_kind, "launch_us": t_g / 5 * 1e6, "launches_per_step": n_g,
             "algorithmic_flops_per_step": 6.0 * fl, "fp32_equivalent_tflops": fl / t_g / 1e12,
             "note": "achieved = bf16 tensor flops of the split algorithm (3 pieces per operand, 6 piece products = 6 x 2MNK, "
                     "summed over the step's five GEMMs) / their launch time, L2 flushed between repetitions; "
