@@ -895,6 +895,59 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
     }
 }
 
+// ---- gyroplane backward on the tensor cores (a == p) ------------------------------------------------------------------
+// Pair gradients over a (64 rows x 256 planes) tile, thread = plane: from px = <x_b, p_j> (recomputed by a GEMM), |x_b|^2,
+// |p_j|^2 and the upstream g it forms
+//   CP[b][j] = dL/d<x_b,p_j>  (bf16, operand of the two backward GEMMs),
+//   rowpart[cb][b] = sum_j dL/d|x_b|^2  over this tile's planes,     colpart[rb][j] = sum_b (2 dL/d|p_j|^2 + dL/d|p_j| / |p_j|)
+// so that  gx = CP P + 2 rowsum x   and   gp = CP^T x + colsum p   (same algebra as the SIMT path, gyroplane.cu).
+constexpr int kGbCols = 256, kGbRows = 64;
+__global__ void __launch_bounds__(kGbCols)
+k_gyro_tc_bwd_pairs(const float* __restrict__ px, const float* __restrict__ g, const float* __restrict__ x2,
+                    const float* __restrict__ p2, __nv_bfloat16* __restrict__ CP, float* __restrict__ rowpart,
+                    float* __restrict__ colpart, int64_t B, int64_t P, GyroParams prm) {
+    __shared__ float rs[kGbCols / 32][kGbRows];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t j = (int64_t)blockIdx.y * kGbCols + tid;   // row blocks on grid.x (can exceed 65535), plane blocks on grid.y
+    const int64_t b0 = (int64_t)blockIdx.x * kGbRows;
+    const bool jok = j < P;
+    const float p2j = jok ? __ldg(p2 + j) : 0.0f;
+    const float pn = sqrtf(p2j);
+    const float rpn = pn > 0.0f ? 1.0f / pn : 0.0f;
+    float colacc = 0.0f;
+    for (int r = 0; r < kGbRows; ++r) {
+        const int64_t b = b0 + r;
+        float dx2 = 0.0f;
+        if (jok && b < B) {
+            const float pxv = __ldg(px + b * P + j), gv = __ldg(g + b * P + j), x2v = __ldg(x2 + b);
+            GyroPairCtx k;
+            gyro_pair_fwd(pxv, pxv, x2v, p2j, p2j, pn, prm, k);
+            const GyroPairGrad gr = gyro_pair_bwd(gv, pxv, pxv, x2v, p2j, p2j, pn, prm, k);
+            CP[b * P + j] = __float2bfloat16_rn(gr.dpx + gr.dxa);
+            dx2 = gr.dx2;
+            colacc += 2.0f * (gr.dp2 + gr.dpa) + gr.dan * rpn;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+        if (lane == 0) rs[warp][r] = dx2;
+    }
+    __syncthreads();
+    if (tid < kGbRows && b0 + tid < B) {
+        float a = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kGbCols / 32; ++w) a += rs[w][tid];
+        rowpart[(int64_t)blockIdx.y * B + b0 + tid] = a;
+    }
+    if (jok) colpart[(int64_t)blockIdx.x * P + j] = colacc;
+}
+__global__ void k_gyro_tc_rowcoef(const float* __restrict__ rowpart, float* __restrict__ rowcoef, int64_t B, int nblk) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float a = 0.0f;
+    for (int i = 0; i < nblk; ++i) a += rowpart[(int64_t)i * B + b];
+    rowcoef[b] = 2.0f * a;
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1299,5 +1352,114 @@ extern "C" int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int
     const int64_t n = M * N;
     const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
     tc::k_splitk_reduce<<<grid, 256, 0, s>>>(part, bias, C, M, N, S, relu);
+    return check_launch();
+}
+
+// ---- gyroplane backward (a == p) on the tensor cores ------------------------------------------------------------------
+namespace hvae { namespace tc {
+struct WsGb { size_t a16, b16, x2, p2, px, cp, cpt, pt16, xt16, rowpart, colpart, rowcoef, colcoef, csws, total; };
+static WsGb ws_gb_layout(int64_t B, int64_t D, int64_t P) {
+    WsGb w;
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return at; };
+    w.a16 = take((size_t)B * D * 2);
+    w.b16 = take((size_t)P * D * 2);
+    w.x2 = take((size_t)B * 4);
+    w.p2 = take((size_t)P * 4);
+    w.px = take((size_t)B * P * 4);
+    w.cp = take((size_t)B * P * 2);
+    w.cpt = take((size_t)B * P * 2);
+    w.pt16 = take((size_t)D * P * 2);
+    w.xt16 = take((size_t)D * B * 2);
+    w.rowpart = take((size_t)((P + kGbCols - 1) / kGbCols) * B * 4);
+    w.colpart = take((size_t)((B + kGbRows - 1) / kGbRows) * P * 4);
+    w.rowcoef = take((size_t)B * 4);
+    w.colcoef = take((size_t)P * 4);
+    w.csws = take(hvae_colsum_workspace_bytes(P));
+    w.total = o;
+    return w;
+}
+}}  // namespace hvae::tc
+
+extern "C" size_t hvae_gyroplane_tc_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P) {
+    if (B <= 0 || D <= 0 || P <= 0) return 0;
+    return tc::ws_gb_layout(B, D, P).total;
+}
+
+// gx (B,D), gp (P,D) of out = gyroplane(x, p, a = p) given gout (B,P); bf16 tensor-core GEMMs, fp32 pair math.
+//   px = x p^T (GEMM)  ->  pair gradients (CP bf16, row / column scalar sums)  ->  gx = CP p + rowcoef x (GEMM over P)
+//   ->  gp = CP^T x + colcoef p (GEMM over B).  B, D, P multiples of 8.
+extern "C" int hvae_gyroplane_tc_bwd_f32(const float* x, const float* p, const float* gout, float* gx, float* gp, int64_t B,
+                                         int64_t D, int64_t P, float c, uint32_t flags, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    if (B <= 0 || D <= 0 || P <= 0 || (B % 8) || (D % 8) || (P % 8)) return HVAE_ESHAPE;
+    if (!x || !p || !gout || !workspace || (!gx && !gp)) return HVAE_EARG;
+    const tc::WsGb L = tc::ws_gb_layout(B, D, P);
+    if (workspace_bytes < L.total) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* a16 = (__nv_bfloat16*)(ws + L.a16);
+    auto* b16 = (__nv_bfloat16*)(ws + L.b16);
+    float* x2 = (float*)(ws + L.x2);
+    float* p2 = (float*)(ws + L.p2);
+    float* px = (float*)(ws + L.px);
+    auto* cp = (__nv_bfloat16*)(ws + L.cp);
+    auto* cpt = (__nv_bfloat16*)(ws + L.cpt);
+    auto* pt16 = (__nv_bfloat16*)(ws + L.pt16);
+    auto* xt16 = (__nv_bfloat16*)(ws + L.xt16);
+    float* rowpart = (float*)(ws + L.rowpart);
+    float* colpart = (float*)(ws + L.colpart);
+    float* rowcoef = (float*)(ws + L.rowcoef);
+    float* colcoef = (float*)(ws + L.colcoef);
+    const unsigned pgrid = (unsigned)((P + 7) / 8 < 1 ? 1 : (P + 7) / 8);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, a16, x2, B, D);
+    tc::k_rows_to_bf16<<<pgrid, 256, 0, s>>>(p, b16, p2, P, D);
+    int rc;
+    {   // px = x p^T
+        tc::Params prm{};
+        prm.D = px; prm.M = B; prm.N = P; prm.K = D;
+        rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
+        if (rc != HVAE_OK) return rc;
+    }
+    const int ncb = (int)((P + tc::kGbCols - 1) / tc::kGbCols);
+    const int64_t nrb = (B + tc::kGbRows - 1) / tc::kGbRows;
+    GyroParams gprm;
+    {
+        const Ball bl = make_ball(c);
+        gprm.c = bl.c; gprm.sc = bl.sc; gprm.rsc = bl.rsc; gprm.maxnorm = bl.maxnorm; gprm.flags = flags;
+    }
+    {
+        if (nrb > 0x7fffffffLL || ncb > 65535) return HVAE_ESHAPE;
+        dim3 grid((unsigned)nrb, (unsigned)ncb);
+        tc::k_gyro_tc_bwd_pairs<<<grid, tc::kGbCols, 0, s>>>(px, gout, x2, p2, cp, rowpart, colpart, B, P, gprm);
+        rc = check_launch();
+        if (rc != HVAE_OK) return rc;
+    }
+    if (gx) {
+        tc::k_gyro_tc_rowcoef<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(rowpart, rowcoef, B, ncb);
+        dim3 grid((unsigned)((P + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+        tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(p, pt16, (int)P, (int)D);  // (P, D) -> (D, P)
+        tc::Params prm{};
+        prm.D = gx; prm.M = B; prm.N = D; prm.K = P; prm.axpy_x = x; prm.axpy_coef = rowcoef;
+        rc = tc::launch_gemm<tc::EPI_PLAIN>(cp, pt16, prm, s);
+        if (rc != HVAE_OK) return rc;
+    }
+    if (gp) {
+        if (B > 0x7fffffffLL) return HVAE_ESHAPE;
+        rc = hvae_colsum_f32(colpart, colcoef, nrb, P, ws + L.csws, hvae_colsum_workspace_bytes(P), stream);
+        if (rc != HVAE_OK) return rc;
+        {
+            dim3 grid((unsigned)((B + 63) / 64), (unsigned)((P + 63) / 64));
+            tc::k_transpose_bf16<<<grid, 256, 0, s>>>(cp, cpt, B, P);  // (B, P) -> (P, B)
+        }
+        {
+            dim3 grid((unsigned)((B + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+            tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(x, xt16, (int)B, (int)D);  // (B, D) -> (D, B)
+        }
+        tc::Params prm{};
+        prm.D = gp; prm.M = P; prm.N = D; prm.K = B; prm.axpy_x = p; prm.axpy_coef = colcoef;
+        rc = tc::launch_gemm<tc::EPI_PLAIN>(cpt, xt16, prm, s);
+        if (rc != HVAE_OK) return rc;
+    }
     return check_launch();
 }

@@ -915,11 +915,36 @@ def _gtc_setup(ctx, inputs, output):
     ctx.has_bias, ctx.c, ctx.flags = bias is not None, c, flags
 
 
+@_op("hvae::gyroplane_tc_bwd", mutates_args=())
+def gyroplane_tc_bwd(x: Tensor, p: Tensor, g: Tensor, c: float, flags: int) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(x, p, g)
+    B, D = x.shape
+    P = p.shape[0]
+    gx, gp = torch.empty_like(x), torch.empty_like(p)
+    ws = _workspace(C.lib().hvae_gyroplane_tc_bwd_workspace_bytes(B, D, P), x.device)
+    C.call("hvae_gyroplane_tc_bwd_f32", C.ptr(x), C.ptr(p), C.ptr(g), C.ptr(gx), C.ptr(gp), B, D, P, c, flags, C.ptr(ws),
+           ws.numel(), C.stream())
+    C.launch_count += 11
+    return gx, gp
+
+
+@gyroplane_tc_bwd.register_fake
+def _(x, p, g, c, flags):
+    return torch.empty_like(x), torch.empty_like(p)
+
+
 def _gtc_backward(ctx, g):
     x, p = ctx.saved_tensors
-    if x.shape[1] > 64:
-        raise NotImplementedError("gyroplane backward for D > 64 (tensor-core shapes) is not implemented yet")
-    gx, gp, _, gb = gyroplane_bwd(x, p, None, _c(g), ctx.c, ctx.flags, ctx.has_bias)
+    g = _c(g)
+    B, D = x.shape
+    P = p.shape[0]
+    if B % 8 == 0 and D % 8 == 0 and P % 8 == 0:
+        gx, gp = gyroplane_tc_bwd(x, p, g, ctx.c, ctx.flags)          # tensor cores
+        gb = colsum(g) if ctx.has_bias else None
+        return gx, gp, gb, None, None
+    if D > 64:
+        raise NotImplementedError("gyroplane backward for D > 64 needs B, D, P to be multiples of 8 (tensor-core path)")
+    gx, gp, _, gb = gyroplane_bwd(x, p, None, g, ctx.c, ctx.flags, ctx.has_bias)
     return gx, gp, (gb if ctx.has_bias else None), None, None
 
 

@@ -174,6 +174,14 @@ int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, const float* y
                                   size_t workspace_bytes, void* stream);
 int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
                               int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+/* backward of the above (a == p): px = x p^T is recomputed by a GEMM, a tile kernel forms the pair gradients
+ * (bf16 coefficient matrix + row / column scalar sums), then gx = CP p + rowcoef x and gp = CP^T x + colcoef p are two
+ * more GEMMs with the axpy fused into their epilogues.  B, D, P multiples of 8; gx or gp may be NULL.  The bias
+ * gradient is the column sum of gout (hvae_colsum_f32). */
+size_t hvae_gyroplane_tc_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P);
+int hvae_gyroplane_tc_bwd_f32(const float* x, const float* p, const float* gout, float* gx, float* gp, int64_t B,
+                              int64_t D, int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 /* ---- reconstruction-loss head: Bernoulli NLL with logits, summed over the feature axis (reference:
  * Bernoulli(logits).log_prob(x).sum(-1) in training/old_pvae_train.py:53-58; F.binary_cross_entropy_with_logits in

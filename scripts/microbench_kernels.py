@@ -62,6 +62,11 @@ def main():
                                 "note": "row pass (bf16 gmx) + bf16 transpose + 2 GEMMs (gx over P with fused axpy, gM over B)"}
         del y, gy
         t = timeit(lambda: ops.gyroplane_tc_fwd(x, pts, None, c, ops.GYRO_SIGNED))
+        og = torch.randn(B, P, device=dev, generator=g)
+        tb = timeit(lambda: ops.gyroplane_tc_bwd(x, pts, og, c, ops.GYRO_SIGNED))
+        out["gyroplane_tc_bwd"] = {"B": B, "D": F, "P": P, "ms": tb * 1e3, "tflops": 3 * fl / tb / 1e12, "frac_tensor": 3 * fl / tb / 1e12 / pk["bf16_tflops"],
+                                   "note": "recompute GEMM + pair-gradient tile kernel + bf16 transpose + 2 GEMMs (3 x 2BDP flop)"}
+        del og
         out["gyroplane_tc_fwd"] = {"B": B, "D": F, "P": P, "ms": t * 1e3, "tflops": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / pk["bf16_tflops"],
                                    "alg_bytes": 4 * (B * F + 2 * P * F + B * P), "gbs_alg": 4 * (B * F + 2 * P * F + B * P) / t / 1e9,
                                    "frac_hbm": 4 * (B * F + 2 * P * F + B * P) / t / 1e9 / pk["hbm_gbs"]}

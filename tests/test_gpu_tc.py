@@ -130,3 +130,39 @@ def test_layer_dispatches_to_tc_in_bf16_mode():
     finally:
         ops.set_gemm_mode("fp32")
     assert (y16 - y32).abs().max() < 1e-2 * y32.abs().max() + 1e-4
+
+
+# gyroplane backward on the tensor cores (recompute GEMM + pair-gradient tile kernel + two GEMMs) against float64
+# autograd of the oracle; bf16 operands -> errors relative to each gradient's row / tensor scale
+@pytest.mark.parametrize("B,D,P,with_bias", [(256, 128, 256, True), (1024, 512, 384, False), (2048, 256, 1000, True), (4096, 64, 640, False)])
+def test_gyroplane_tc_backward(B, D, P, with_bias):
+    import hvae
+    from hvae import ops
+    from oracle.geoopt_min.manifolds.stereographic import math as gm
+
+    torch.manual_seed(B + D + P)
+    c = 1.0
+    ob = _oball(c)
+    x = ob.expmap0(torch.randn(B, D) * 0.6 / D ** 0.5).detach()
+    p = ob.expmap0(torch.randn(P, D) * 0.6 / D ** 0.5).detach()
+    bias = torch.randn(P) if with_bias else None
+    g = torch.randn(B, P)
+    k = torch.tensor(-c, dtype=torch.float64)
+    xd, pd = x.double().requires_grad_(True), p.double().requires_grad_(True)
+    bd = bias.double().requires_grad_(True) if with_bias else None
+    with gm.fp32_semantics():
+        ref = gm.dist2plane(xd.unsqueeze(-1), pd.t(), pd.t(), k=k, signed=True, dim=-2)
+    if with_bias:
+        ref = ref + bd
+    ref.backward(g.double())
+    xc, pc = x.cuda().requires_grad_(True), p.cuda().requires_grad_(True)
+    bc = bias.cuda().requires_grad_(True) if with_bias else None
+    out = ops.gyroplane_tc_fwd(xc, pc, bc, hvae.PoincareBall(c).c_value, ops.GYRO_SIGNED)
+    out.backward(g.cuda())
+    torch.cuda.synchronize()
+    ex = (xc.grad.double().cpu() - xd.grad).norm(dim=-1) / xd.grad.norm(dim=-1).clamp_min(1e-12)
+    assert float(ex.max()) < 3e-2 and float(ex.mean()) < 1e-2, (float(ex.max()), float(ex.mean()))
+    ep = (pc.grad.double().cpu() - pd.grad).norm(dim=-1) / pd.grad.norm(dim=-1).clamp_min(1e-12)
+    assert float(ep.max()) < 3e-2 and float(ep.mean()) < 1e-2, (float(ep.max()), float(ep.mean()))
+    if with_bias:
+        assert float((bc.grad.double().cpu() - bd.grad).abs().max() / bd.grad.abs().max()) < 1e-5
