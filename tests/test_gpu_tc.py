@@ -166,3 +166,38 @@ def test_gyroplane_tc_backward(B, D, P, with_bias):
     assert float(ep.max()) < 3e-2 and float(ep.mean()) < 1e-2, (float(ep.max()), float(ep.mean()))
     if with_bias:
         assert float((bc.grad.double().cpu() - bd.grad).abs().max() / bd.grad.abs().max()) < 1e-5
+
+
+def test_layers_train_in_bf16_mode():
+    """MobiusLayer -> expmap0 -> gyroplane decoder (geoopt's Distance2PoincareHyperplanes, a == p) at tensor-core sizes: forward AND backward run on the tcgen05 paths in
+    bf16 mode and agree with the fp32 SIMT/fp32 paths to bf16 accuracy (gradients relative to their own norm)."""
+    import hvae
+    from hvae import _cabi, layers, ops
+
+    torch.manual_seed(3)
+    ball = hvae.PoincareBall(1.0)
+    enc = layers.MobiusLayer(512, 64, ball).cuda()
+    dec = layers.Distance2PoincareHyperplanes(64, 256, ball=ball, std=0.3).cuda()
+    x = (torch.randn(1024, 512, device="cuda") * 0.03).requires_grad_(True)
+    g = torch.randn(1024, 256, device="cuda")
+    res = {}
+    for mode in ("fp32", "bf16"):
+        ops.set_gemm_mode(mode)
+        try:
+            for m in (enc, dec):
+                m.zero_grad(set_to_none=True)
+            x.grad = None
+            out = dec(ball.expmap0(enc(x)))
+            out.backward(g)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_gemm_mode("fp32")
+        res[mode] = {"out": out.detach().clone(), "x": x.grad.clone()}
+        for tag, m in (("enc", enc), ("dec", dec)):
+            for n, p in m.named_parameters():
+                if p.grad is not None:
+                    res[mode][tag + "." + n] = p.grad.clone()
+    assert set(res["bf16"]) == set(res["fp32"]) and "enc._weight" in res["fp32"] and "dec.points" in res["fp32"]
+    for n, b in res["fp32"].items():
+        a = res["bf16"][n]
+        assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 2e-2, n
