@@ -85,6 +85,27 @@ class FlatGradBucket:
     def zero_(self):
         self.buffer.zero_()
 
+    def release(self):
+        """Detach .grad from the bucket before a backward: autograd then hands each gradient tensor over as is (no
+        `grad += g` kernel per parameter); adopt() copies them into the bucket afterwards in one multi-tensor copy."""
+        for p in self.params:
+            p.grad = None
+
+    def adopt(self, lo: int = 0, hi: int = None):
+        """Copy the gradients autograd produced for params[lo:hi] into their bucket views (one fused multi-tensor copy)
+        and point .grad back at the views.  Parameters without a gradient keep their (zeroed) view."""
+        hi = len(self.params) if hi is None else hi
+        src, dst = [], []
+        for p, off in zip(self.params[lo:hi], self.offsets[lo:hi]):
+            view = self.buffer[off:off + p.numel()].view_as(p)
+            g = p.grad
+            if g is not None and g.data_ptr() != view.data_ptr():
+                src.append(g if g.is_contiguous() else g.contiguous())
+                dst.append(view)
+            p.grad = view
+        if src:
+            torch._foreach_copy_(dst, src)
+
     def rebind(self):
         """Re-point .grad at the bucket (e.g. after an optimizer did set_to_none)."""
         for p, off in zip(self.params, self.offsets):

@@ -77,6 +77,7 @@ class TrainStep:
             self._fired += 1
             if self._fired == self._n_early:
                 cur = torch.cuda.current_stream()
+                self.bucket.adopt(0, self._n_early)
                 self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):
                     self.bucket.all_reduce_segment("early", self.average)
@@ -85,16 +86,22 @@ class TrainStep:
         self._hooks = [p.register_post_accumulate_grad_hook(hook) for p in early]
 
     def _step(self):
+        # .grad is detached from the bucket during the backward (autograd hands gradients over without an add kernel per
+        # parameter) and adopted back with one multi-tensor copy; after the step .grad is the (reduced) bucket view.
         self.bucket.zero_()
+        self.bucket.release()
         self._fired, self._early_launched = 0, False
         out = self.model.loss(self.x, **self.loss_kwargs)
         out[self.loss_key].backward()
         if self.overlap:
             if not self._early_launched:  # (a parameter without gradient this step): reduce it here instead
+                self.bucket.adopt(0, self.bucket.n_early)
                 self.bucket.all_reduce_segment("early", self.average)
+            self.bucket.adopt(self.bucket.n_early, None)
             self.bucket.all_reduce_segment("late", self.average)
             torch.cuda.current_stream().wait_stream(self._side)
         else:
+            self.bucket.adopt()
             self.bucket.all_reduce(average=self.average)
         return out[self.loss_key].detach()
 
