@@ -457,6 +457,7 @@ extern "C" int hvae_gyroplane_fwd_f32(const float* x, const float* p, const floa
     cudaStream_t s = (cudaStream_t)stream;
     if (D <= 4) return gyro_fwd_launch<4>(x, p, a, bias, out, B, D, P, prm, s);
     if (D <= 8) return gyro_fwd_launch<8>(x, p, a, bias, out, B, D, P, prm, s);
+    if (D <= 12) return gyro_fwd_launch<12>(x, p, a, bias, out, B, D, P, prm, s);  // latent 10 (config 2): 25 % less padding than 16
     if (D <= 16) return gyro_fwd_launch<16>(x, p, a, bias, out, B, D, P, prm, s);
     if (D <= 32) return gyro_fwd_launch<32>(x, p, a, bias, out, B, D, P, prm, s);
     return gyro_fwd_launch<64>(x, p, a, bias, out, B, D, P, prm, s);
@@ -481,6 +482,7 @@ extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const floa
     float* ws = (float*)workspace;
     if (D <= 4) return gyro_bwd_launch<4>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
     if (D <= 8) return gyro_bwd_launch<8>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 12) return gyro_bwd_launch<12>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
     if (D <= 16) return gyro_bwd_launch<16>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
     if (D <= 32) return gyro_bwd_launch<32>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
     return gyro_bwd_launch<64>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);

@@ -100,8 +100,12 @@ class FlatGradBucket:
             view = self.buffer[off:off + p.numel()].view_as(p)
             g = p.grad
             if g is not None and g.data_ptr() != view.data_ptr():
-                src.append(g if g.is_contiguous() else g.contiguous())
-                dst.append(view)
+                if g.numel() >= (1 << 16):
+                    view.copy_(g)  # big tensors: a plain copy kernel fills the GPU; the multi-tensor kernel gives each
+                                   # tensor only numel/64K blocks (measured 10 us per 1.9 MB weight)
+                else:
+                    src.append(g if g.is_contiguous() else g.contiguous())
+                    dst.append(view)
             p.grad = view
         if src:
             torch._foreach_copy_(dst, src)
