@@ -121,8 +121,9 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
 constexpr int kGyroBxThreads = 128;  // rows per CTA
 constexpr int kGyroBxTJ = 32;        // planes per smem stage
 
+// small D: cap registers so 5 CTAs fit an SM (the static smem allows 5): 115 -> 89 registers at D4 = 12, no spills
 template <int D4, bool kAliased>
-__global__ void __launch_bounds__(kGyroBxThreads)
+__global__ void __launch_bounds__(kGyroBxThreads, (D4 <= 16 ? 5 : 1))
 k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
                  const float* __restrict__ gout, float* __restrict__ gx, float* __restrict__ CP, float* __restrict__ CA,
                  float* __restrict__ wsum /* [rowblocks][P][4] */, int B, int D, int P_, int planes_per_chunk,

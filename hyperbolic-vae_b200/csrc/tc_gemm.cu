@@ -858,26 +858,53 @@ __global__ void __launch_bounds__(256) k_split3_rows(const float* __restrict__ i
     }
 }
 
-// (R, C) fp32 -> (C, 3*Rp) bf16: transposed, the contraction runs over the rows of the input.  32x32 smem tiles.
-__global__ void __launch_bounds__(256) k_split3_transposed(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                           int64_t R, int64_t C, int64_t Rp) {
-    __shared__ float tile[32][33];
+// Both layouts from one read: (R, C) fp32 -> rows split (R, 3*Cp) AND transposed split (C, 3*Rp).  A dense layer needs
+// every tensor both ways (x: forward + weight gradient, W: forward + input gradient, gy: input + weight gradient).
+__global__ void __launch_bounds__(256) k_split3_both(const float* __restrict__ in, __nv_bfloat16* __restrict__ out_r,
+                                                     __nv_bfloat16* __restrict__ out_t, int64_t R, int64_t C, int64_t Cp,
+                                                     int64_t Rp) {
+    // 64 x 64 tile, every global access 4-8 bytes per lane: float2 loads, bf16x2 stores in both layouts (Cp, Rp are
+    // multiples of 64, so the tiles cover the zero padding of both outputs exactly)
+    __shared__ float tile[64][65];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;  // r0 covers [0, Rp)
-    for (int i = ty; i < 32; i += 8) {
-        const int64_t r = r0 + i, c = c0 + tx;
-        tile[i][tx] = (r < R && c < C) ? __ldg(in + r * C + c) : 0.0f;
+    const int64_t r0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 64;
+    const bool c_even = (C & 1) == 0;
+    for (int i = ty; i < 64; i += 8) {
+        const int64_t r = r0 + i, c = c0 + 2 * tx;
+        float v0 = 0.0f, v1 = 0.0f;
+        if (r < R) {
+            if (c_even && c + 1 < C) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(in + r * C + c));
+                v0 = v.x; v1 = v.y;
+            } else {
+                if (c < C) v0 = __ldg(in + r * C + c);
+                if (c + 1 < C) v1 = __ldg(in + r * C + c + 1);
+            }
+        }
+        tile[i][2 * tx] = v0;
+        tile[i][2 * tx + 1] = v1;
+        if (out_r && r < R) {
+            __nv_bfloat162 h, m, l;
+            split3(v0, h.x, m.x, l.x);
+            split3(v1, h.y, m.y, l.y);
+            __nv_bfloat16* o = out_r + r * 3 * Cp + c;
+            *reinterpret_cast<__nv_bfloat162*>(o) = h;
+            *reinterpret_cast<__nv_bfloat162*>(o + Cp) = m;
+            *reinterpret_cast<__nv_bfloat162*>(o + 2 * Cp) = l;
+        }
     }
+    if (!out_t) return;
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int64_t c = c0 + i, r = r0 + tx;
-        if (c < C && r < Rp) {
-            __nv_bfloat16 h, m, l;
-            split3(tile[tx][i], h, m, l);
-            __nv_bfloat16* o = out + c * 3 * Rp + r;
-            o[0] = h;
-            o[Rp] = m;
-            o[2 * Rp] = l;
+    for (int i = ty; i < 64; i += 8) {
+        const int64_t c = c0 + i, r = r0 + 2 * tx;
+        if (c < C) {
+            __nv_bfloat162 h, m, l;
+            split3(tile[2 * tx][i], h.x, m.x, l.x);
+            split3(tile[2 * tx + 1][i], h.y, m.y, l.y);
+            __nv_bfloat16* o = out_t + c * 3 * Rp + r;
+            *reinterpret_cast<__nv_bfloat162*>(o) = h;
+            *reinterpret_cast<__nv_bfloat162*>(o + Rp) = m;
+            *reinterpret_cast<__nv_bfloat162*>(o + 2 * Rp) = l;
         }
     }
 }
@@ -1247,6 +1274,19 @@ extern "C" int hvae_split3_f32(const float* src, void* dst, int64_t rows, int64_
     return check_launch();
 }
 
+// src (rows, cols) fp32 -> dst_rows (rows, 3*Cp) and dst_t (cols, 3*Rp) bf16 in one pass (either may be NULL)
+extern "C" int hvae_split3_both_f32(const float* src, void* dst_rows, void* dst_t, int64_t rows, int64_t cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return HVAE_ESHAPE;
+    if (!src || (!dst_rows && !dst_t)) return HVAE_EARG;
+    if (!dst_t) return hvae_split3_f32(src, dst_rows, rows, cols, stream);
+    const int64_t Cp = tc::x3_kp(cols), Rp = tc::x3_kp(rows);
+    if (Cp / 64 > 65535) return HVAE_ESHAPE;
+    dim3 grid((unsigned)(Rp / 64), (unsigned)(Cp / 64));
+    tc::k_split3_both<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst_rows, (__nv_bfloat16*)dst_t, rows, cols, Cp,
+                                                             Rp);
+    return check_launch();
+}
+
 extern "C" size_t hvae_gemm_x3s_workspace_bytes(int64_t M, int64_t N) {
     if (M <= 0 || N <= 0) return 0;
     return (size_t)tc::X3_MAX_SPLITS * M * N * 4 + 256;
@@ -1328,8 +1368,8 @@ extern "C" int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int
             const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
             tc::k_split3_rows<<<grid, 256, 0, s>>>(src, dst, rows, K, Kp);
         } else {  // stored (K, rows)
-            dim3 grid((unsigned)(Kp / 32), (unsigned)((rows + 31) / 32));
-            tc::k_split3_transposed<<<grid, 256, 0, s>>>(src, dst, K, rows, Kp);
+            dim3 grid((unsigned)(Kp / 64), (unsigned)(tc::x3_kp(rows) / 64));
+            tc::k_split3_both<<<grid, 256, 0, s>>>(src, nullptr, dst, K, rows, tc::x3_kp(rows), Kp);
         }
     };
     split(A, a_trans, a16, M);

@@ -1102,36 +1102,76 @@ def _(x):
     return x.new_empty(x.shape[1])
 
 
+def _cp64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+@_op("hvae::split3_both", mutates_args=())
+def split3_both(x: Tensor, want_rows: bool, want_t: bool) -> Tuple[Tensor, Tensor]:
+    """(rows, cols) fp32 -> (rows split (rows, 3*Cp), transposed split (cols, 3*Rp)) from one read of x; a layout that
+    is not wanted comes back empty."""
+    C.require_cuda(x)
+    rows, cols = x.shape
+    r = torch.empty((rows, 3 * _cp64(cols)) if want_rows else (0,), dtype=torch.bfloat16, device=x.device)
+    t = torch.empty((cols, 3 * _cp64(rows)) if want_t else (0,), dtype=torch.bfloat16, device=x.device)
+    C.call("hvae_split3_both_f32", C.ptr(x), C.ptr(r) if want_rows else None, C.ptr(t) if want_t else None, rows, cols,
+           C.stream())
+    return r, t
+
+
+@split3_both.register_fake
+def _(x, want_rows, want_t):
+    rows, cols = x.shape
+    return (torch.empty((rows, 3 * _cp64(cols)) if want_rows else (0,), dtype=torch.bfloat16, device=x.device),
+            torch.empty((cols, 3 * _cp64(rows)) if want_t else (0,), dtype=torch.bfloat16, device=x.device))
+
+
 @_op("hvae::linear_x3", mutates_args=())
-def linear_x3_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
-    return gemm_x3(x, False, weight, False, bias, False)
+def linear_x3_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (y, transposed split of x, transposed split of W).  Every tensor of a dense layer is needed in both layouts
+    (x: forward + weight gradient, W: forward + input gradient), so each is read once and split both ways here; the
+    transposed splits are kept for the backward (empty when that gradient is not needed)."""
+    xs, xts = split3_both(x, True, need_gw)
+    ws, wts = split3_both(weight, True, need_gx)
+    y = gemm_x3s(xs, False, ws, False, bias, False, x.shape[0], weight.shape[0], x.shape[1])
+    return y, xts, wts
 
 
 @linear_x3_fwd.register_fake
-def _(x, weight, bias):
-    return x.new_empty(x.shape[0], weight.shape[0])
+def _(x, weight, bias, need_gx, need_gw):
+    M, K = x.shape
+    N = weight.shape[0]
+    return (x.new_empty(M, N), torch.empty((K, 3 * _cp64(M)) if need_gw else (0,), dtype=torch.bfloat16, device=x.device),
+            torch.empty((K, 3 * _cp64(N)) if need_gx else (0,), dtype=torch.bfloat16, device=x.device))
 
 
 def _lx3_setup(ctx, inputs, output):
-    x, weight, bias = inputs
-    ctx.save_for_backward(x, weight)
+    x, weight, bias, need_gx, need_gw = inputs
+    ctx.save_for_backward(output[1], output[2])
+    ctx.dims = (x.shape[0], weight.shape[0], x.shape[1])  # rows, out, in
     ctx.has_bias = bias is not None
+    ctx.need = (need_gx, need_gw)
 
 
-def _lx3_backward(ctx, gy):
-    # Both backward GEMMs contract over an axis that is not contiguous in the stored operands; the split kernels
-    # transpose while they split (K-major tiles).  Reading the forward's splits MN-major instead (gemm_x3s) was
-    # measured slower: 81 / 94 us against 71 / 79 us for dgrad / wgrad at config-2 sizes, splits included.
-    x, weight = ctx.saved_tensors
+def _lx3_backward(ctx, gy, _g1, _g2):
+    # gy is read once and split both ways: rows layout (contraction over `out`) for the input gradient, transposed
+    # (contraction over the batch) for the weight gradient; x^T and W^T splits come from the forward.
+    xts, wts = ctx.saved_tensors
+    M, n_out, n_in = ctx.dims
+    need_gx, need_gw = ctx.need
     gy = _c(gy)
     gx = gw = gb = None
-    if ctx.needs_input_grad[0]:
-        gx = gemm_x3(gy, False, weight, True, None, False)   # (M, in) = gy (M, out) . W (out, in): contraction over out
-    if ctx.needs_input_grad[1]:
-        gw = gemm_x3(gy, True, x, True, None, False)         # (out, in) = gy^T (out, M) . x (M, in): contraction over M
+    want_gx = ctx.needs_input_grad[0] and need_gx
+    want_gw = ctx.needs_input_grad[1] and need_gw
+    if want_gx or want_gw:
+        gs, gts = split3_both(gy, want_gx, want_gw)
+        if want_gx:
+            gx = gemm_x3s(gs, False, wts, False, None, False, M, n_in, n_out)    # gy (M,out) . W (out,in)
+        if want_gw:
+            gw = gemm_x3s(gts, False, xts, False, None, False, n_out, n_in, M)   # gy^T (out,M) . x (M,in)
     if ctx.has_bias and ctx.needs_input_grad[2]:
         gb = colsum(gy)
-    return gx, gw, gb
+    return gx, gw, gb, None, None
 
 
 linear_x3_fwd.register_autograd(_lx3_backward, setup_context=_lx3_setup)
@@ -1141,7 +1181,9 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     """torch.nn.functional.linear semantics; the tensor-core fp32 path for GEMM-sized CUDA inputs."""
     if trunk_x3_eligible(x, weight):
         lead = x.shape[:-1]
-        y = linear_x3_fwd(_rows(x), _c(weight), None if bias is None else _c(bias))
+        grad_on = torch.is_grad_enabled()
+        y, _, _ = linear_x3_fwd(_rows(x), _c(weight), None if bias is None else _c(bias), grad_on and x.requires_grad,
+                                grad_on and weight.requires_grad)
         return y.view(*lead, weight.shape[0])
     return torch.nn.functional.linear(x, weight, bias)
 

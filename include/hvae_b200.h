@@ -217,6 +217,8 @@ int hvae_colsum_f32(const float* x, float* out, int64_t R, int64_t C, void* work
  *   (K, N) matrix - the contraction runs over its rows and the tensor core reads it MN-major, no transpose is made. */
 size_t hvae_split3_bytes(int64_t rows, int64_t cols);
 int hvae_split3_f32(const float* src, void* dst, int64_t rows, int64_t cols, void* stream);
+/* rows split (rows, 3*Cp) and transposed split (cols, 3*Rp) of the same matrix from one read; either may be NULL */
+int hvae_split3_both_f32(const float* src, void* dst_rows, void* dst_t, int64_t rows, int64_t cols, void* stream);
 size_t hvae_gemm_x3s_workspace_bytes(int64_t M, int64_t N);
 int hvae_gemm_x3s_num_launches(int64_t M, int64_t N, int64_t K);
 int hvae_gemm_x3s_f32(const void* As, int a_mn, const void* Bs, int b_mn, const float* bias, int relu, float* C,
