@@ -395,6 +395,7 @@ def log_sinhc(x: Tensor) -> Tensor:
 # K2 gyroplane
 # ---------------------------------------------------------------------------------------------------
 _WS = {}
+_WS_RETIRED = []  # outgrown workspaces stay allocated: a captured CUDA graph may still hold their addresses
 
 
 def _workspace(nbytes: int, device) -> Tensor:
@@ -402,6 +403,8 @@ def _workspace(nbytes: int, device) -> Tensor:
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _WS_RETIRED.append(buf)
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf
