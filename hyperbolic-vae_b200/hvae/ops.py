@@ -357,6 +357,7 @@ def _(mu, sigma, eps, gz, gkl, prior_scale, c):
 
 
 def _lh_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # an unused output's gradient arrives as None, not as a zero-filled tensor
     ctx.save_for_backward(inputs[0], inputs[1], inputs[2])
     ctx.prior_scale, ctx.c = inputs[3], inputs[4]
 
@@ -512,6 +513,7 @@ def _(W, beta, gM, gbpt, c):
 
 
 def _wp_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(inputs[0], inputs[1])
     ctx.c = inputs[2]
 
@@ -614,11 +616,14 @@ def _(x, M, mx, gy, c):
 
 
 def _mm_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the saved pre-activation mx never receives a gradient: no (B,P) zero fill
     ctx.save_for_backward(inputs[0], inputs[1], output[1])
     ctx.c = inputs[2]
 
 
 def _mm_backward(ctx, gy, _gmx):
+    if gy is None:
+        return None, None, None
     x, M, mx = ctx.saved_tensors
     gx, gM = mobius_matvec_bwd(x, M, mx, _c(gy), ctx.c)
     return gx, gM, None
@@ -660,10 +665,13 @@ def _(sigma, dim, c):
 
 
 def _hl_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(output[1])
 
 
 def _hl_backward(ctx, g, _g2):
+    if g is None:
+        return None, None, None
     (dlogz,) = ctx.saved_tensors
     return g * dlogz, None, None
 
@@ -718,10 +726,13 @@ def _(r, sigma, dim, c):
 
 
 def _hr_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(output[1])
 
 
 def _hr_backward(ctx, g, _g2):
+    if g is None:
+        return None, None, None, None
     (dr,) = ctx.saved_tensors
     return None, (g * dr).sum(0), None, None
 
@@ -881,11 +892,14 @@ def _(x, M, y, mxsq, gy, c):
 
 
 def _mmtc_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(inputs[0], inputs[1], output[0], output[1])
     ctx.c = inputs[2]
 
 
 def _mmtc_backward(ctx, gy, _g):
+    if gy is None:
+        return None, None, None
     x, M, y, mxsq = ctx.saved_tensors
     gx, gM = mobius_matvec_tc_bwd(x, M, y, mxsq, _c(gy), ctx.c)
     return gx, gM, None
@@ -1149,6 +1163,7 @@ def _(x, weight, bias, need_gx, need_gw):
 
 
 def _lx3_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the kept splits (19 MB of bf16 at config 2) never receive a gradient
     x, weight, bias, need_gx, need_gw = inputs
     ctx.save_for_backward(output[1], output[2])
     ctx.dims = (x.shape[0], weight.shape[0], x.shape[1])  # rows, out, in
@@ -1159,6 +1174,8 @@ def _lx3_setup(ctx, inputs, output):
 def _lx3_backward(ctx, gy, _g1, _g2):
     # gy is read once and split both ways: rows layout (contraction over `out`) for the input gradient, transposed
     # (contraction over the batch) for the weight gradient; x^T and W^T splits come from the forward.
+    if gy is None:
+        return None, None, None, None, None
     xts, wts = ctx.saved_tensors
     M, n_out, n_in = ctx.dims
     need_gx, need_gw = ctx.need
