@@ -138,11 +138,8 @@ def run_reference(args, wl):
 # ---------------------------------------------------------------------------------------------------
 def build_model(wl, device):
     from hvae import models as HM
-    from hvae.distributions.riemannian_normal import HyperbolicRadius
-
     torch.manual_seed(42)
     m = HM.PvaeMnist(latent_dim=wl["latent"], hidden_dim=wl["hidden"], c=wl["c"], data_size=wl["data"]).to(device)
-    HyperbolicRadius.philox_counter = torch.zeros((), dtype=torch.int64, device=device)
     return m
 
 

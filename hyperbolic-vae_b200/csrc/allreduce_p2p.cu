@@ -11,7 +11,9 @@
 
 namespace hvae {
 
-constexpr int kArBlocks = 128;  // upper bound (pad slots are sized for it); HVAE_AR_BLOCKS picks fewer
+constexpr int kArBlocks = 128;  // upper bound (pad slots are sized for it); the caller passes the block count, agreed across ranks
+constexpr long long kArSpinCycles = 8000000000LL;  // ~4 s at 2 GHz: a peer that never arrives is an error, not a hang
+constexpr int kArErrSlot = 0;   // pad word 0 of this rank's own pad: set to 1 when a barrier timed out
 constexpr int kArUnroll = 4;    // positions per thread in flight: the kernel is bound by NVLink round-trip latency
 constexpr int kArThreads = 512;
 constexpr int kArMaxWorld = 16;
@@ -22,16 +24,26 @@ __device__ __forceinline__ uint32_t cas_sys(uint32_t* addr, uint32_t cmp, uint32
     return old;
 }
 
-// block b of this rank meets block b of every rank: signal each peer's pad, then consume each peer's signal in mine
+// block b of this rank meets block b of every rank: signal each peer's pad, then consume each peer's signal in mine.
+// The spins are bounded: a rank that skipped the step (exception, death) must not leave its peers' kernels spinning on
+// the GPU forever where no watchdog sees them.  On time-out the error word of this rank's pad is set (the host reads it:
+// hvae.parallel.FlatGradBucket.check) and the kernel runs to completion with whatever data it has.
 __device__ __forceinline__ void block_sync_remote(uint32_t* const* pads, int rank, int world, int slot) {
     __syncthreads();
     if ((int)threadIdx.x < world) {
         const int p = threadIdx.x;
         __threadfence_system();
+        const long long t0 = clock64();
+        bool ok = true;
         uint32_t* dst = pads[p] + slot + rank;
-        while (cas_sys(dst, 0u, 1u) != 0u) {}
+        while (cas_sys(dst, 0u, 1u) != 0u) {
+            if (clock64() - t0 > kArSpinCycles) { ok = false; break; }
+        }
         uint32_t* src = pads[rank] + slot + p;
-        while (cas_sys(src, 1u, 0u) != 1u) {}
+        while (ok && cas_sys(src, 1u, 0u) != 1u) {
+            if (clock64() - t0 > kArSpinCycles) { ok = false; break; }
+        }
+        if (!ok) pads[rank][kArErrSlot] = 1u;
         __threadfence_system();
     }
     __syncthreads();
@@ -102,16 +114,15 @@ extern "C" int hvae_allreduce_p2p_slots(int world) { return world > 0 ? kArBlock
 // pad, e.g. torch symmetric memory's buffer_ptrs_dev / signal_pad_ptrs_dev).  Reduces elements [offset, offset + n) of
 // the buckets in place (n and offset multiples of 4), result scaled by `scale`.  pad_slot_base: first uint32 slot of the
 // pad this call may use (hvae_allreduce_p2p_slots(world) slots, zero-initialised; concurrent calls need disjoint ranges).
+// blocks: grid size, 1..128, MUST be the same on every rank (block b meets block b); 0 picks the default (64).
 extern "C" int hvae_allreduce_p2p_f32(const void* buf_ptrs_dev, const void* pad_ptrs_dev, int rank, int world, int64_t offset,
-                                      int64_t n, int pad_slot_base, float scale, void* stream) {
+                                      int64_t n, int pad_slot_base, float scale, int blocks, void* stream) {
     if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || n <= 0 || (n & 3) || (offset & 3) || offset < 0)
         return HVAE_ESHAPE;
     if (!buf_ptrs_dev || !pad_ptrs_dev || pad_slot_base < 0) return HVAE_EARG;
-    static const int blocks = [] {
-        const char* e = getenv("HVAE_AR_BLOCKS");
-        const int b = e ? atoi(e) : 64;
-        return b < 1 ? 1 : (b > kArBlocks ? kArBlocks : b);
-    }();
+    if (blocks == 0) blocks = 64;
+    if (blocks < 1 || blocks > kArBlocks) return HVAE_EARG;
+    if (pad_slot_base < 1) return HVAE_EARG;  // word 0 is the error word
     k_allreduce_p2p<<<blocks, kArThreads, 0, (cudaStream_t)stream>>>((float* const*)buf_ptrs_dev, (uint32_t* const*)pad_ptrs_dev,
                                                                         rank, world, offset, n, pad_slot_base, scale);
     return check_launch();

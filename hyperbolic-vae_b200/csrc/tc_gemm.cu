@@ -4,20 +4,23 @@
 // reference: hyperbolic_vae/layers.py:145-147 (MobiusLayer -> geoopt mobius_matvec's tensordot) and
 //            layers.py:193-210 (gyroplane: the reference broadcasts (B,D,P); here <x,p> is a GEMM).
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage smem ring, mbarrier expect_tx
+// Structure (one CTA per SM, persistent over output tiles, THREADS = 576 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> STAGES = 6 smem ring, mbarrier expect_tx
 //   warp 1      MMA issuer     one elected lane: tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16 x4 per stage,
 //                              tcgen05.commit frees the smem stage / publishes the accumulator
-//   warps 2-5   epilogue       tcgen05.ld 32x32b.x32 from TMEM (2 accumulator stages of 128 columns, so the
-//                              epilogue of tile i overlaps the MMAs of tile i+1), fused math, global stores
+//   warps 2-17  epilogue       16 warps = 4 TMEM lane quarters x CG = 4 column groups; tcgen05.ld 16x256b.x4 from TMEM
+//                              (2 accumulator stages of 128 columns, so the epilogue of tile i overlaps the MMAs of
+//                              tile i+1), fused math, sector-complete global stores straight from registers
 // Operands are K-major: A = rows of x (B,K), B = rows of the weight (P,K); both are converted fp32 -> bf16 by a
 // streaming pre-pass that also produces the row norms the epilogues need.
 //
 // Epilogues
-//   PLAIN : D = acc (* rowscale) ; optional per-(row, n-tile) sum of acc^2  (Mobius pass 1: mx and |mx|^2 partials)
-//   GYRO  : D = asinh-distance of row b to plane j from <x_b,p_j>, |x_b|^2, |p_j|^2  (gyro_pair_fwd, a == p)
-// The Mobius rescale y = psi(|x|,|mx|) mx needs |mx_b| over ALL of P, i.e. across n-tiles: v1 finishes it with a
-// light second pass (k_mobius_rescale_rows); DESIGN.md lists the Gram-matrix single-pass variant as next.
+//   PLAIN  : D = acc (* rowscale) (+ axpy) ; optional per-(row, n-tile) sum of acc^2
+//   MOBIUS : D = rowscale[m] * acc  (the Gram-matrix single pass: psi and the projection clip are known per row)
+//   ROWDOT : per-row partial sums of acc * xrow (the x^T G x pass of the Gram variant)
+//   GYRO   : D = asinh-distance of row b to plane j from <x_b,p_j>, |x_b|^2, |p_j|^2  (a == p)
+//   X3     : chunked fp32-accurate accumulation of the six bf16 piece products (trunk dense layers)
+// The 2-CTA (cta_group::2, 256x256 tiles) kernel for the big Mobius / gyroplane shapes lives in tc_gemm2.cu.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -70,7 +73,9 @@ struct Params {
     int a_mn, b_mn;        // operand stored contraction-major-OUTER: buffer rows = contraction index, columns = M / N index
     int a_off[6], b_off[6];
     int relu;              // PLAIN: bias (per column, via `bias`) then optional ReLU
+#ifdef HVAE_EXPERIMENT
     int dbg;               // experiments only (HVAE_TC_DBG): 1 = skip the global stores, 2 = skip the whole drain
+#endif
     const float* rowscale; // PLAIN: optional (M,); MOBIUS: required (M,)
     const float* axpy_x;   // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
     const float* axpy_coef;//        (M,)
@@ -502,7 +507,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tc_fence_after();
 #pragma unroll 1
             for (int cb = cg * COLS; cb < (cg + 1) * COLS; cb += 32) {
+#ifdef HVAE_EXPERIMENT
                 if (prm.dbg & 2) break;
+#endif
                 float v[2][16];
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb), v[0]);
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + (uint32_t)(as * BN + cb), v[1]);
@@ -572,12 +579,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                             }
                         }
                 }
+#ifdef HVAE_EXPERIMENT
                 if (EPI != EPI_ROWDOT && (prm.dbg & 1)) {
                     float t = 0.0f;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) t += v[0][i] + v[1][i];
                     if (t == 123.456f) prm.D[0] = t;
-                } else if (EPI != EPI_ROWDOT) {
+                } else
+#endif
+                if (EPI != EPI_ROWDOT) {
                     if (fin) {
                         // dense-layer epilogue: per-column bias, optional ReLU
 #pragma unroll
@@ -1012,22 +1022,25 @@ template <int EPI>
 static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm_in, cudaStream_t s,
                        OperandShapes sh = OperandShapes()) {
     Params prm = prm_in;
+#ifdef HVAE_EXPERIMENT
     static const int dbg = getenv("HVAE_TC_DBG") ? atoi(getenv("HVAE_TC_DBG")) : 0;
     prm.dbg = dbg;
+#endif
     CUtensorMap ma, mb;
     const int64_t ar = sh.a_rows >= 0 ? sh.a_rows : prm.M, ac = sh.a_cols >= 0 ? sh.a_cols : prm.K;
     const int64_t br = sh.b_rows >= 0 ? sh.b_rows : prm.N, bc = sh.b_cols >= 0 ? sh.b_cols : prm.K;
     if (!make_map(&ma, A, ar, ac, prm.a_mn ? 64 : BM) || !make_map(&mb, Bm, br, bc, prm.b_mn ? 64 : BN)) return HVAE_ELAUNCH;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_tc_gemm<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        cudaFuncSetAttribute(k_tc_gemm<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_ARES);
-        attr_set = true;
-    }
+    // the attribute is per device (a process may drive several GPUs): set it on every launch, it is a cheap driver call
+    cudaFuncSetAttribute(k_tc_gemm<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(k_tc_gemm<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_ARES);
     const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + BN - 1) / BN;
     // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over, and enough m-blocks
     // (not for the gyroplane epilogue: measured slower there, its per-tile column-constant exchange serialises the n-tiles)
+#ifdef HVAE_EXPERIMENT
     static const bool want_ares = getenv("HVAE_TC_NO_ARES") == nullptr;
+#else
+    constexpr bool want_ares = true;
+#endif
     const bool ares = want_ares && EPI != EPI_GYRO && prm.npairs == 0 && prm.splits <= 1 && !prm.a_mn && !prm.b_mn && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= kNumSMs;
     if (ares) {
         const int grid = (int)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
@@ -1312,7 +1325,7 @@ extern "C" int hvae_gemm_x3s_f32(const void* As, int a_mn, const void* Bs, int b
     prm.M = M; prm.N = N; prm.K = 3 * Kp;
     prm.npairs = 6; prm.kbp = (int)(Kp / tc::BK); prm.splits = S;
     prm.a_mn = a_mn ? 1 : 0; prm.b_mn = b_mn ? 1 : 0;
-    prm.share = (!a_mn && !b_mn && !getenv("HVAE_X3_NOSHARE")) ? 1 : 0;
+    prm.share = (!a_mn && !b_mn) ? 1 : 0;
     const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};  // 0 = hi, 1 = mid, 2 = lo; smallest products first
     for (int i = 0; i < 6; ++i) {
         prm.a_off[i] = (int)(pa[i] * (a_mn ? Mp : Kp));
@@ -1378,7 +1391,7 @@ extern "C" int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int
     tc::Params prm{};
     prm.M = M; prm.N = N; prm.K = 3 * Kp;
     prm.npairs = 6; prm.kbp = (int)(Kp / tc::BK); prm.splits = S;
-    prm.share = getenv("HVAE_X3_NOSHARE") ? 0 : 1;
+    prm.share = 1;
     // pieces: 0 = hi, 1 = mid, 2 = lo; smallest products first
     const int pa[6] = {1, 0, 2, 0, 1, 0}, pb[6] = {1, 2, 0, 1, 0, 0};
     for (int i = 0; i < 6; ++i) { prm.a_off[i] = (int)(pa[i] * Kp); prm.b_off[i] = (int)(pb[i] * Kp); }

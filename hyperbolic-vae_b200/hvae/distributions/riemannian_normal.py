@@ -64,9 +64,11 @@ class HyperbolicRadius(torch.distributions.Distribution):
         self.log_normalizer = ops.hradius_lognorm(scale, self.dim, self.c_value)
         super().__init__(self.scale.size(), validate_args=False)
 
-    philox_counter: Tensor = None  # optional int64 device scalar: graph-safe noise counter shared by all instances
+    philox_counter: Tensor = None  # optional override of the per-device noise counter (ops.philox_counter)
 
     def sample(self, sample_shape=torch.Size(), seed=None, offset=None) -> Tensor:
+        """Counters default to the per-device DEVICE-side Philox counter, advanced in-stream: graph replays draw fresh
+        noise (a host offset would be frozen into a captured graph)."""
         S = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
         r = ops.hradius_sample(self.scale, S, self.dim, self.c_value, seed=seed, offset=offset,
                                offset_dev=HyperbolicRadius.philox_counter)

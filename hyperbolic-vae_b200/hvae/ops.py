@@ -684,29 +684,72 @@ def hradius_lognorm(sigma: Tensor, dim: int, c: float) -> Tensor:
     return hradius_lognorm_fwd(_c(sigma).view(-1), int(dim), c)[0].view(shape)
 
 
-_philox_offset = 0
+# Noise stream of the in-kernel samplers.  Sample i of a call draws from Philox counters (seed, base + *counter + i):
+#   * `counter` is a per-device int64 DEVICE scalar advanced in-stream after every call, so a captured CUDA graph
+#     draws fresh noise on every replay (a host-side offset would be baked into the graph: every replay would repeat
+#     the same radii).  It is the default; it must exist before capture starts (TrainStep's eager warm-up steps, or
+#     philox_counter(device), create it).
+#   * data parallel: set_noise_shard(lo, global_rows) makes a rank that owns rows [lo, lo + B_local) of a
+#     global batch draw exactly the numbers the single-GPU run draws for those rows: base = lo and the counter advances by
+#     the GLOBAL row count per call.
+_philox_counters = {}
+_noise_shard = (0, None)  # (first global row of this rank's shard, global rows per call or None = local rows)
+
+
+def philox_counter(device) -> Tensor:
+    """The per-device int64 noise counter (created on first use; creating it inside a graph capture is an error)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    t = _philox_counters.get(idx)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("hvae: the Philox noise counter must exist before CUDA-graph capture starts; run one "
+                               "eager step first or call hvae.ops.philox_counter(device)")
+        t = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+        _philox_counters[idx] = t
+    return t
+
+
+def set_noise_shard(lo: int, global_rows: Optional[int]):
+    """Data-parallel noise rule: this rank owns rows [lo, lo + B_local) of a global batch of `global_rows` rows
+    (hvae.parallel.philox_offset_for_shard).  (0, None) restores the single-process behaviour."""
+    global _noise_shard
+    _noise_shard = (int(lo), None if global_rows is None else int(global_rows))
+
+
+def reset_noise(device=None):
+    """Zero the device noise counter(s): two runs with the same torch seed then draw the same stream."""
+    for idx, t in _philox_counters.items():
+        if device is None or idx == (device.index if device.index is not None else torch.cuda.current_device()):
+            t.zero_()
 
 
 def hradius_sample(sigma: Tensor, S: int, dim: int, c: float, seed: Optional[int] = None, offset: Optional[int] = None,
                    offset_dev: Optional[Tensor] = None) -> Tensor:
     """r (S,B) ~ rho(.; sigma_b) by in-kernel rejection sampling (Philox4x32-10).  No gradient.
-    offset_dev: optional int64 device scalar added to the counter and advanced in-stream (CUDA-graph safe)."""
-    global _philox_offset
+    offset: explicit host counter base (deterministic tests) - then no device counter is used unless offset_dev is given.
+    Default: the per-device counter + this rank's shard rule (see above)."""
     C.require_cuda(sigma)
     sig = _c(sigma.detach()).view(-1)
     B = sig.numel()
     if seed is None:
         seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-    if offset is None:
-        if offset_dev is not None:
-            offset = 0
-        else:
-            offset = _philox_offset
-            _philox_offset += S * B
     r = sig.new_empty(S, B)
-    C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r), S, B, dim, c, seed, offset, C.ptr(offset_dev), C.stream())
-    if offset_dev is not None:
+    if offset is not None:
+        C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r), S, B, dim, c, seed, offset, C.ptr(offset_dev), C.stream())
+        if offset_dev is not None:
+            offset_dev.add_(S * B)
+        return r
+    if offset_dev is None:
+        offset_dev = philox_counter(sig.device)
+    lo, grows = _noise_shard
+    if grows is None or grows == B:
+        C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r), S, B, dim, c, seed, lo, C.ptr(offset_dev), C.stream())
         offset_dev.add_(S * B)
+    else:  # sharded: sample s of global row g uses counter s * global_rows + g, as the single-GPU call would
+        for s_ in range(S):
+            C.call("hvae_hradius_sample_f32", C.ptr(sig), C.ptr(r[s_]), 1, B, dim, c, seed, s_ * grows + lo,
+                   C.ptr(offset_dev), C.stream())
+        offset_dev.add_(S * grows)
     return r
 
 

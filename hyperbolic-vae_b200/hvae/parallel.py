@@ -50,8 +50,13 @@ class FlatGradBucket:
             symmetric = (dev.type == "cuda" and dt == torch.float32 and self._active() and dist.get_backend() == "nccl"
                          and os.environ.get("HVAE_DP_P2P", "1") != "0")
         self._symm = None
+        self.p2p_blocks = 64  # grid of the peer-memory kernel; agreed across ranks below (block b meets block b)
         if symmetric:
             self.buffer, self._symm = self._alloc_symmetric(total, dev)
+            if self._symm is not None:
+                nb = torch.tensor([int(os.environ.get("HVAE_AR_BLOCKS", "64"))], device=dev)
+                dist.all_reduce(nb, op=dist.ReduceOp.MIN)  # one value for the whole job, whatever each process's env says
+                self.p2p_blocks = max(1, min(128, int(nb.item())))
         if self._symm is None:
             self.buffer = torch.zeros(total, device=dev, dtype=dt)
         for p, off in zip(self.params, self.offsets):
@@ -147,7 +152,17 @@ class FlatGradBucket:
         W = h.world_size
         base = 64 + site * C.lib().hvae_allreduce_p2p_slots(W)
         C.call("hvae_allreduce_p2p_f32", h.buffer_ptrs_dev, h.signal_pad_ptrs_dev, h.rank, W, offset, n, base,
-               1.0 / W if average else 1.0, C.stream())
+               1.0 / W if average else 1.0, self.p2p_blocks, C.stream())
+
+    def check(self):
+        """Host-side health check of the peer-memory exchange (syncs the device): raises if one of this rank's
+        all-reduce barriers timed out, i.e. a peer never arrived (it skipped a step, raised, or died)."""
+        if self._symm is None:
+            return
+        pad = self._symm.get_signal_pad(self._symm.rank, (1,), dtype=torch.int32)
+        if int(pad[0].item()) != 0:
+            raise RuntimeError("hvae.parallel: a peer-memory all-reduce barrier timed out on rank %d "
+                               "(a peer rank did not reach the exchange)" % self._symm.rank)
 
     def all_reduce(self, average: bool, group=None, async_op: bool = False):
         if not self._active(group):

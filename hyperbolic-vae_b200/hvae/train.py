@@ -19,9 +19,23 @@ from .parallel import FlatGradBucket
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, example_input: torch.Tensor, average_grads: bool = False,
-                 use_graph: bool = True, loss_key: str = "loss_total", **loss_kwargs):
+                 use_graph: bool = True, loss_key: str = "loss_total", noise_shard="auto", **loss_kwargs):
+        """noise_shard: (first_global_row, global_rows) of this rank's shard for the in-kernel samplers, "auto" =
+        rank * B_local of a world * B_local batch in a multi-rank job (every rank then draws its own rows' noise, the
+        rows a single-GPU run of the global batch would draw), None = leave the process-wide setting alone."""
         self.model, self.loss_key, self.loss_kwargs = model, loss_key, loss_kwargs
         self.average = average_grads
+        if noise_shard == "auto":
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                from . import ops
+                from .parallel import philox_offset_for_shard
+
+                b_local = int(example_input.shape[0])
+                ops.set_noise_shard(philox_offset_for_shard(0, dist.get_rank() * b_local, 1), dist.get_world_size() * b_local)
+        elif noise_shard is not None:
+            from . import ops
+
+            ops.set_noise_shard(int(noise_shard[0]), int(noise_shard[1]))
         self.bucket = FlatGradBucket(model.parameters())
         self._hooks, self._order, self._fired = [], [], 0
         self._side = torch.cuda.Stream()
@@ -155,6 +169,10 @@ class TrainStep:
             self.x.copy_(x, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
+            # a replay writes the bucket, not .grad: re-point .grad at the views in case an optimizer's
+            # zero_grad(set_to_none=True) dropped them since the last step (it would silently get no updates)
+            if any(p.grad is None for p in self.bucket.params):
+                self.bucket.rebind()
         else:
             self.loss = self._step()
         return self.loss

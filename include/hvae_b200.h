@@ -195,10 +195,13 @@ int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const floa
  * training/trainer_mnist.py:19).  buf_ptrs_dev / pad_ptrs_dev: DEVICE arrays of `world` pointers - every rank's copy of
  * the flat gradient bucket and of a zero-initialised uint32 signal pad, as mapped into THIS rank's address space
  * (symmetric memory).  Sums elements [offset, offset+n) across ranks in place (fixed rank order: identical bits on all
- * ranks), scaled by `scale`; one kernel per rank, barriers on the pad slots [pad_slot_base, + hvae_allreduce_p2p_slots). */
+ * ranks), scaled by `scale`; one kernel per rank, barriers on the pad slots [pad_slot_base, + hvae_allreduce_p2p_slots),
+ * pad_slot_base >= 1: word 0 of a rank's pad is its error word, set to 1 when a barrier timed out (~4 s; a peer never
+ * arrived) - the kernel then finishes instead of spinning forever and the host reads the word.  blocks: grid size
+ * (1..128, 0 = default 64); it MUST be the same on every rank. */
 int hvae_allreduce_p2p_slots(int world);
 int hvae_allreduce_p2p_f32(const void* buf_ptrs_dev, const void* pad_ptrs_dev, int rank, int world, int64_t offset,
-                           int64_t n, int pad_slot_base, float scale, void* stream);
+                           int64_t n, int pad_slot_base, float scale, int blocks, void* stream);
 
 /* column sums of a row-major (R, C) matrix: the bias gradient of a dense layer (autograd of nn.Linear's bias). */
 size_t hvae_colsum_workspace_bytes(int64_t C);
