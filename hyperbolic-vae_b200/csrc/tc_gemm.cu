@@ -26,6 +26,8 @@
 #include <stdlib.h>
 
 #include "hvae_common.cuh"
+#include "tc_common.cuh"
+#include "tc_gemm2.cuh"
 #include "gyro_pair.cuh"
 #include "mobius_row.cuh"
 
@@ -88,112 +90,8 @@ struct Params {
     float* rowdot;         // ROWDOT: [n_tiles][M] partial sums of acc * xrow
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), one atom along K
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address >> 4
-    d |= (uint64_t)0 << 16;                             // leading byte offset (unused: one swizzle atom along K)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-// MN-major, 128B-swizzled operand tile, loaded as two TMA boxes {64 MN elements (128 B), 64 contraction rows}: a
-// contraction row is 128 B, 8-row groups are 1024 B apart (SBO), the second 64-wide MN block sits 8192 B later (LBO).
-// One UMMA consumes 16 contraction rows = 2048 B, so the k-step advance is whole swizzle atoms.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset: between 64-element MN blocks
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: between 8-row contraction groups
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(addr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 16 lanes x (4 repeats of 256 bits): 16 registers; issue both halves, then wait once
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(addr));
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// the asm takes the loaded registers as in/out operands so no use of them can be scheduled above the wait
-__device__ __forceinline__ void tmem_ld_wait(float (&a)[16], float (&b)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]),
-                   "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]), "+f"(b[0]),
-                   "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]), "+f"(b[8]), "+f"(b[9]),
-                   "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15])
-                 :
-                 : "memory");
-}
 
 template <int EPI, bool ARES>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -686,6 +584,34 @@ __global__ void k_rows_to_bf16(const float* __restrict__ in, __nv_bfloat16* __re
     }
 }
 
+// plane pre-pass of the a != p gyroplane: rows of p and a -> bf16, with |p|^2, <p,a> and |a| of the ROUNDED values
+__global__ void k_plane_pair_to_bf16(const float* __restrict__ p, const float* __restrict__ a, __nv_bfloat16* __restrict__ p16,
+                                     __nv_bfloat16* __restrict__ a16, float* __restrict__ p2, float* __restrict__ pa,
+                                     float* __restrict__ an, int64_t rows, int64_t cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nw) {
+        float spp = 0.0f, spa = 0.0f, saa = 0.0f;
+        for (int64_t c = lane; c < cols; c += 32) {
+            const __nv_bfloat16 hp = __float2bfloat16_rn(p[r * cols + c]), ha = __float2bfloat16_rn(a[r * cols + c]);
+            p16[r * cols + c] = hp;
+            a16[r * cols + c] = ha;
+            const float fp = __bfloat162float(hp), fa = __bfloat162float(ha);
+            spp = fmaf(fp, fp, spp);
+            spa = fmaf(fp, fa, spa);
+            saa = fmaf(fa, fa, saa);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            spp += __shfl_xor_sync(0xffffffffu, spp, o);
+            spa += __shfl_xor_sync(0xffffffffu, spa, o);
+            saa += __shfl_xor_sync(0xffffffffu, saa, o);
+        }
+        if (lane == 0) { p2[r] = spp; pa[r] = spa; an[r] = sqrtf(saa); }
+    }
+}
+
 // (R, C) fp32 row-major -> (C, R) bf16 row-major (32x32 smem tiles)
 __global__ void k_transpose_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C) {
     __shared__ float tile[32][33];
@@ -986,34 +912,6 @@ __global__ void k_gyro_tc_rowcoef(const float* __restrict__ rowpart, float* __re
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
-
-// bf16 row-major (rows, K) -> 2-D tensor map with a {BK, box_rows} box, 128B swizzle
-static bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int box_rows) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // buffer shapes (rows, cols) of the two operands: by default (M, K) and (N, K); an MN-major operand (prm.a_mn / b_mn) is a
 // (contraction, >= M or N) buffer fetched in {64, 64} boxes
 struct OperandShapes { int64_t a_rows = -1, a_cols = -1, b_rows = -1, b_cols = -1; };
@@ -1051,6 +949,27 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
         k_tc_gemm<EPI, false><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, prm);
     }
     return check_launch();
+}
+
+// Big problems go to the CTA-pair kernel (tc_gemm2.cu: cta_group::2, 256x256 tiles); small ones, split/X3/MN-major users
+// and the dense-layer epilogue stay on the 128x128 kernel above.
+static bool pair_kernel_eligible(const Params& prm) {
+    return prm.npairs == 0 && !prm.a_mn && !prm.b_mn && prm.splits <= 1 && !prm.relu && prm.M >= 1024 && prm.N >= 128 && (prm.K % 8) == 0 && (prm.N % 4) == 0;
+}
+// number of [..][M] row-partial planes (rowsq / rowdot) the kernel chosen for this problem writes
+static int row_partial_planes(const Params& prm) {
+    return pair_kernel_eligible(prm) ? tc2::row_partials(prm.N) : (int)((prm.N + BN - 1) / BN) * CG;
+}
+template <int EPI>
+static int launch_auto(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Params& prm, cudaStream_t s) {
+    static_assert(EPI == EPI_PLAIN || EPI == EPI_GYRO || EPI == EPI_ROWDOT || EPI == EPI_MOBIUS, "no pair-kernel epilogue");
+    if (!pair_kernel_eligible(prm) || (EPI == EPI_PLAIN && prm.bias)) return launch_gemm<EPI>(A, Bm, prm, s);
+    tc2::Params2 q{};
+    q.D = prm.D; q.M = prm.M; q.N = prm.N; q.K = prm.K; q.splits = 1;
+    q.rowscale = prm.rowscale; q.axpy_x = prm.axpy_x; q.axpy_coef = prm.axpy_coef; q.rowsq = prm.rowsq;
+    q.x2 = prm.x2; q.p2 = prm.p2; q.bias = prm.bias; q.gp = prm.gp; q.xrow = prm.xrow; q.rowdot = prm.rowdot;
+    constexpr int e2 = EPI == EPI_PLAIN ? tc2::EPI_PLAIN : EPI == EPI_GYRO ? tc2::EPI_GYRO : EPI == EPI_ROWDOT ? tc2::EPI_ROWDOT : tc2::EPI_MOBIUS;
+    return tc2::launch_gemm2(e2, A, Bm, nullptr, q, s);
 }
 
 struct Ws {
@@ -1129,10 +1048,10 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
         float* rowsq = (float*)(ws + L.rowsq);
         tc::Params prm{};
         prm.D = mx_out; prm.M = B; prm.N = P; prm.K = F; prm.rowsq = rowsq;
-        int rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
+        int rc = tc::launch_auto<tc::EPI_PLAIN>(a16, b16, prm, s);
         if (rc != HVAE_OK) return rc;
         tc::k_mobius_rescale_rows<<<kNumSMs * 8, 256, 0, s>>>(mx_out, x2, rowsq, y, mxsq_out, B, P,
-                                                              (int)((P + tc::BN - 1) / tc::BN) * tc::CG, make_ball(c));
+                                                              tc::row_partial_planes(prm), make_ball(c));
         return check_launch();
     }
     // forward-only path, single pass over the output: |mx_b|^2 = x_b^T (M^T M) x_b from the Gram matrix, so the
@@ -1153,18 +1072,19 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
         if (rc != HVAE_OK) return rc;
         tc::k_rows_to_bf16<<<(unsigned)((F + 7) / 8), 256, 0, s>>>(g32, g16, nullptr, F, F);
     }
+    int q_planes = 0;
     {   // q_b = <x_b G, x_b> partials
         tc::Params prm{};
         prm.D = nullptr; prm.M = B; prm.N = F; prm.K = F; prm.xrow = x; prm.rowdot = rowdot;
-        int rc = tc::launch_gemm<tc::EPI_ROWDOT>(a16, g16, prm, s);
+        int rc = tc::launch_auto<tc::EPI_ROWDOT>(a16, g16, prm, s);
         if (rc != HVAE_OK) return rc;
+        q_planes = tc::row_partial_planes(prm);
     }
     float* rs = (float*)(ws + L.rowsq);  // (B,) row scale; the rowsq slot is unused on this path
-    tc::k_mobius_rowscale<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(x2, rowdot, (int)((F + tc::BN - 1) / tc::BN) * tc::CG, rs,
-                                                                      mxsq_out, B, make_ball(c));
+    tc::k_mobius_rowscale<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(x2, rowdot, q_planes, rs, mxsq_out, B, make_ball(c));
     tc::Params prm{};
     prm.D = y; prm.M = B; prm.N = P; prm.K = F; prm.rowscale = rs;
-    return tc::launch_gemm<tc::EPI_MOBIUS>(a16, b16, prm, s);
+    return tc::launch_auto<tc::EPI_MOBIUS>(a16, b16, prm, s);
 }
 
 // backward of y = mobius_matvec(M, x) on the tensor cores.  y and mxsq = |M x_b|^2 are the forward's outputs:
@@ -1192,7 +1112,7 @@ extern "C" int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, con
         tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(M, mt16, (int)P, (int)F);  // (P, F) -> (F, P)
         tc::Params prm{};
         prm.D = gx; prm.M = B; prm.N = F; prm.K = P; prm.axpy_x = x; prm.axpy_coef = gxc;
-        rc = tc::launch_gemm<tc::EPI_PLAIN>(gmx16, mt16, prm, s);
+        rc = tc::launch_auto<tc::EPI_PLAIN>(gmx16, mt16, prm, s);
         if (rc != HVAE_OK) return rc;
     }
     if (gM) {
@@ -1232,7 +1152,42 @@ extern "C" int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const f
     prm.D = out; prm.M = B; prm.N = P; prm.K = D; prm.x2 = x2; prm.p2 = p2; prm.bias = bias;
     const Ball b = make_ball(c);
     prm.gp.c = b.c; prm.gp.sc = b.sc; prm.gp.rsc = b.rsc; prm.gp.maxnorm = b.maxnorm; prm.gp.flags = flags;
-    return tc::launch_gemm<tc::EPI_GYRO>(a16, b16, prm, s);
+    return tc::launch_auto<tc::EPI_GYRO>(a16, b16, prm, s);
+}
+
+// GeodesicLayer / normdist2plane with a != p on the tensor cores (bf16 mode): ONE N-concatenated GEMM gives <x,p_j> and
+// <x,a_j> (tc_gemm2.cu, EPI_GEO), the scalar pair function with the reference's clamps / projection runs in the epilogue.
+// reference: hyperbolic_vae/layers.py:96-121 -> manifolds.py:41-65.
+extern "C" size_t hvae_geodesic_tc_workspace_bytes(int64_t B, int64_t D, int64_t P) {
+    if (B <= 0 || D <= 0 || P <= 0) return 0;
+    return tc::ws_layout(B, D, P).total + (size_t)P * D * 2 + 2 * (((size_t)P * 4 + 255) / 256 * 256) + 512;
+}
+extern "C" int hvae_geodesic_tc_fwd_f32(const float* x, const float* p, const float* a, const float* bias, float* out,
+                                        int64_t B, int64_t D, int64_t P, float c, uint32_t flags, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    if (tc_check(B, D, P) != HVAE_OK) return HVAE_ESHAPE;
+    if (!x || !p || !a || !out || !workspace) return HVAE_EARG;
+    const tc::Ws L = tc::ws_layout(B, D, P);
+    if (workspace_bytes < hvae_geodesic_tc_workspace_bytes(B, D, P)) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* x16 = (__nv_bfloat16*)(ws + L.a16);
+    auto* p16 = (__nv_bfloat16*)(ws + L.b16);
+    float* x2 = (float*)(ws + L.x2);
+    float* p2 = (float*)(ws + L.p2);
+    uint8_t* extra = ws + L.total;
+    auto* a16 = (__nv_bfloat16*)extra;
+    const size_t pvec = ((size_t)P * 4 + 255) / 256 * 256;
+    float* pa = (float*)(extra + ((size_t)P * D * 2 + 255) / 256 * 256);
+    float* an = (float*)((uint8_t*)pa + pvec);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, x16, x2, B, D);
+    tc::k_plane_pair_to_bf16<<<(unsigned)((P + 7) / 8), 256, 0, s>>>(p, a, p16, a16, p2, pa, an, P, D);
+    tc2::Params2 q{};
+    q.D = out; q.M = B; q.N = P; q.K = D; q.splits = 1;
+    q.x2 = x2; q.p2 = p2; q.pa = pa; q.an = an; q.bias = bias;
+    const Ball b = make_ball(c);
+    q.gp.c = b.c; q.gp.sc = b.sc; q.gp.rsc = b.rsc; q.gp.maxnorm = b.maxnorm; q.gp.flags = flags;
+    return tc2::launch_gemm2(tc2::EPI_GEO, x16, p16, a16, q, s);
 }
 
 // ---- fp32-accurate GEMM on the tensor cores (trunk dense layers; SURVEY 8f "next") ----------------------------------
@@ -1471,7 +1426,7 @@ extern "C" int hvae_gyroplane_tc_bwd_f32(const float* x, const float* p, const f
     {   // px = x p^T
         tc::Params prm{};
         prm.D = px; prm.M = B; prm.N = P; prm.K = D;
-        rc = tc::launch_gemm<tc::EPI_PLAIN>(a16, b16, prm, s);
+        rc = tc::launch_auto<tc::EPI_PLAIN>(a16, b16, prm, s);
         if (rc != HVAE_OK) return rc;
     }
     const int ncb = (int)((P + tc::kGbCols - 1) / tc::kGbCols);
@@ -1494,7 +1449,7 @@ extern "C" int hvae_gyroplane_tc_bwd_f32(const float* x, const float* p, const f
         tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(p, pt16, (int)P, (int)D);  // (P, D) -> (D, P)
         tc::Params prm{};
         prm.D = gx; prm.M = B; prm.N = D; prm.K = P; prm.axpy_x = x; prm.axpy_coef = rowcoef;
-        rc = tc::launch_gemm<tc::EPI_PLAIN>(cp, pt16, prm, s);
+        rc = tc::launch_auto<tc::EPI_PLAIN>(cp, pt16, prm, s);
         if (rc != HVAE_OK) return rc;
     }
     if (gp) {

@@ -1,0 +1,526 @@
+// K1-TC / K2-TC on CTA pairs: the dense contractions of the Mobius and gyroplane layers as cta_group::2 tcgen05 GEMMs
+// (bf16 operands, fp32 TMEM accumulators) with the hyperbolic math fused into the epilogue.
+//
+// reference: hyperbolic_vae/layers.py:145-147 (MobiusLayer -> geoopt mobius_matvec's tensordot),
+//            layers.py:193-210 (Distance2PoincareHyperplanes, a == p) and layers.py:96-121 -> manifolds.py:41-65
+//            (GeodesicLayer / normdist2plane, a != p: TWO inner products per (row, plane), <x,p> and <x,a>).
+//
+// Why a second kernel: with cta_group::1 a 128x128x16 MMA reads 8 KB of operands from shared memory every 64 cycles,
+// the SM's whole 128 B/clk, while TMA writes the next stage into the same memory (tc_gemm.cu measured 0.35 of the bf16
+// peak on config 5, nothing saturated).  Here two CTAs of a cluster (the two SMs of a TPC) own one 256 x 256 tile:
+// each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns), one thread of the leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16: 128 cycles), the hardware reads each half from its own SM.
+// Operand bytes per flop from shared memory and from L2 are both half of the 128x128 kernel's.
+//
+// Structure (cluster of 2 CTAs, one CTA per SM, persistent over tiles, 576 threads per CTA):
+//   warp 0      TMA producer (both CTAs): cp.async.bulk.tensor.2d.cta_group::2 -> own shared memory, 6-stage ring;
+//               the transaction bytes of BOTH CTAs complete on the LEADER's full barrier
+//   warp 1      MMA issuer (leader CTA only); tcgen05.commit.multicast frees the stage / publishes the accumulator in
+//               both CTAs
+//   warps 2-17  epilogue (both CTAs): each CTA drains its own 128 TMEM lanes x 256 columns (2 accumulator stages =
+//               all 512 TMEM columns: the epilogue of tile i overlaps the MMAs of tile i+1); 16x256b TMEM loads,
+//               fused math, sector-complete streaming stores; every epilogue warp of both CTAs releases the stage on
+//               the leader's barrier
+// GEO epilogue (a != p): the B tile is [128 rows of p | 128 rows of a] - the leader CTA stages the planes' p rows, the
+// peer their a rows - so accumulator columns j and 128 + j hold <x,p_j> and <x,a_j> of the same plane: one GEMM, N-concatenated.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "tc_common.cuh"
+#include "tc_gemm2.cuh"
+
+namespace hvae {
+namespace tc2 {
+
+using namespace hvae::tc;
+
+constexpr int BMC = 128;                     // rows per CTA
+constexpr int BNH = kTileN / 2;              // B rows staged per CTA
+constexpr int BK = kTcBK, UMMA_K = 16;
+constexpr int STAGES = 4, ACC_STAGES = 2;
+constexpr int EPI_WARPS = 4 * kCG;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr uint32_t TILE_A_BYTES = BMC * BK * 2, TILE_B_BYTES = BNH * BK * 2;
+constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+constexpr uint32_t COLC_BYTES = ACC_STAGES * kTileN * 16;  // per-column float4 constants
+constexpr uint32_t STG_BYTES = 32 * 128;                   // per-warp staging box of the TMA store: 32 rows x 32 fp32
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory");
+// A-resident schedule (K <= 512): a CTA keeps its 128 x K panel of A for ALL n-tiles of the m-block and streams only its
+// half of the B tiles.  The streaming schedule moves 512 KB from L2 per 256x256x512 tile - 12 TB/s at the measured mainloop
+// rate, the L2's whole read bandwidth, so the output stores (which also pass through L2) ADD to the kernel time
+// (measured: 0.72 ms without stores, 1.24 ms with; 8.6 + 4.3 GB at 10.4 TB/s).  Keeping A halves the operand traffic.
+// Shared memory: 8 x 16 KB panel + 3 x 16 KB B ring + 16 x 2 KB staging boxes (32 rows x 16 fp32, 64B swizzle).
+constexpr int ARES_KB = 8;                                 // k-blocks of the resident panel: K <= 512
+constexpr int ARES_NSB = 3;                                // B ring
+constexpr uint32_t STG_BYTES_ARES = 32 * 64;
+constexpr uint32_t SMEM_BYTES_ARES = ARES_KB * TILE_A_BYTES + ARES_NSB * TILE_B_BYTES + EPI_WARPS * STG_BYTES_ARES + 1024 + 256 + COLC_BYTES;
+static_assert(SMEM_BYTES_ARES <= 232448, "exceeds the 227 KB per-CTA shared memory");
+constexpr uint32_t TMEM_COLS = ACC_STAGES * kTileN;  // 512: the whole tensor memory
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 256 (the pair), N = 256
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kPairM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// the shared::cluster address of `addr` (an address in this CTA's shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    // default semantics (release at CTA scope): orders this thread's tcgen05.ld (after tcgen05.fence::before_thread_sync)
+    // without a cluster-scope fence - .release.cluster made every epilogue warp wait for its global stores to drain
+    // (MEMBAR, 18 % of the stall samples) before the MMA warp got the accumulator stage back
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// 2-CTA TMA load: data lands in THIS CTA's shared memory, the bytes are counted on the barrier `cluster_bar` (the leader's)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+// 32 lanes x 16 consecutive columns (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld16x(uint32_t addr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int EPI, bool ARES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+           const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_d, Params2 prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle wants 1024-byte aligned tiles (same offset in both CTAs)
+    constexpr int NSTG = ARES ? ARES_NSB : STAGES;                        // ring depth (ARES: the ring holds B tiles only)
+    constexpr uint32_t RING_BYTES = ARES ? ARES_KB * TILE_A_BYTES + ARES_NSB * TILE_B_BYTES : STAGES * STAGE_BYTES;
+    constexpr uint32_t SBYTES = ARES ? STG_BYTES_ARES : STG_BYTES;        // staging box per epilogue warp
+    constexpr int SB_COLS = ARES ? 16 : 32;                               // its width in fp32 columns
+    const uint32_t stg_base = base + RING_BYTES;                          // 1024-byte aligned (swizzle atom)
+    const uint32_t bars = stg_base + EPI_WARPS * SBYTES;
+    const uint32_t colc_base = bars + 256u;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (NSTG + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * NSTG + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * NSTG + ACC_STAGES + s); };
+    auto afull_bar = [&](int kb) { return bars + 8u * (2 * NSTG + 2 * ACC_STAGES + kb); };             // ARES: panel slice kb landed
+    auto aempty_bar = [&](int kb) { return bars + 8u * (2 * NSTG + 2 * ACC_STAGES + ARES_KB + kb); };  // ARES: ... may be overwritten
+    const uint32_t tmem_slot = bars + 8u * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB);
+    static_assert(8 * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB) + 4 <= 256, "barrier block");
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+    // streaming: [stage][A | B];  A-resident: [A panel: kb][B ring: stage]
+    auto a_tile = [&](int stage_or_kb) { return ARES ? base + (uint32_t)stage_or_kb * TILE_A_BYTES : base + (uint32_t)stage_or_kb * STAGE_BYTES; };
+    auto b_tile = [&](int stage) {
+        return ARES ? base + ARES_KB * TILE_A_BYTES + (uint32_t)stage * TILE_B_BYTES : base + (uint32_t)stage * STAGE_BYTES + TILE_A_BYTES;
+    };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    constexpr int TN = (EPI == EPI_GEO) ? kTileN / 2 : kTileN;   // output columns per tile
+    const int64_t m_tiles = (prm.M + kPairM - 1) / kPairM, n_tiles = (prm.N + TN - 1) / TN;
+    const int k_blocks = (int)((prm.K + BK - 1) / BK);
+    const int S = (!ARES && prm.splits > 1) ? prm.splits : 1;
+    // work unit: one output tile (x split) when streaming, one m-block with all its n-tiles when A-resident
+    const int64_t units = ARES ? m_tiles : m_tiles * n_tiles * S;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (EPI == EPI_GEO) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b2) : "memory");
+        if (EPI != EPI_ROWDOT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
+        for (int s = 0; s < NSTG; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EPI_WARPS); }
+        for (int kb = 0; kb < ARES_KB; ++kb) { mbar_init(afull_bar(kb), 1); mbar_init(aempty_bar(kb), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs allocates (and later frees) the pair's tensor memory
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own half of the B tile =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, pphase = 0;
+            const uint32_t lead_full = mapa(full_bar(0), 0), lead_afull = mapa(afull_bar(0), 0);
+            const CUtensorMap* mb = (EPI == EPI_GEO && rank) ? &map_b2 : &map_b;
+            for (int64_t u = pair; u < units; u += npairs) {
+                const int64_t tile = ARES ? u : u / S;
+                const int sp = ARES ? 0 : (int)(u % S);
+                const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
+                const int64_t mt = ARES ? u : tile / n_tiles;
+                const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+                const int m0 = (int)(mt * kPairM + rank * BMC);
+                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                    const int n0 = (EPI == EPI_GEO) ? (int)(nt * TN) : (int)(nt * kTileN + rank * BNH);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        if (ARES && nt == 0) {
+                            // slice kb of this m-block's panel, as soon as the previous m-block's last n-tile is done with it
+                            mbar_wait(aempty_bar(kb), pphase ^ 1u);
+                            if (rank == 0) mbar_expect_tx(afull_bar(kb), 2u * TILE_A_BYTES);
+                            tma_load_2d_2sm(a_tile(kb), &map_a, lead_afull + 8u * kb, kb * BK, m0);
+                        }
+                        mbar_wait(empty_bar(stage), phase ^ 1u);   // this CTA's copy of the stage has been consumed
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), ARES ? 2u * TILE_B_BYTES : 2u * STAGE_BYTES);
+                        if (!ARES) tma_load_2d_2sm(a_tile(stage), &map_a, lead_full + 8u * stage, kb * BK, m0);
+                        tma_load_2d_2sm(b_tile(stage), mb, lead_full + 8u * stage, kb * BK, n0);
+                        if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                pphase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (rank == 0 && lane == 0) {
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0, pphase = 0;
+            for (int64_t u = pair; u < units; u += npairs) {
+                const int64_t tile = ARES ? u : u / S;
+                const int sp = ARES ? 0 : (int)(u % S);
+                const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
+                const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                    mbar_wait(tempty_bar(as), aphase ^ 1u);   // the epilogues of BOTH CTAs have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * kTileN);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        if (ARES && nt == 0) {
+                            mbar_wait(afull_bar(kb), pphase);     // both CTAs' slices kb of the panel have landed
+                            tc_fence_after();
+                        }
+                        mbar_wait(full_bar(stage), phase);    // both CTAs' tiles of this stage have landed
+                        tc_fence_after();
+                        const uint64_t da = make_desc(a_tile(ARES ? kb : stage)), db = make_desc(b_tile(stage));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (uint32_t)(((kb - kb0) | k) != 0));
+                        umma_commit2(empty_bar(stage));       // frees the stage in both CTAs when these MMAs retire
+                        if (ARES && nt == nt1 - 1) umma_commit2(aempty_bar(kb));   // last use of the panel slice
+                        if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit2(tfull_bar(as));              // accumulator complete: wakes both epilogues
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+                }
+                pphase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warp w owns TMEM lane quarter (w % 4) and column group (w - 2) / 4 of this CTA's 128 rows =====
+        // 32x32b loads: lane l holds 32 consecutive columns of ONE row (TMEM lane 32q + l), so the row scalars are per
+        // thread.  Results go through a per-warp 4 KB shared-memory box (32 rows x 128 B, 128B-swizzled: conflict-free
+        // 16-byte writes) and leave as ONE TMA tensor store per box: full 128-byte lines, ragged edges clipped by the
+        // tensor map.  (Direct st.global from the 16x256b fragment layout - 8 rows x 32 B per instruction - ran at one
+        // L1 wavefront / L2 tag lookup per 32 bytes and added 0.54 ms to a 0.74 ms mainloop on config 5.)
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;
+        float4* colc = reinterpret_cast<float4*>(smem_raw + (colc_base - raw));   // [ACC_STAGES][kTileN]
+        const uint32_t stage_buf = stg_base + (uint32_t)(warp - 2) * SBYTES;      // this warp's staging box
+        const uint32_t lead_tempty = mapa(tempty_bar(0), 0);
+        int as = 0;
+        uint32_t aphase = 0;
+        constexpr int COLS = TN / kCG;   // 64 (32 for GEO)
+        for (int64_t u = pair; u < units; u += npairs) {
+          const int64_t tile = ARES ? u : u / S;
+          const int sp = ARES ? 0 : (int)(u % S);
+          const int64_t mt = ARES ? u : tile / n_tiles;
+          const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
+          const int64_t row_w = mt * kPairM + rank * BMC + q * 32;   // first row of this warp's 32
+          const int64_t grow = row_w + lane;
+          const bool rok = grow < prm.M;
+          float rs = 1.0f, x2r = 0.0f, cf = 0.0f;
+          if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && rok) rs = __ldg(prm.rowscale + grow);
+          if ((EPI == EPI_GYRO || EPI == EPI_GEO) && rok) x2r = __ldg(prm.x2 + grow);
+          const bool axpy = (EPI == EPI_PLAIN) && prm.axpy_x != nullptr;
+          if (axpy && rok) cf = __ldg(prm.axpy_coef + grow);
+          for (int64_t nt = nt0; nt < nt1; ++nt) {
+            float accr = 0.0f;
+            if (EPI == EPI_GYRO || EPI == EPI_GEO) {
+                // per-column constants of this tile, once per tile
+                if (et < TN) {
+                    const int64_t n = nt * TN + et;
+                    const bool in = n < prm.N;
+                    const float p2 = in ? __ldg(prm.p2 + n) : 0.0f;
+                    const float bb = (prm.bias && in) ? __ldg(prm.bias + n) : 0.0f;
+                    if (EPI == EPI_GYRO) {
+                        // lean path constants (see below): u = r (1 + c|p|^2), v = r |p|^2, r = 2 sqrt(c) / ((1 - c|p|^2)|p|)
+                        const float c = prm.gp.c, pn = sqrtf(p2);
+                        const float rcol = 2.0f * prm.gp.sc / ((1.0f - c * p2) * pn + kMinNorm);
+                        colc[as * kTileN + et] = make_float4(rcol * (1.0f + c * p2), rcol * p2, bb, p2);
+                    } else {
+                        colc[as * kTileN + et] = make_float4(p2, in ? __ldg(prm.pa + n) : 0.0f, in ? __ldg(prm.an + n) : 0.0f, bb);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            }
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = cg * COLS; cb < (cg + 1) * COLS; cb += 32) {
+                const bool last = cb + 32 >= (cg + 1) * COLS;
+                float v[32];
+#ifdef HVAE_EXPERIMENT
+                if (prm.dbg & 2) {
+                    if (last) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(lead_tempty + 8u * as); }
+                    continue;
+                }
+#endif
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN + cb), v);
+                const int64_t n0 = nt * TN + cb;
+                const float4* cc4 = colc + as * kTileN + cb;
+                if (EPI == EPI_GEO) {
+                    // columns cb .. cb+31 hold <x,p_j>, columns 128 + cb .. hold <x,a_j> of the same planes; in two halves
+                    // of 16 planes to bound the live registers
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float w[16];
+                        tmem_ld16x(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN + TN + cb + 16 * hf), w);
+                        if (last && hf == 1) {   // the accumulator stage is in registers: hand it back before the math
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(lead_tempty + 8u * as);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 cc = cc4[16 * hf + i];  // {p2, <p,a>, |a|, bias}
+                            GyroPairCtx kk;
+                            v[16 * hf + i] = gyro_pair_fwd(v[16 * hf + i], w[i], x2r, cc.x, cc.y, cc.z, prm.gp, kk) + cc.w;
+                        }
+                    }
+                } else if (last) {   // the accumulator stage is in registers: hand it back before the math and the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(lead_tempty + 8u * as);
+                }
+                if (EPI == EPI_PLAIN) {
+                    if (prm.rowsq) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) accr = fmaf(v[i], v[i], accr);   // out-of-range columns are zero-filled
+                    }
+                    if (prm.rowscale) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= rs;
+                    }
+                    if (axpy && rok) {
+                        const float* xr = prm.axpy_x + grow * prm.N + n0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (n0 + 4 * i + 4 <= prm.N) {   // N % 4 == 0 on this path
+                                const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + 4 * i));
+                                v[4 * i] = fmaf(cf, xv.x, v[4 * i]);
+                                v[4 * i + 1] = fmaf(cf, xv.y, v[4 * i + 1]);
+                                v[4 * i + 2] = fmaf(cf, xv.z, v[4 * i + 2]);
+                                v[4 * i + 3] = fmaf(cf, xv.w, v[4 * i + 3]);
+                            }
+                        }
+                    }
+                } else if (EPI == EPI_MOBIUS) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= rs;
+                } else if (EPI == EPI_ROWDOT) {
+                    if (rok) {
+                        const float* xr = prm.xrow + grow * prm.N + n0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (n0 + 4 * i + 4 <= prm.N) {
+                                const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + 4 * i));
+                                accr = fmaf(v[4 * i], xv.x, fmaf(v[4 * i + 1], xv.y, fmaf(v[4 * i + 2], xv.z, fmaf(v[4 * i + 3], xv.w, accr))));
+                            }
+                        }
+                    }
+                } else if (EPI == EPI_GYRO) {
+                    // geoopt signed distance with a == p.  With z = (-p) (+) x,
+                    //   <z, p> = (Bc <x,p> - A |p|^2) / den   and   1 - c|z|^2 = Bc (1 - c|x|^2) / den     (Bc = 1 - c|p|^2)
+                    // so den cancels and asinh's argument separates into row and column factors around <x,p>:
+                    //   y = 2 sqrt(c) [<x,p>(1 + c|p|^2) - |p|^2 (1 + c|x|^2)] / (Bc |p| (1 - c|x|^2)) = a_b (px u_j - w_b v_j)
+                    // (the clamps of the reference only bind for |p| ~ 1e-15, kept via the + MIN_NORM in u, v).  Other flag
+                    // combinations take the general pair function.
+                    const bool lean = (prm.gp.flags & ~(uint32_t)HVAE_GYRO_SIGNED) == 0u && (prm.gp.flags & HVAE_GYRO_SIGNED);
+                    const float rsc = prm.gp.rsc;
+                    const float ar = 1.0f / fmaxf(1.0f - prm.gp.c * x2r, 1e-30f);
+                    const float wr = -(1.0f + prm.gp.c * x2r);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float4 cc = cc4[i];  // {u, v, bias, p2}: the same address in every lane (broadcast)
+                        if (lean) {
+                            const float y = ar * fmaf(v[i], cc.x, wr * cc.y);
+                            v[i] = fmaf(asinh_fast(y), rsc, cc.z);
+                        } else {
+                            GyroPairCtx kk;
+                            v[i] = gyro_pair_fwd(v[i], v[i], x2r, cc.w, cc.w, sqrtf(cc.w), prm.gp, kk) + cc.z;
+                        }
+                    }
+                }
+                if (EPI != EPI_ROWDOT) {
+#ifdef HVAE_EXPERIMENT
+                    if (prm.dbg & 1) {
+                        float t = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t += v[i];
+                        if (t == 123.456f) prm.D[0] = t;
+                        continue;
+                    }
+#endif
+                    // SB_COLS-wide boxes: row `lane`, 16-byte chunk c at position c ^ swz(lane) - the pattern of
+                    // CU_TENSOR_MAP_SWIZZLE_128B (32 columns: c ^ (row % 8)) / SWIZZLE_64B (16 columns: c ^ ((row / 2) % 4))
+#pragma unroll
+                    for (int sb = 0; sb < 32 / SB_COLS; ++sb) {
+                        // the previous box of this warp must have been read out of shared memory by its TMA store
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        const uint32_t rowp = stage_buf + (uint32_t)lane * (uint32_t)(SB_COLS * 4);
+                        const int swz = ARES ? ((lane >> 1) & 3) : (lane & 7);
+#pragma unroll
+                        for (int c = 0; c < SB_COLS / 4; ++c) {
+                            const uint32_t addr = rowp + (uint32_t)((c ^ swz) << 4);
+                            const int e0 = sb * SB_COLS + 4 * c;
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[e0]), "f"(v[e0 + 1]),
+                                         "f"(v[e0 + 2]), "f"(v[e0 + 3])
+                                         : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+                        __syncwarp();
+                        const int64_t nb = n0 + sb * SB_COLS;
+                        if (lane == 0 && row_w < prm.M && nb < prm.N) {   // (a box wholly outside the matrix is not issued)
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                         ::"l"(&map_d), "r"(stage_buf), "r"((int)nb), "r"((int)row_w), "r"(sp)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                }
+            }
+            // per-(row, n-tile, column-group) partials: [(nt * kCG + cg)][M]
+            if ((EPI == EPI_PLAIN && prm.rowsq) || EPI == EPI_ROWDOT) {
+                float* dstp = (EPI == EPI_PLAIN) ? prm.rowsq : prm.rowdot;
+                if (rok) dstp[(nt * kCG + cg) * prm.M + grow] = accr;
+            }
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until read
+        __syncwarp();
+    }
+    tc_fence_before();
+    cluster_sync_all();   // both CTAs are done with the pair's tensor memory and with each other's barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// fp32 (S, M, N) row-major output -> 3-D tensor map with a {32, 32, 1} box (one 128-byte row segment x 32 rows), 128B swizzle
+static bool make_map_out(CUtensorMap* m, float* D, int64_t S, int64_t M, int64_t N, bool ares) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)S};
+    const cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)N * (cuuint64_t)M * 4};
+    const cuuint32_t box[3] = {ares ? 16u : 32u, 32, 1};   // A-resident schedule: 2 KB boxes (64B swizzle)
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               ares ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static int launch_t(const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_bfloat16* B2, const Params2& prm, cudaStream_t s) {
+    CUtensorMap ma, mb, mb2, md;
+    if (!make_map(&ma, A, prm.M, prm.K, BMC) || !make_map(&mb, B, prm.N, prm.K, BNH)) return HVAE_ELAUNCH;
+    if (!make_map(&mb2, B2 ? B2 : B, prm.N, prm.K, BNH)) return HVAE_ELAUNCH;
+    constexpr int TN = (EPI == EPI_GEO) ? kTileN / 2 : kTileN;
+    const int64_t m_tiles = (prm.M + kPairM - 1) / kPairM, n_tiles = (prm.N + TN - 1) / TN;
+    const int S = prm.splits > 1 ? prm.splits : 1;
+    // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over and enough m-blocks to
+    // keep every pair busy (the unit of work becomes a whole m-block)
+    bool ares = S == 1 && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= 2 * (kNumSMs / 2);
+#ifdef HVAE_EXPERIMENT
+    if (prm.dbg & 4) ares = false;
+#endif
+    // output: fp32 (S, M, N), boxes of 32 rows x 32 (16) columns through swizzled staging; ROWDOT writes no matrix
+    if (EPI != EPI_ROWDOT) {
+        if (!make_map_out(&md, prm.D, S, prm.M, prm.N, ares)) return HVAE_ELAUNCH;
+    } else {
+        md = ma;
+    }
+    // per-device attribute (a process may drive several GPUs): set on every launch, a cheap driver call
+    cudaFuncSetAttribute(k_tc_gemm2<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaFuncSetAttribute(k_tc_gemm2<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_ARES);
+    const int64_t units = ares ? m_tiles : m_tiles * n_tiles * S;
+    const int pairs = (int)(units < kNumSMs / 2 ? units : kNumSMs / 2);
+    if (ares)
+        k_tc_gemm2<EPI, true><<<2 * pairs, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, mb2, md, prm);
+    else
+        k_tc_gemm2<EPI, false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(ma, mb, mb2, md, prm);
+    return check_launch();
+}
+
+int launch_gemm2(int epi, const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_bfloat16* B2, const Params2& prm,
+                 cudaStream_t s) {
+    if (prm.M <= 0 || prm.N <= 0 || prm.K <= 0 || (prm.K % 8) != 0) return HVAE_ESHAPE;
+    if (epi != EPI_ROWDOT && (prm.N % 4) != 0) return HVAE_ESHAPE;   // TMA store: 16-byte row pitch
+    const int k_blocks = (int)((prm.K + BK - 1) / BK);
+    if (prm.splits > k_blocks) return HVAE_EARG;
+    if (prm.splits > 1 && (epi != EPI_PLAIN || prm.rowsq || prm.axpy_x || prm.rowscale)) return HVAE_EARG;
+    switch (epi) {
+        case EPI_PLAIN: return launch_t<EPI_PLAIN>(A, B, nullptr, prm, s);
+        case EPI_GYRO: return launch_t<EPI_GYRO>(A, B, nullptr, prm, s);
+        case EPI_ROWDOT: return launch_t<EPI_ROWDOT>(A, B, nullptr, prm, s);
+        case EPI_MOBIUS: return launch_t<EPI_MOBIUS>(A, B, nullptr, prm, s);
+        case EPI_GEO: return B2 ? launch_t<EPI_GEO>(A, B, B2, prm, s) : HVAE_EARG;
+    }
+    return HVAE_EARG;
+}
+
+}  // namespace tc2
+}  // namespace hvae
+
+#ifdef HVAE_EXPERIMENT
+// experiment build only (libhvae_b200_exp.so, scripts/tc2_probe.py): the pair kernel alone on bf16 operands
+extern "C" int hvae_exp_gemm2_bf16(const void* A, const void* B, float* D, const float* rowscale, int64_t M, int64_t N, int64_t K,
+                                   int epi, int dbg, void* stream) {
+    hvae::tc2::Params2 q{};
+    q.D = D; q.M = M; q.N = N; q.K = K; q.splits = 1; q.rowscale = rowscale; q.dbg = dbg;
+    return hvae::tc2::launch_gemm2(epi, (const __nv_bfloat16*)A, (const __nv_bfloat16*)B, nullptr, q, (cudaStream_t)stream);
+}
+#endif

@@ -1,0 +1,47 @@
+// Interface of the 2-CTA (cta_group::2) tcgen05 GEMM in tc_gemm2.cu: the big Mobius / gyroplane contractions
+// (config 5: B = 2^20, F/D = 512, P = 4096) on 256x256 output tiles owned by a CTA pair.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gyro_pair.cuh"
+#include "hvae_common.cuh"
+
+namespace hvae {
+namespace tc2 {
+
+enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4 };
+
+constexpr int kPairM = 256;   // output rows per CTA pair (128 per CTA)
+constexpr int kTileN = 256;   // accumulator columns per tile
+constexpr int kCG = 4;        // epilogue column groups per tile (row-partial layouts: [(n_tile * kCG + cg)][M])
+
+struct Params2 {
+    float* D;               // (M, N) row-major output (split-K: S partial planes of M x N)
+    int64_t M, N, K;        // N = output columns (GEO: planes; the B operand then has 2N rows in two maps)
+    int splits;             // > 1: split-K, unit (tile, s) writes its partial tile to D + s * M * N
+    const float* rowscale;  // PLAIN: optional (M,); MOBIUS: required (M,)
+    const float* axpy_x;    // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
+    const float* axpy_coef; //        (M,)
+    float* rowsq;           // PLAIN: optional [n_tiles * kCG][M] partial sums of acc^2
+    const float* x2;        // GYRO / GEO: (M,) |x|^2
+    const float* p2;        // GYRO / GEO: (N,) |p|^2
+    const float* pa;        // GEO: (N,) <p_j, a_j>
+    const float* an;        // GEO: (N,) |a_j|
+    const float* bias;      // GYRO / GEO: optional (N,)
+    GyroParams gp;
+    const float* xrow;      // ROWDOT: (M, N) fp32 rows dotted with the accumulator rows
+    float* rowdot;          // ROWDOT: [n_tiles * kCG][M] partial sums of acc * xrow
+#ifdef HVAE_EXPERIMENT
+    int dbg;                // experiment build only: 1 = skip the global stores, 2 = skip the whole drain
+#endif
+};
+
+// number of row-partial planes a (.., N) problem produces (rowsq / rowdot)
+inline int row_partials(int64_t N) { return (int)((N + kTileN - 1) / kTileN) * kCG; }
+
+// A (M, K) bf16 K-major, B (N, K) bf16 K-major (GEO: B = p rows, B2 = a rows, both (N, K)).  Returns HVAE_OK / error code.
+int launch_gemm2(int epi, const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_bfloat16* B2, const Params2& prm,
+                 cudaStream_t s);
+
+}  // namespace tc2
+}  // namespace hvae

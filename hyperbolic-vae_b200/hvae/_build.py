@@ -34,13 +34,28 @@ def _stamp(src):
     return h.hexdigest()
 
 
-def build(verbose=False, force=False, jobs=None):
+def build(verbose=False, force=False, jobs=None, experiment=False):
+    """experiment=True builds libhvae_b200_exp.so with -DHVAE_EXPERIMENT (debug knobs + probe entry points of the
+    tensor-core kernels; never loaded by the package unless HVAE_LIB_PATH points at it)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs, procs = [], []
+    global NVCC_FLAGS, LIB_PATH
+    flags0, lib0 = NVCC_FLAGS, LIB_PATH
+    if experiment:
+        NVCC_FLAGS = NVCC_FLAGS + ["-DHVAE_EXPERIMENT"]
+        LIB_PATH = os.path.join(LIB_DIR, "libhvae_b200_exp.so")
+    try:
+        return _build(nvcc, verbose, force, "exp_" if experiment else "")
+    finally:
+        NVCC_FLAGS, LIB_PATH = flags0, lib0
+
+
+def _build(nvcc, verbose, force, prefix):
+    objs, procs = [], []
     for src in sources():
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(OBJ_DIR, prefix + os.path.basename(src)[:-3] + ".o")
         stamp_file = obj + ".stamp"
         stamp = _stamp(src)
         objs.append(obj)
@@ -67,4 +82,4 @@ def build(verbose=False, force=False, jobs=None):
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, experiment="--exp" in sys.argv))

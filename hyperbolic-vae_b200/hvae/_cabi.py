@@ -7,7 +7,7 @@ import re
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libhvae_b200.so")
+LIB_PATH = os.environ.get("HVAE_LIB_PATH") or os.path.join(HERE, "_lib", "libhvae_b200.so")  # override: experiment builds
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "hvae_b200.h")
 
 _lib = None

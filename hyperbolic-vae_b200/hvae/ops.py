@@ -474,6 +474,9 @@ def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor],
     a_arg = None if (a is None or a is p) else _c(a)
     if a_arg is None and _tc_eligible(xr.shape[0], xr.shape[1], p.shape[0]):
         out = gyroplane_tc_fwd(xr, _c(p), None if bias is None else _c(bias), c, int(flags))
+    elif a_arg is not None and _tc_eligible(xr.shape[0], xr.shape[1], p.shape[0]) and not torch.is_grad_enabled():
+        # a != p (GeodesicLayer): tensor-core forward (inference / evaluation; the a != p backward is the fp32 kernels')
+        out = geodesic_tc_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
     else:
         out = gyroplane_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
     return out.view(*lead, p.shape[0])
@@ -966,6 +969,25 @@ def gyroplane_tc_fwd(x: Tensor, p: Tensor, bias: Optional[Tensor], c: float, fla
 
 @gyroplane_tc_fwd.register_fake
 def _(x, p, bias, c, flags):
+    return x.new_empty(x.shape[0], p.shape[0])
+
+
+@_op("hvae::geodesic_tc_fwd", mutates_args=())
+def geodesic_tc_fwd(x: Tensor, p: Tensor, a: Tensor, bias: Optional[Tensor], c: float, flags: int) -> Tensor:
+    """a != p gyroplane (GeodesicLayer) on the tensor cores: one N-concatenated cta_group::2 GEMM + fused pair epilogue."""
+    C.require_cuda(x, p, a, bias)
+    B, D = x.shape
+    P = p.shape[0]
+    out = x.new_empty(B, P)
+    ws = _workspace(C.lib().hvae_geodesic_tc_workspace_bytes(B, D, P), x.device)
+    C.call("hvae_geodesic_tc_fwd_f32", C.ptr(x), C.ptr(p), C.ptr(a), C.ptr(bias), C.ptr(out), B, D, P, c, flags, C.ptr(ws),
+           ws.numel(), C.stream())
+    C.launch_count += 2
+    return out
+
+
+@geodesic_tc_fwd.register_fake
+def _(x, p, a, bias, c, flags):
     return x.new_empty(x.shape[0], p.shape[0])
 
 

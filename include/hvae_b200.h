@@ -174,6 +174,14 @@ int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, const float* y
                                   size_t workspace_bytes, void* stream);
 int hvae_gyroplane_tc_fwd_f32(const float* x, const float* p, const float* bias, float* out, int64_t B, int64_t D,
                               int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+/* GeodesicLayer / normdist2plane with a != p (hyperbolic_vae/layers.py:96-121 -> manifolds.py:41-65) on the tensor
+ * cores: <x,p_j> and <x,a_j> come from ONE N-concatenated cta_group::2 GEMM (the B tile of a CTA pair is 128 rows of p
+ * and the same planes' 128 rows of a), the pair function with the reference's clamps and projection (HVAE_GYRO_PVAE) is
+ * the epilogue.  p: (P,D) Mobius-subtracted point, a: (P,D) normal; bf16 operands, 1e-2 tolerance.  D % 8 == 0. */
+size_t hvae_geodesic_tc_workspace_bytes(int64_t B, int64_t D, int64_t P);
+int hvae_geodesic_tc_fwd_f32(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B,
+                             int64_t D, int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes,
+                             void* stream);
 /* backward of the above (a == p): px = x p^T is recomputed by a GEMM, a tile kernel forms the pair gradients
  * (bf16 coefficient matrix + row / column scalar sums), then gx = CP p + rowcoef x and gp = CP^T x + colcoef p are two
  * more GEMMs with the axpy fused into their epilogues.  B, D, P multiples of 8; gx or gp may be NULL.  The bias

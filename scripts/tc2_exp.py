@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Experiment driver for the CTA-pair tcgen05 kernel (needs the experiment build: python hyperbolic-vae_b200/hvae/_build.py
+--exp; run with HVAE_LIB_PATH=hyperbolic-vae_b200/hvae/_lib/libhvae_b200_exp.so).  Times the kernel alone on bf16
+operands with the drain / the stores switched off, next to cuBLAS on the same shape.  Prints one JSON object."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "hyperbolic-vae_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    e.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    logB = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+    only = sys.argv[2] if len(sys.argv) > 2 else ""
+    L = ctypes.CDLL(os.environ["HVAE_LIB_PATH"])
+    f = L.hvae_exp_gemm2_bf16
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64] * 3 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    dev = torch.device("cuda")
+    M, N, K = 1 << logB, 4096, 512
+    A = (torch.randn(M, K, device=dev) * 0.05).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    D = torch.empty(M, N, device=dev)
+    rs = torch.rand(M, device=dev) + 0.5
+    st = torch.cuda.current_stream().cuda_stream
+    out = {"M": M, "N": N, "K": K}
+    fl = 2.0 * M * N * K
+
+    def run(epi, dbg):
+        rc = f(A.data_ptr(), B.data_ptr(), D.data_ptr(), rs.data_ptr(), M, N, K, epi, dbg, st)
+        assert rc == 0, rc
+
+    if only == "ncu":
+        run(3, 0)
+        torch.cuda.synchronize()
+        return
+    # dbg bits: 1 = no stores, 2 = no drain, 4 = force the streaming schedule (default: A-resident when eligible)
+    for name, epi, dbg in (("mobius_ares_full", 3, 0), ("mobius_ares_nostore", 3, 1), ("mobius_ares_nodrain", 3, 2),
+                           ("mobius_stream_full", 3, 4), ("mobius_stream_nodrain", 3, 6), ("plain_ares_full", 0, 0)):
+        ms = timeit(lambda: run(epi, dbg))
+        out[name] = {"ms": ms, "tflops": fl / ms / 1e9}
+    # correctness of the full variant against cuBLAS
+    run(3, 0)
+    ref = (A.float() @ B.float().t()) * rs[:, None] if M <= (1 << 18) else None
+    if ref is not None:
+        out["max_rel_err"] = float((D - ref).abs().max() / ref.abs().max())
+        del ref
+    ms = timeit(lambda: torch.matmul(A, B.t()))
+    out["cublas_bf16_out_bf16"] = {"ms": ms, "tflops": fl / ms / 1e9}
+    Df = torch.empty(M, N, device=dev)
+    ms = timeit(lambda: torch.mm(A.float()[:1], B.float().t()[:, :1]))  # keep allocator warm (tiny)
+    # a pure write of the output (the HBM floor of the store phase)
+    ms = timeit(lambda: Df.fill_(1.0))
+    out["fill_fp32_output"] = {"ms": ms, "gbs": M * N * 4 / ms / 1e6}
+    ms = timeit(lambda: Df.copy_(D))
+    out["copy_fp32_output"] = {"ms": ms, "gbs": 2 * M * N * 4 / ms / 1e6}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -39,3 +39,27 @@ def golden_models():
     import torch
 
     return torch.load(os.path.join(ROOT, "tests", "golden", "models_golden.pt"), weights_only=False)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the strict-1e-5 audit of every parity comparison made in this session (tests/util_parity.py)."""
+    try:
+        import json
+
+        import util_parity as U
+
+        if not U.AUDIT:
+            return
+        tot = dict(comparisons=len(U.AUDIT), elements=sum(r["n"] for r in U.AUDIT),
+                   strict_fail=sum(r["strict_fail"] for r in U.AUDIT), well_elements=sum(r["n_well"] for r in U.AUDIT),
+                   strict_fail_well=sum(r["strict_fail_well"] for r in U.AUDIT),
+                   worst_well=max(r["worst_well"] for r in U.AUDIT), worst_all=max(r["worst_all"] for r in U.AUDIT))
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        worst = sorted(U.AUDIT, key=lambda r: -r["worst_all"])[:40]
+        with open(os.path.join(out, "parity_audit_%d.json" % os.getpid()), "w") as f:
+            json.dump(dict(total=tot, worst=worst, strict_rtol=U.STRICT_RTOL), f, indent=1)
+        print("\n[parity audit] %(comparisons)d comparisons, %(elements)d elements: %(strict_fail)d fail plain 1e-5*scale "
+              "(%(strict_fail_well)d of %(well_elements)d well-conditioned); worst ratio well %(worst_well).3g / all %(worst_all).3g" % tot)
+    except Exception as ex:  # the audit never breaks a run
+        print("[parity audit] not written: %s" % ex)

@@ -188,13 +188,83 @@ def make_models():
     return out
 
 
+def make_riemannian():
+    """a-7: run the reference's OWN distributions/old_pvae_riemannian_normal.py:12-52 (over the pvae_min / geoopt_min
+    shims) and record what it drew and computed: the clamp of sigma to [0.1, 7], the (alpha, r) of its rsample (captured
+    by wrapping the two sampler calls on the instance; the reference code itself runs verbatim), z = expmap_polar(mu,
+    alpha, r), the implicit-reparameterisation gradients, log_prob and its gradients, and the log-normaliser."""
+    rl.load()
+    RN = importlib.import_module("hyperbolic_vae.distributions.old_pvae_riemannian_normal")
+    import pvae.manifolds as PM
+
+    cases = []
+    for c in (0.5, 1.0, 2.0):
+        for D in (2, 5, 10):
+            torch.manual_seed(4200 + int(c * 10) + D)
+            ball = PM.PoincareBall(D, c)
+            B = 24
+            mu = ball.expmap0(torch.randn(B, D) * 0.6).detach().requires_grad_(True)
+            # (pvae's fixed-hull ARS raises "initial anchor points must span mode" for sigma >~ 2 at D = 10: sampled rows stay
+            # below that; the upper clamp is exercised through log_prob, which needs no sampling)
+            scale = torch.rand(B, 1) * 1.5 + 0.3
+            scale[0] = 0.05   # below the clamp -> 0.1
+            scale.requires_grad_(True)
+            q = RN.RiemannianNormal(mu, scale, ball)
+            drawn = {}
+            d_sample, r_rsample = q.direction.sample, q.radius.rsample
+
+            def rec_alpha(shape, _f=d_sample):
+                drawn["alpha"] = _f(shape)
+                return drawn["alpha"]
+
+            def rec_radius(shape=torch.Size(), _f=r_rsample):
+                drawn["r"] = _f(shape)
+                return drawn["r"]
+
+            q.direction.sample, q.radius.rsample = rec_alpha, rec_radius
+            z = q.rsample(torch.Size([1]))
+            g = torch.Generator().manual_seed(7)
+            gz_up = torch.randn(z.shape, generator=g)
+            z.backward(gz_up)
+            rec = dict(c_ctor=c, c=float(ball.c), D=D, B=B, mu=plain(mu), scale=plain(scale), scale_clamped=plain(q.scale),
+                       alpha=plain(drawn["alpha"]), r=plain(drawn["r"]), z=plain(z), gz_up=gz_up, gmu_z=plain(mu.grad),
+                       gscale_z=plain(scale.grad), logZ=plain(q.radius.log_normalizer))
+            mu.grad = None
+            scale.grad = None
+            zz = plain(z).clone().requires_grad_(True)
+            scale2 = plain(scale).clone()
+            scale2[1] = 9.0   # above the clamp -> 7.0
+            scale2.requires_grad_(True)
+            q2 = RN.RiemannianNormal(mu, scale2, ball)
+            lp = q2.log_prob(zz)
+            glp = torch.randn(lp.shape, generator=g)
+            lp.backward(glp)
+            rec.update(scale_lp=plain(scale2), scale_lp_clamped=plain(q2.scale), logZ_lp=plain(q2.radius.log_normalizer),
+                       log_prob=plain(lp), glp_up=glp, gmu_lp=plain(mu.grad), gscale_lp=plain(scale2.grad), gz_lp=plain(zz.grad))
+            # prior-style construction: origin loc, one scalar sigma (pvae prior_iso); log_prob of the same z
+            mu.grad = None
+            scale.grad = None
+            p0 = RN.RiemannianNormal(ball.zero, torch.full((1, 1), 1.3), ball)
+            rec["log_prob_prior"] = plain(p0.log_prob(plain(z)))
+            rec["prior_sigma"] = 1.3
+            cases.append(rec)
+    return cases
+
+
 def main():
-    ops = make_ops()
-    models = make_models()
-    torch.save(ops, os.path.join(HERE, "ops_golden.pt"))
-    torch.save(models, os.path.join(HERE, "models_golden.pt"))
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in ("", "ops"):
+        torch.save(make_ops(), os.path.join(HERE, "ops_golden.pt"))
+    if only in ("", "models"):
+        torch.save(make_models(), os.path.join(HERE, "models_golden.pt"))
+    if only in ("", "riemannian"):
+        torch.save(make_riemannian(), os.path.join(HERE, "riemannian_golden.pt"))
+    if only in ("", "optim"):
+        torch.save(make_optim(), os.path.join(HERE, "optim_golden.pt"))
     man = {}
-    for fn in ("ops_golden.pt", "models_golden.pt"):
+    for fn in ("ops_golden.pt", "models_golden.pt", "riemannian_golden.pt", "optim_golden.pt"):
+        if not os.path.exists(os.path.join(HERE, fn)):
+            continue
         with open(os.path.join(HERE, fn), "rb") as f:
             man[fn] = {"sha256": hashlib.sha256(f.read()).hexdigest(), "bytes": os.path.getsize(os.path.join(HERE, fn))}
     man["generator"] = "tests/golden/make_golden.py (reference files executed verbatim over oracle shims)"

@@ -201,3 +201,41 @@ def test_layers_train_in_bf16_mode():
     for n, b in res["fp32"].items():
         a = res["bf16"][n]
         assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 2e-2, n
+
+
+# GeodesicLayer (a != p; pvae clamps + projected mobius_add) on the tensor cores: one N-concatenated cta_group::2 GEMM
+# (<x,p>, <x,a>) + the pair epilogue, against the float64 oracle of the reference's layer (layers.py:96-121).
+@pytest.mark.parametrize("B,D,P,wn", [(1024, 64, 128, False), (4096, 512, 4096, False), (2000, 256, 520, True), (1280, 128, 300, False)])
+def test_geodesic_tc_forward(B, D, P, wn):
+    import hvae
+    from hvae import layers as HL
+    from hvae import ops
+    from oracle import ref_port as R
+
+    torch.manual_seed(B + D + P)
+    c = 1.0
+    lay = HL.GeodesicLayer(D, P, hvae.PoincareBall(c), weight_norm=wn)
+    ob64 = _oball(c).double()
+    ref_l = R.GeodesicLayer(D, P, ob64, weight_norm=wn).double()
+    with torch.no_grad():
+        ref_l._weight.copy_(lay._weight.double())
+        ref_l._bias.copy_(lay._bias.double())
+    x = _oball(c).expmap0(torch.randn(B, D) * 0.6 / D ** 0.5).detach()
+    with torch.no_grad():
+        ref = ref_l(x.double())
+        pw = ref_l.weight.float()
+    lay = lay.cuda()
+    ops.set_gemm_mode("bf16")
+    try:
+        with torch.no_grad():
+            n0 = hvae._cabi.launch_count
+            out = lay(x.cuda())
+            torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_mode("fp32")
+    pk = pair_kappa(c, x, pw)
+    err = (out.double().cpu() - ref).abs()
+    bound = 1e-2 * ref.abs() + 1e-2 * pk
+    assert bool((err <= bound).all()), float((err / bound).max())
+    assert float(err.max()) < 0.05 * float(ref.abs().max()) + 1e-2
+    assert hvae._cabi.launch_count - n0 >= 3   # weight prep + the tensor-core entry (not the SIMT gyroplane)
