@@ -63,3 +63,10 @@ def pytest_sessionfinish(session, exitstatus):
               "(%(strict_fail_well)d of %(well_elements)d well-conditioned); worst ratio well %(worst_well).3g / all %(worst_all).3g" % tot)
     except Exception as ex:  # the audit never breaks a run
         print("[parity audit] not written: %s" % ex)
+
+
+@pytest.fixture(scope="session")
+def golden_riemannian():
+    import torch
+
+    return torch.load(os.path.join(ROOT, "tests", "golden", "riemannian_golden.pt"), weights_only=False)

@@ -186,3 +186,65 @@ def test_pvae_mnist_step_matches_oracle(fused):
     assert set(grads) == set(G32), set(grads) ^ set(G32)
     for k in G32:
         assert_parity(grads[k], G32[k], G64[k], what="pvae grad " + k, rtol=5e-5, atol=1e-6, norm_relative=True, slack_mult=2.0)
+
+
+def test_riemannian_normal_golden(golden_riemannian):
+    """a-7 against the fixture minted by running the reference's OWN old_pvae_riemannian_normal.py (its draws of
+    (alpha, r) recorded and injected here): sigma clamp [0.1, 7] incl. its zero gradient, z = expmap_polar, the implicit
+    reparameterisation gradient, log_prob (+ gradients) with a clamped-high row, the log-normaliser, the prior form."""
+    import hvae
+    from hvae.distributions import RiemannianNormal
+    from oracle import ref_port as R
+    from oracle.geoopt_min.manifolds.stereographic import math as gmath
+
+    for g in golden_riemannian:
+        D, c = g["D"], g["c_ctor"]
+
+        def oracle64():
+            ball = _oracle_pball(D, c, torch.float64)
+            mu = g["mu"].double().requires_grad_(True)
+            sg = g["scale"].double().requires_grad_(True)
+            mu2, sg2, zz = g["mu"].double().requires_grad_(True), g["scale_lp"].double().requires_grad_(True), g["z"].double().requires_grad_(True)
+            with gmath.fp32_semantics(True):
+                q = R.RiemannianNormal(mu, sg, ball)
+                z = q.rsample(torch.Size([1]), alpha=g["alpha"].double(), r=g["r"].detach().double())
+                z.backward(g["gz_up"].double())
+                q2 = R.RiemannianNormal(mu2, sg2, ball)
+                lp = q2.log_prob(zz)
+                lp.backward(g["glp_up"].double())
+                lz = q.radius.log_normalizer
+            return dict(z=z.detach(), gmu_z=mu.grad, gscale_z=sg.grad, log_prob=lp.detach(), gmu_lp=mu2.grad, gscale_lp=sg2.grad,
+                        gz_lp=zz.grad, logZ=lz.detach())
+
+        o64 = oracle64()
+        ball = hvae.PoincareBall(c)
+        assert ball.c_value == pytest.approx(g["c"], rel=1e-7)
+        mu, sg = g["mu"].cuda().requires_grad_(True), g["scale"].cuda().requires_grad_(True)
+        q = RiemannianNormal(mu, sg, ball)
+        assert torch.equal(q.scale.detach().cpu(), g["scale_clamped"])
+        z = q.rsample(torch.Size([1]), alpha=g["alpha"].cuda(), r=g["r"].detach().cuda())
+        z.backward(g["gz_up"].cuda())
+        tag = "RN golden c=%s D=%d " % (c, D)
+        kap = kappa(g["c"], o64["z"], g["mu"])
+        assert_parity(q.radius.log_normalizer, g["logZ"], o64["logZ"], what=tag + "logZ", rtol=1e-5, atol=1e-5, row_relative=False)
+        assert_parity(z, g["z"], o64["z"], what=tag + "z", rtol=rtol_val(kap, 2e-5).view(1, -1, 1), atol=2e-6)
+        assert_parity(mu.grad, g["gmu_z"], o64["gmu_z"], what=tag + "gmu(z)", rtol=rtol_grad(kap, 5e-5), atol=2e-5, slack_mult=2.0)
+        assert_parity(sg.grad, g["gscale_z"], o64["gscale_z"], what=tag + "gsigma(z)", rtol=rtol_grad(kap, 5e-5), atol=2e-5,
+                      row_relative=False, slack_mult=2.0)
+        assert float(sg.grad[0].abs().max()) == 0.0   # sigma below the clamp: no gradient, as in the reference
+        mu2, sg2 = g["mu"].cuda().requires_grad_(True), g["scale_lp"].cuda().requires_grad_(True)
+        zz = g["z"].cuda().requires_grad_(True)
+        q2 = RiemannianNormal(mu2, sg2, ball)
+        assert torch.equal(q2.scale.detach().cpu(), g["scale_lp_clamped"])
+        lp = q2.log_prob(zz)
+        lp.backward(g["glp_up"].cuda())
+        assert_parity(lp, g["log_prob"], o64["log_prob"], what=tag + "log_prob", rtol=rtol_val(kap, 2e-5).view(1, -1, 1), atol=2e-5,
+                      row_relative=False, slack_mult=2.0)
+        assert_parity(mu2.grad, g["gmu_lp"], o64["gmu_lp"], what=tag + "gmu(lp)", rtol=rtol_grad(kap, 5e-5), atol=2e-5, slack_mult=2.0)
+        assert_parity(sg2.grad, g["gscale_lp"], o64["gscale_lp"], what=tag + "gsigma(lp)", rtol=rtol_grad(kap, 5e-5), atol=2e-5,
+                      row_relative=False, slack_mult=2.0)
+        assert float(sg2.grad[1].abs().max()) == 0.0  # sigma above the clamp
+        assert_parity(zz.grad, g["gz_lp"], o64["gz_lp"], what=tag + "gz(lp)", rtol=rtol_grad(kap, 5e-5).view(1, -1, 1), atol=2e-5, slack_mult=2.0)
+        p0 = RiemannianNormal(torch.zeros(1, D, device="cuda"), torch.full((1, 1), g["prior_sigma"], device="cuda"), ball)
+        lp0 = p0.log_prob(g["z"].cuda())
+        torch.testing.assert_close(lp0.cpu(), g["log_prob_prior"], rtol=2e-5, atol=2e-4)

@@ -3,6 +3,7 @@ fixtures minted from the reference's OWN files (tests/golden/make_golden.py).  S
 the same CPU => tolerance is a few ulp."""
 import hashlib
 import json
+import math
 import os
 
 import pytest
@@ -29,7 +30,7 @@ def close_norm(a, b, tol=1e-4):
 
 def test_manifest_hashes():
     man = json.load(open(os.path.join(HERE, "golden", "MANIFEST.json")))
-    for fn in ("ops_golden.pt", "models_golden.pt"):
+    for fn in ("ops_golden.pt", "models_golden.pt", "riemannian_golden.pt"):
         h = hashlib.sha256(open(os.path.join(HERE, "golden", fn), "rb").read()).hexdigest()
         assert h == man[fn]["sha256"]
 
@@ -154,3 +155,70 @@ def test_ref_port_matches_reference_live():
     z = R.WrappedNormal(mu, sc, ball).rsample(torch.Size([1]), eps=eps)
     close(z, z_ref)
     close(R.WrappedNormal(mu, sc, ball).log_prob(z), W.WrappedNormal(mu, sc, ball).log_prob(z_ref), rtol=1e-5, atol=1e-6)
+
+
+# ---- a-7: RiemannianNormal / HyperbolicRadius ---------------------------------------------------------------------------
+def test_riemannian_normal_against_golden(golden_riemannian):
+    """The travelling restatement (ref_port.RiemannianNormal, injected alpha / r) against what the reference's OWN
+    distributions/old_pvae_riemannian_normal.py computed for the draws it made (tests/golden/make_golden.py)."""
+    from oracle.pvae_min.manifolds import PoincareBall as PBall
+
+    for g in golden_riemannian:
+        ball = PBall(g["D"], g["c_ctor"])
+        assert float(ball.c) == g["c"]
+        mu, sc = g["mu"].clone().requires_grad_(True), g["scale"].clone().requires_grad_(True)
+        q = R.RiemannianNormal(mu, sc, ball)
+        close(q.scale, g["scale_clamped"])                      # clamp [0.1, 7]
+        assert float(q.scale.min()) == pytest.approx(0.1)
+        close(q.radius.log_normalizer, g["logZ"], rtol=1e-6)
+        z = q.rsample(torch.Size([1]), alpha=g["alpha"], r=g["r"].detach())
+        close(z, g["z"])
+        gmu, gsc = _bwd(z, g["gz_up"], [mu, sc])
+        close(gmu, g["gmu_z"], rtol=1e-5, atol=1e-6)
+        close(gsc, g["gscale_z"], rtol=1e-5, atol=1e-6)
+        assert float(gsc[0].abs().max()) == 0.0                # the clamped row carries no gradient
+        mu2, sc2, zz = g["mu"].clone().requires_grad_(True), g["scale_lp"].clone().requires_grad_(True), g["z"].clone().requires_grad_(True)
+        q2 = R.RiemannianNormal(mu2, sc2, ball)
+        close(q2.scale, g["scale_lp_clamped"])
+        assert float(q2.scale.max()) == pytest.approx(7.0)
+        lp = q2.log_prob(zz)
+        close(lp, g["log_prob"], rtol=1e-5, atol=1e-5)
+        gmu, gsc, gz = _bwd(lp, g["glp_up"], [mu2, sc2, zz])
+        close(gmu, g["gmu_lp"], rtol=1e-4, atol=1e-5)
+        close(gsc, g["gscale_lp"], rtol=1e-4, atol=1e-5)
+        close(gz, g["gz_lp"], rtol=1e-4, atol=1e-5)
+        p0 = R.RiemannianNormal(ball.zero, torch.full((1, 1), g["prior_sigma"]), ball)
+        close(p0.log_prob(g["z"]), g["log_prob_prior"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dim,c", [(2, 1.0), (3, 0.5), (5, 1.0), (10, 1.0), (10, 2.0), (16, 0.7)])
+def test_radius_normaliser_and_cdf_against_quadrature(dim, c):
+    """pvae_min's closed-form log-normaliser (signed log-sum-exp over erf terms) and radial CDF against brute-force
+    quadrature of rho(r) ~ exp(-r^2/2s^2) (sinh(sqrt(c) r)/sqrt(c))^(dim-1) in float64 - the third-party arithmetic has
+    no copy here to diff against, so its maths is pinned to the integral it claims to evaluate."""
+    from oracle.pvae_min.distributions import hyperbolic_radius as hr
+
+    ct = torch.tensor(c, dtype=torch.float64)
+    for s in (0.1, 0.35, 1.0, 2.5, 7.0):
+        if dim >= 10 and s < 0.3:
+            continue  # the alternating series loses digits there (in pvae too); covered by the GPU tests' range
+        sc = math.sqrt(c)
+        n = dim - 1
+        mode = 0.5 * (n * sc * s * s + math.sqrt((n * sc * s * s) ** 2 + 4 * n * s * s)) if n else 0.0
+        hi = mode + 14 * s + 1.0
+        r = torch.linspace(0, hi, 400001, dtype=torch.float64)
+        logf = -r.pow(2) / (2 * s * s) + n * (torch.log(torch.sinh((sc * r).clamp_max(300)).clamp_min(1e-300)) - 0.5 * math.log(c))
+        if n:
+            big = sc * r > 300
+            logf = torch.where(big, -r.pow(2) / (2 * s * s) + n * (sc * r - math.log(2) - 0.5 * math.log(c)), logf)
+        m = logf.max()
+        f = torch.exp(logf - m)
+        Z = torch.trapezoid(f, r)
+        logZ_q = float(m + Z.log())
+        logZ = float(hr.log_normalizer(torch.tensor([[s]], dtype=torch.float64), ct, dim))
+        assert abs(logZ - logZ_q) <= 1e-7 * max(1.0, abs(logZ_q)), (dim, c, s, logZ, logZ_q)
+        cum = torch.cumulative_trapezoid(f, r) / Z
+        for frac in (0.1, 0.5, 0.9):
+            i = int(torch.searchsorted(cum, torch.tensor(frac, dtype=torch.float64)))
+            F = float(hr.cdf_r(r[i + 1].view(1, 1), torch.tensor([[s]], dtype=torch.float64), ct, dim))
+            assert abs(F - float(cum[i])) <= 2e-6, (dim, c, s, frac, F, float(cum[i]))
