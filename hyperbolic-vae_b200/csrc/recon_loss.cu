@@ -74,6 +74,111 @@ k_bce_logits_rows_bwd(const float* __restrict__ logits, const float* __restrict_
     }
 }
 
+// ---- generic reconstruction heads: per-(sample, row) sums over the feature axis ---------------------
+//   HVAE_RECON_MSE          sum_n (in - x)^2                      F.mse_loss(x_hat, x, "sum")       models/vae_hyperbolic.py:219
+//   HVAE_RECON_SIGMOID_MSE  sum_n (sigmoid(in) - x)^2             decoder's final nn.Sigmoid fused  ...rnaseq.py:57,107
+//   HVAE_RECON_RB_LOGITS    -RelaxedBernoulli(T, logits=in).log_prob(x)   models/vae_hyperbolic.py:224-225
+//   HVAE_RECON_RB_PROBS     -RelaxedBernoulli(T, probs=in).log_prob(x)    ...gyroplane_decoder.py:121-122
+//   HVAE_RECON_RB_SIGMOID   the same with probs = sigmoid(in) (the decoder's final nn.Sigmoid fused)
+// RelaxedBernoulli = torch.distributions semantics (LogitRelaxedBernoulli + SigmoidTransform): probs clamped to
+// [eps, 1-eps] (eps = 2^-23), value to [tiny, 1-eps];  with y = logit(v), d = logits - T y:
+//   -log_prob = -log T - d + 2 softplus(d) - softplus(-y) - softplus(y),      d(-log_prob)/dlogits = 2 sigmoid(d) - 1.
+__device__ __forceinline__ float softplus_acc(float v) { return fmaxf(v, 0.0f) + log1pf(expf(-fabsf(v))); }
+
+template <int KIND>
+__device__ __forceinline__ float recon_term(float in, float x, float T, float logT) {
+    if (KIND == HVAE_RECON_MSE) { const float d = in - x; return d * d; }
+    if (KIND == HVAE_RECON_SIGMOID_MSE) { const float d = sigmoid_acc(in) - x; return d * d; }
+    constexpr float eps = 1.1920928955078125e-07f, tiny = 1.17549435e-38f;
+    float lg = in;
+    if (KIND != HVAE_RECON_RB_LOGITS) {
+        const float p = (KIND == HVAE_RECON_RB_SIGMOID) ? sigmoid_acc(in) : in;
+        const float ps = fminf(fmaxf(p, eps), 1.0f - eps);
+        lg = logf(ps) - log1pf(-ps);
+    }
+    const float v = fminf(fmaxf(x, tiny), 1.0f - eps);
+    const float y = logf(v) - log1pf(-v);
+    const float d = lg - y * T;
+    return -logT - d + 2.0f * softplus_acc(d) - softplus_acc(-y) - softplus_acc(y);
+}
+// d term / d in
+template <int KIND>
+__device__ __forceinline__ float recon_grad(float in, float x, float T) {
+    if (KIND == HVAE_RECON_MSE) return 2.0f * (in - x);
+    if (KIND == HVAE_RECON_SIGMOID_MSE) { const float s = sigmoid_acc(in); return 2.0f * (s - x) * s * (1.0f - s); }
+    constexpr float eps = 1.1920928955078125e-07f, tiny = 1.17549435e-38f;
+    float lg = in, dlg = 1.0f;
+    if (KIND != HVAE_RECON_RB_LOGITS) {
+        const float p = (KIND == HVAE_RECON_RB_SIGMOID) ? sigmoid_acc(in) : in;
+        const bool inside = p >= eps && p <= 1.0f - eps;       // clamp: zero gradient outside
+        const float ps = fminf(fmaxf(p, eps), 1.0f - eps);
+        lg = logf(ps) - log1pf(-ps);
+        // d logit(ps)/d in: 1/(ps (1-ps)) [probs]   or   1 [sigmoid: logit(sigmoid(in)) = in]
+        dlg = inside ? ((KIND == HVAE_RECON_RB_SIGMOID) ? 1.0f : 1.0f / (ps * (1.0f - ps))) : 0.0f;
+    }
+    const float v = fminf(fmaxf(x, tiny), 1.0f - eps);
+    const float y = logf(v) - log1pf(-v);
+    return (2.0f * sigmoid_acc(lg - y * T) - 1.0f) * dlg;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_recon_rows_fwd(const float* __restrict__ in, const float* __restrict__ x, float* __restrict__ out, int64_t S, int64_t B,
+                 int64_t N, float T, float logT) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool v4 = (N & 3) == 0;
+    for (int64_t row = warp; row < S * B; row += nw) {
+        const float* lr = in + row * N;
+        const float* xr = x + (row % B) * N;
+        float acc = 0.0f;
+        if (v4) {
+            for (int64_t i = lane * 4; i < N; i += 128) {
+                const float4 l = __ldg(reinterpret_cast<const float4*>(lr + i));
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+                acc += (recon_term<KIND>(l.x, t.x, T, logT) + recon_term<KIND>(l.y, t.y, T, logT)) +
+                       (recon_term<KIND>(l.z, t.z, T, logT) + recon_term<KIND>(l.w, t.w, T, logT));
+            }
+        } else {
+            for (int64_t i = lane; i < N; i += 32) acc += recon_term<KIND>(__ldg(lr + i), __ldg(xr + i), T, logT);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[row] = acc;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_recon_rows_bwd(const float* __restrict__ in, const float* __restrict__ x, const float* __restrict__ gout,
+                 float* __restrict__ gin, int64_t S, int64_t B, int64_t N, float T) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool v4 = (N & 3) == 0;
+    for (int64_t row = warp; row < S * B; row += nw) {
+        const float* lr = in + row * N;
+        const float* xr = x + (row % B) * N;
+        float* gr = gin + row * N;
+        const float g = __ldg(gout + row);
+        if (v4) {
+            for (int64_t i = lane * 4; i < N; i += 128) {
+                const float4 l = __ldg(reinterpret_cast<const float4*>(lr + i));
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xr + i));
+                float4 o;
+                o.x = g * recon_grad<KIND>(l.x, t.x, T);
+                o.y = g * recon_grad<KIND>(l.y, t.y, T);
+                o.z = g * recon_grad<KIND>(l.z, t.z, T);
+                o.w = g * recon_grad<KIND>(l.w, t.w, T);
+                *reinterpret_cast<float4*>(gr + i) = o;
+            }
+        } else {
+            for (int64_t i = lane; i < N; i += 32) gr[i] = g * recon_grad<KIND>(__ldg(lr + i), __ldg(xr + i), T);
+        }
+    }
+}
+
 // Column sums of a row-major (R, C) matrix (bias gradient of a dense layer: gb = sum_rows gy), deterministic two-pass:
 // pass 1: block (col tile of 32, row chunk) -> partial[chunk][C]; pass 2: sum the chunks.  A warp reads 128 contiguous
 // bytes of a row.  torch's generic reduction spends ~12 us on (4096, 784); this is bandwidth-bound (~3 us from L2).
@@ -147,5 +252,42 @@ extern "C" int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x,
     if (S <= 0 || B <= 0 || N <= 0) return HVAE_ESHAPE;
     if (!logits || !x || !gnll || !glogits) return HVAE_EARG;
     k_bce_logits_rows_bwd<<<bce_grid(S * B), 256, 0, (cudaStream_t)stream>>>(logits, x, gnll, glogits, S, B, N);
+    return check_launch();
+}
+
+// in (S,B,N), x (B,N) broadcast over S -> out (S,B); kind: HVAE_RECON_*; temperature: RelaxedBernoulli kinds only
+extern "C" int hvae_recon_rows_fwd_f32(const float* in, const float* x, float* out, int64_t S, int64_t B, int64_t N, int kind,
+                                       float temperature, void* stream) {
+    if (S <= 0 || B <= 0 || N <= 0) return HVAE_ESHAPE;
+    if (!in || !x || !out) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const float T = temperature, lT = (kind >= HVAE_RECON_RB_LOGITS) ? logf(temperature) : 0.0f;
+    const unsigned grid = bce_grid(S * B);
+    switch (kind) {
+        case HVAE_RECON_MSE: k_recon_rows_fwd<HVAE_RECON_MSE><<<grid, 256, 0, s>>>(in, x, out, S, B, N, T, lT); break;
+        case HVAE_RECON_SIGMOID_MSE: k_recon_rows_fwd<HVAE_RECON_SIGMOID_MSE><<<grid, 256, 0, s>>>(in, x, out, S, B, N, T, lT); break;
+        case HVAE_RECON_RB_LOGITS: k_recon_rows_fwd<HVAE_RECON_RB_LOGITS><<<grid, 256, 0, s>>>(in, x, out, S, B, N, T, lT); break;
+        case HVAE_RECON_RB_PROBS: k_recon_rows_fwd<HVAE_RECON_RB_PROBS><<<grid, 256, 0, s>>>(in, x, out, S, B, N, T, lT); break;
+        case HVAE_RECON_RB_SIGMOID: k_recon_rows_fwd<HVAE_RECON_RB_SIGMOID><<<grid, 256, 0, s>>>(in, x, out, S, B, N, T, lT); break;
+        default: return HVAE_EARG;
+    }
+    return check_launch();
+}
+
+extern "C" int hvae_recon_rows_bwd_f32(const float* in, const float* x, const float* gout, float* gin, int64_t S, int64_t B,
+                                       int64_t N, int kind, float temperature, void* stream) {
+    if (S <= 0 || B <= 0 || N <= 0) return HVAE_ESHAPE;
+    if (!in || !x || !gout || !gin) return HVAE_EARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const float T = temperature;
+    const unsigned grid = bce_grid(S * B);
+    switch (kind) {
+        case HVAE_RECON_MSE: k_recon_rows_bwd<HVAE_RECON_MSE><<<grid, 256, 0, s>>>(in, x, gout, gin, S, B, N, T); break;
+        case HVAE_RECON_SIGMOID_MSE: k_recon_rows_bwd<HVAE_RECON_SIGMOID_MSE><<<grid, 256, 0, s>>>(in, x, gout, gin, S, B, N, T); break;
+        case HVAE_RECON_RB_LOGITS: k_recon_rows_bwd<HVAE_RECON_RB_LOGITS><<<grid, 256, 0, s>>>(in, x, gout, gin, S, B, N, T); break;
+        case HVAE_RECON_RB_PROBS: k_recon_rows_bwd<HVAE_RECON_RB_PROBS><<<grid, 256, 0, s>>>(in, x, gout, gin, S, B, N, T); break;
+        case HVAE_RECON_RB_SIGMOID: k_recon_rows_bwd<HVAE_RECON_RB_SIGMOID><<<grid, 256, 0, s>>>(in, x, gout, gin, S, B, N, T); break;
+        default: return HVAE_EARG;
+    }
     return check_launch();
 }

@@ -34,12 +34,12 @@ def relaxed_bernoulli_nll(value, temperature, probs=None, logits=None):
         eps = torch.finfo(probs.dtype).eps
         ps = probs.clamp(min=eps, max=1 - eps)
         logits = torch.log(ps) - torch.log1p(-ps)
-    t = torch.as_tensor(temperature, dtype=value.dtype, device=value.device)
+    t = float(temperature)  # a Python scalar: no host->device copy (a tensor built here would break CUDA-graph capture)
     finfo = torch.finfo(value.dtype)
     v = value.clamp(min=finfo.tiny, max=1.0 - finfo.eps)
     y = v.log() - (-v).log1p()
     diff = logits - y * t
-    base = t.log() + diff - 2 * diff.exp().log1p()
+    base = math.log(t) + diff - 2 * diff.exp().log1p()
     ladj = -F.softplus(-y) - F.softplus(y)
     return -(base - ladj)
 
@@ -83,8 +83,12 @@ class ModelA(nn.Module, _LatentMixin):
         h = self.encoder(x)
         mu, scale = self.mu(h), self.scale(h)
         z, kl = self._sample_and_kl(mu, scale, eps, self.prior_scale)
-        x_hat = self.decoder(z)
-        recon = relaxed_bernoulli_nll(x.flatten(1), 1.0, probs=x_hat.flatten(1)).sum(-1)
+        if self.fused and z.is_cuda:
+            # the decoder's final Sigmoid (+ Unflatten) folded into the RelaxedBernoulli head: one row kernel per direction
+            recon = ops.recon_rows(self.decoder[:-2](z), x.flatten(1), ops.RECON_RB_SIGMOID, 1.0)
+        else:
+            x_hat = self.decoder(z)
+            recon = relaxed_bernoulli_nll(x.flatten(1), 1.0, probs=x_hat.flatten(1)).sum(-1)
         return dict(loss_total=(recon + self.beta * kl).mean(), recon_loss=recon.mean(), kl_loss=kl.mean())
 
 
@@ -153,12 +157,18 @@ class ModelB(nn.Module, _LatentMixin):
     def loss(self, x, eps=None):
         mu_m, scale = self.model.encode(x)
         z, kl_rows = self._sample_and_kl(mu_m, scale, eps, 1.0)
-        x_hat = self.model.decoder(z)
         kl = kl_rows.sum()
-        if self.loss_recon == "mse":
-            recon = F.mse_loss(x_hat, x, reduction="sum")
+        head = self.fused and z.is_cuda
+        if self.loss_recon == "mse" and head:
+            pre = self.model.decoder[:-1](z)   # the final Sigmoid is folded into the MSE head
+            recon = ops.recon_rows(pre.flatten(1), x.flatten(1), ops.RECON_SIGMOID_MSE).sum()
+        elif self.loss_recon == "bernoulli" and head:
+            logits = self.model.decoder(z).flatten(1)
+            recon = ops.recon_rows(logits, x.flatten(1), ops.RECON_RB_LOGITS, 0.1).sum() / logits.numel()
+        elif self.loss_recon == "mse":
+            recon = F.mse_loss(self.model.decoder(z), x, reduction="sum")
         elif self.loss_recon == "bernoulli":
-            recon = relaxed_bernoulli_nll(x.flatten(1), 0.1, logits=x_hat.flatten(1)).mean()
+            recon = relaxed_bernoulli_nll(x.flatten(1), 0.1, logits=self.model.decoder(z).flatten(1)).mean()
         else:
             raise ValueError(f"loss_recon {self.loss_recon} not supported")
         return dict(loss_total=recon + self.beta * kl, loss_recon=recon, loss_kl=kl)
@@ -182,8 +192,11 @@ class ModelC(nn.Module, _LatentMixin):
         h = self.encoder(x)
         mu, scale = self.mu(h), self.scale(h)
         z, kl = self._sample_and_kl(mu, scale, eps, self.prior_scale)
-        x_hat = self.decoder(z)
-        recon = (x_hat.flatten(1) - x.flatten(1)).pow(2).sum(-1)
+        if self.fused and z.is_cuda:
+            recon = ops.recon_rows(self.decoder[:-1](z).flatten(1), x.flatten(1), ops.RECON_SIGMOID_MSE)  # Sigmoid folded in
+        else:
+            x_hat = self.decoder(z)
+            recon = (x_hat.flatten(1) - x.flatten(1)).pow(2).sum(-1)
         return dict(loss_total=(recon + self.beta * kl).mean(), recon_loss=recon.mean(), kl_loss=kl.mean())
 
 

@@ -1326,3 +1326,61 @@ def bernoulli_nll_rows(logits: Tensor, x: Tensor) -> Tensor:
     B, N = logits.shape[-2:]
     out = bce_logits_rows_fwd(_c(logits).view(-1, B, N), _c(x).view(B, N))
     return out.view(*lead, B)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Generic reconstruction heads: MSE-sum and RelaxedBernoulli NLL, optionally with the decoder's final
+# nn.Sigmoid fused; one row kernel per direction
+# ---------------------------------------------------------------------------------------------------
+RECON_MSE, RECON_SIGMOID_MSE, RECON_RB_LOGITS, RECON_RB_PROBS, RECON_RB_SIGMOID = 1, 2, 3, 4, 5
+
+
+@_op("hvae::recon_rows_fwd", mutates_args=())
+def recon_rows_fwd(inp: Tensor, x: Tensor, kind: int, temperature: float) -> Tensor:
+    """inp (S,B,N), x (B,N) -> (S,B) row sums of the reconstruction term `kind` (x broadcast over S)."""
+    C.require_cuda(inp, x)
+    S, B, N = inp.shape
+    out = inp.new_empty(S, B)
+    C.call("hvae_recon_rows_fwd_f32", C.ptr(inp), C.ptr(x), C.ptr(out), S, B, N, kind, temperature, C.stream())
+    return out
+
+
+@recon_rows_fwd.register_fake
+def _(inp, x, kind, temperature):
+    return inp.new_empty(inp.shape[0], inp.shape[1])
+
+
+@_op("hvae::recon_rows_bwd", mutates_args=())
+def recon_rows_bwd(inp: Tensor, x: Tensor, gout: Tensor, kind: int, temperature: float) -> Tensor:
+    C.require_cuda(inp, x, gout)
+    S, B, N = inp.shape
+    out = torch.empty_like(inp)
+    C.call("hvae_recon_rows_bwd_f32", C.ptr(inp), C.ptr(x), C.ptr(gout), C.ptr(out), S, B, N, kind, temperature, C.stream())
+    return out
+
+
+@recon_rows_bwd.register_fake
+def _(inp, x, gout, kind, temperature):
+    return torch.empty_like(inp)
+
+
+def _rr_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+    ctx.kind, ctx.temperature = inputs[2], inputs[3]
+
+
+def _rr_backward(ctx, g):
+    inp, x = ctx.saved_tensors
+    return recon_rows_bwd(inp, x, _c(g), ctx.kind, ctx.temperature), None, None, None
+
+
+recon_rows_fwd.register_autograd(_rr_backward, setup_context=_rr_setup)
+
+
+def recon_rows(inp: Tensor, x: Tensor, kind: int, temperature: float = 1.0) -> Tensor:
+    """Per-row reconstruction loss: inp (..., B, N) against the target x (B, N) (no gradient to the target, as in the
+    reference objectives) -> (..., B).  kind: RECON_MSE | RECON_SIGMOID_MSE | RECON_RB_LOGITS | RECON_RB_PROBS | RECON_RB_SIGMOID."""
+    lead = inp.shape[:-2]
+    B, N = inp.shape[-2:]
+    out = recon_rows_fwd(_c(inp).view(-1, B, N), _c(x.detach()).view(B, N), int(kind), float(temperature))
+    return out.view(*lead, B)

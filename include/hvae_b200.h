@@ -199,6 +199,21 @@ int hvae_bce_logits_rows_fwd_f32(const float* logits, const float* x, float* nll
 int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const float* gnll, float* glogits, int64_t S,
                                  int64_t B, int64_t N, void* stream);
 
+/* ---- generic reconstruction heads, per-(sample,row) sums over the feature axis.  `in` (S,B,N) is the
+ * decoder output (or its pre-sigmoid activation for the *_SIGMOID kinds: the decoder's final nn.Sigmoid is fused),
+ * x (B,N) the target, broadcast over S; out (S,B).  reference: F.mse_loss(x_hat, x, "sum") models/vae_hyperbolic.py:219;
+ * (x_hat - x)^2.sum(-1) models/vae_hyperbolic_rnaseq.py:107; RelaxedBernoulli(T, probs|logits).log_prob
+ * models/vae_hyperbolic_gyroplane_decoder.py:121-122, models/vae_hyperbolic.py:224-225 (torch.distributions clamps). */
+#define HVAE_RECON_MSE 1
+#define HVAE_RECON_SIGMOID_MSE 2
+#define HVAE_RECON_RB_LOGITS 3
+#define HVAE_RECON_RB_PROBS 4
+#define HVAE_RECON_RB_SIGMOID 5
+int hvae_recon_rows_fwd_f32(const float* in, const float* x, float* out, int64_t S, int64_t B, int64_t N, int kind,
+                            float temperature, void* stream);
+int hvae_recon_rows_bwd_f32(const float* in, const float* x, const float* gout, float* gin, int64_t S, int64_t B, int64_t N,
+                            int kind, float temperature, void* stream);
+
 /* ---- data-parallel gradient exchange over NVLink peer memory (the reference is single-device:
  * training/trainer_mnist.py:19).  buf_ptrs_dev / pad_ptrs_dev: DEVICE arrays of `world` pointers - every rank's copy of
  * the flat gradient bucket and of a zero-initialised uint32 signal pad, as mapped into THIS rank's address space

@@ -133,3 +133,51 @@ def test_unknown_shapes_fail_loudly():
         ball.expmap0(torch.randn(4, 2, device="cuda", dtype=torch.float64))
     with pytest.raises(NotImplementedError):
         ball.expmap0(torch.randn(4, 2, device="cuda"), dim=0)
+
+
+@pytest.mark.parametrize("S,B,N", [(1, 33, 784), (2, 17, 101), (1, 8, 20000)])
+def test_recon_heads_match_torch(S, B, N):
+    """MSE-sum and RelaxedBernoulli heads (with and without the fused decoder Sigmoid) against float64 torch:
+    F.mse_loss / torch.distributions.RelaxedBernoulli (models/vae_hyperbolic.py:218-225, ...gyroplane_decoder.py:121-122)."""
+    from hvae import ops
+
+    torch.manual_seed(S * 100 + N)
+    l = (torch.randn(S, B, N) * 3).requires_grad_(True)
+    l.data[0, 0, :4] = torch.tensor([40.0, -40.0, 17.0, -17.0])   # saturated sigmoid: probs clamp binds
+    x = torch.rand(B, N)
+    x[0, :3] = torch.tensor([0.0, 1.0, 1e-30])                    # value clamp binds
+    g = torch.randn(S, B)
+
+    def ref(kind, T):
+        l64 = l.detach().double().requires_grad_(True)
+        x64 = x.double().expand(S, B, N)
+        if kind == ops.RECON_MSE:
+            out = (l64 - x64).pow(2).sum(-1)
+        elif kind == ops.RECON_SIGMOID_MSE:
+            out = (torch.sigmoid(l64) - x64).pow(2).sum(-1)
+        else:
+            eps32, tiny32 = torch.finfo(torch.float32).eps, torch.finfo(torch.float32).tiny
+            if kind == ops.RECON_RB_LOGITS:
+                lg = l64
+            else:
+                p = torch.sigmoid(l64) if kind == ops.RECON_RB_SIGMOID else l64
+                ps = p.clamp(eps32, 1 - eps32)
+                lg = ps.log() - (-ps).log1p()
+            v = x64.clamp(tiny32, 1 - eps32)
+            y = v.log() - (-v).log1p()
+            d = lg - y * T
+            sp = torch.nn.functional.softplus
+            out = (-torch.log(torch.tensor(T, dtype=torch.float64)) - d + 2 * sp(d) - sp(-y) - sp(y)).sum(-1)
+        out.backward(g.double())
+        return out.detach(), l64.grad
+
+    for kind, T in ((ops.RECON_MSE, 1.0), (ops.RECON_SIGMOID_MSE, 1.0), (ops.RECON_RB_LOGITS, 0.1), (ops.RECON_RB_SIGMOID, 1.0),
+                    (ops.RECON_RB_PROBS, 0.7)):
+        if kind == ops.RECON_RB_PROBS:   # probs input: feed probabilities
+            l.data = torch.sigmoid(l.data).clamp(1e-6, 1 - 1e-6)
+        o_ref, g_ref = ref(kind, T)
+        lc = l.detach().cuda().requires_grad_(True)
+        out = ops.recon_rows(lc, x.cuda(), kind, T)
+        out.backward(g.cuda())
+        torch.testing.assert_close(out.double().cpu(), o_ref, rtol=2e-5, atol=2e-5 * float(o_ref.abs().max()))
+        torch.testing.assert_close(lc.grad.double().cpu(), g_ref, rtol=2e-5, atol=2e-5 * float(g_ref.abs().max()))
