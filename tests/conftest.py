@@ -58,7 +58,9 @@ def pytest_sessionfinish(session, exitstatus):
         os.makedirs(out, exist_ok=True)
         worst = sorted(U.AUDIT, key=lambda r: -r["worst_all"])[:40]
         with open(os.path.join(out, "parity_audit_%d.json" % os.getpid()), "w") as f:
-            json.dump(dict(total=tot, worst=worst, strict_rtol=U.STRICT_RTOL), f, indent=1)
+            json.dump(dict(total=tot, worst=worst, strict_rtol=U.STRICT_RTOL,
+                           all=[[r["what"], r["n"], r["strict_fail"], r["n_well"], r["strict_fail_well"], round(r["worst_well"], 2),
+                                 round(r["worst_all"], 2)] for r in U.AUDIT]), f)
         print("\n[parity audit] %(comparisons)d comparisons, %(elements)d elements: %(strict_fail)d fail plain 1e-5*scale "
               "(%(strict_fail_well)d of %(well_elements)d well-conditioned); worst ratio well %(worst_well).3g / all %(worst_all).3g" % tot)
     except Exception as ex:  # the audit never breaks a run

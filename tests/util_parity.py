@@ -44,7 +44,7 @@ def _strict_audit(what, cuda, o32, scale_kind, rtol, ok_mask):
         well = well & ok_mask if torch.is_tensor(well) and well.dim() else ok_mask & bool(well)
     else:
         well = ok_mask if rtol <= 2 * RTOL else torch.zeros_like(ok_mask)
-    ratio = torch.where(ok_mask, err / (STRICT_RTOL * scale + tiny).clamp_min(1e-300), torch.zeros_like(err))
+    ratio = torch.where(ok_mask, err / (STRICT_RTOL * scale + tiny).clamp_min(1e-30), torch.zeros_like(err)).clamp_max(1e9)
     rec = dict(what=what, n=int(ok_mask.sum()), strict_fail=int(fail.sum()), n_well=int(well.sum()),
                strict_fail_well=int((fail & well).sum()),
                worst_well=float(ratio[well].max()) if bool(well.any()) else 0.0,
