@@ -132,11 +132,12 @@ inline PFN_encodeTiled get_encode() {
 }
 
 // bf16 row-major (rows, K) -> 2-D tensor map with a {BK, box_rows} box, 128B swizzle
-inline bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+// pitch: elements between consecutive rows (0 = K, densely packed); must be a multiple of 8 (16-byte row stride)
+inline bool make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int box_rows, int64_t pitch = 0) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint64_t strides[1] = {(cuuint64_t)(pitch > 0 ? pitch : K) * 2};
     const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,

@@ -951,6 +951,70 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     return check_launch();
 }
 
+// ---- lean gyroplane backward (a == p, signed): post-passes of the two gradient GEMMs -----------------------------------
+// reference: autograd of geoopt dist2plane (hyperbolic_vae/layers.py:193-210); algebra in tc_gemm2.cu (EPI_GYRO_BWD).
+// per-plane constants of the lean form: u = r (1 + c p2), r = 2 sqrt(c) / ((1 - c p2) |p| + MIN_NORM), and the
+// derivatives du/dp2, dv/dp2 (v = r p2) the column post-pass needs
+__global__ void k_gyro_lean_colconst(const float* __restrict__ p2, float* __restrict__ u, float* __restrict__ du,
+                                     float* __restrict__ dv, int64_t P, float c, float sc) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P) return;
+    const float q = p2[j], pn = sqrtf(q), Bc = 1.0f - c * q;
+    const float den = Bc * pn + kMinNorm;
+    const float r = 2.0f * sc / den;
+    // d(Bc pn)/dp2 = -c pn + Bc / (2 pn)
+    const float dden = (pn > 0.0f) ? (-c * pn + 0.5f * Bc / pn) : 0.0f;
+    const float dr = -r / den * dden;
+    u[j] = r * (1.0f + c * q);
+    du[j] = dr * (1.0f + c * q) + r * c;
+    dv[j] = dr * q + r;
+}
+// gx_b = G_b + 2 c a_b (<x_b, G_b> - 2 S_b) x_b,   a_b = 1 / (1 - c|x_b|^2),  S_b = sum of the epilogue's row partials
+__global__ void __launch_bounds__(256)
+k_gyro_lean_rowpost(const float* __restrict__ x, const float* __restrict__ x2, const float* __restrict__ srow, int nsp,
+                    float* __restrict__ gx, int64_t B, int64_t D, float c) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nw) {
+        float dot = 0.0f, S = 0.0f;
+        for (int64_t i = lane * 4; i < D; i += 128) {   // D % 4 == 0
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + b * D + i));
+            const float4 g = *reinterpret_cast<const float4*>(gx + b * D + i);
+            dot += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+        }
+        for (int t = lane; t < nsp; t += 32) S += __ldg(srow + (int64_t)t * B + b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            S += __shfl_xor_sync(0xffffffffu, S, o);
+        }
+        const float ab = 1.0f / fmaxf(1.0f - c * x2[b], 1e-30f);
+        const float k = 2.0f * c * ab * (dot - 2.0f * S);
+        for (int64_t i = lane * 4; i < D; i += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + b * D + i));
+            float4 g = *reinterpret_cast<const float4*>(gx + b * D + i);
+            g.x = fmaf(k, a.x, g.x); g.y = fmaf(k, a.y, g.y); g.z = fmaf(k, a.z, g.z); g.w = fmaf(k, a.w, g.w);
+            *reinterpret_cast<float4*>(gx + b * D + i) = g;
+        }
+    }
+}
+// gp_j = H_j + 2 dp2_j p_j,  dp2_j = U_j du_j + V_j dv_j,  U_j = <p_j, H_j> / u_j,  V_j = vsum_j / u_j
+__global__ void __launch_bounds__(256)
+k_gyro_lean_colpost(const float* __restrict__ p, const float* __restrict__ u, const float* __restrict__ du,
+                    const float* __restrict__ dv, const float* __restrict__ vsum, float* __restrict__ gp, int64_t P, int64_t D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= P) return;
+    float dot = 0.0f;
+    for (int64_t i = lane; i < D; i += 32) dot = fmaf(__ldg(p + j * D + i), gp[j * D + i], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float ru = 1.0f / u[j];
+    const float k = 2.0f * (dot * ru * du[j] + vsum[j] * ru * dv[j]);
+    for (int64_t i = lane; i < D; i += 32) gp[j * D + i] = fmaf(k, __ldg(p + j * D + i), gp[j * D + i]);
+}
+
 // Big problems go to the CTA-pair kernel (tc_gemm2.cu: cta_group::2, 256x256 tiles); small ones, split/X3/MN-major users
 // and the dense-layer epilogue stay on the 128x128 kernel above.
 static bool pair_kernel_eligible(const Params& prm) {
@@ -1389,9 +1453,104 @@ static WsGb ws_gb_layout(int64_t B, int64_t D, int64_t P) {
 }
 }}  // namespace hvae::tc
 
+namespace hvae { namespace tc {
+// lean path (a == p, signed): x16, p16, pT16 | x2, p2, u, du, dv | CP16 | row partials, column partials, column sums |
+// split-K partial planes of the gp GEMM
+constexpr int kGbSplits = 9;   // 32 tiles x 9 = 288 units on 74 CTA pairs: 3.9 waves
+struct WsGbLean { size_t x16, p16, pt16, x2, p2, u, du, dv, cp16, srow, vcol, vsum, csws, part, total; };
+static WsGbLean ws_gb_lean_layout(int64_t B, int64_t D, int64_t P) {
+    WsGbLean w;
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return at; };
+    w.x16 = take((size_t)B * D * 2);
+    w.p16 = take((size_t)P * D * 2);
+    w.pt16 = take((size_t)D * P * 2);
+    w.x2 = take((size_t)B * 4);
+    w.p2 = take((size_t)P * 4);
+    w.u = take((size_t)P * 4);
+    w.du = take((size_t)P * 4);
+    w.dv = take((size_t)P * 4);
+    w.cp16 = take((size_t)B * P * 2);
+    w.srow = take((size_t)tc2::row_partials(P) * B * 4);
+    w.vcol = take((size_t)((B + 31) / 32) * P * 4);
+    w.vsum = take((size_t)P * 4);
+    w.csws = take(hvae_colsum_workspace_bytes(P));
+    w.part = take((size_t)kGbSplits * P * D * 4);
+    w.total = o;
+    return w;
+}
+static bool gyro_lean_eligible(int64_t B, int64_t D, int64_t P, uint32_t flags) {
+    return flags == (uint32_t)HVAE_GYRO_SIGNED && B >= 1024 && P >= 256 && (B % 8) == 0 && (D % 8) == 0 && (P % 8) == 0;
+}
+}}  // namespace hvae::tc
+
 extern "C" size_t hvae_gyroplane_tc_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P) {
     if (B <= 0 || D <= 0 || P <= 0) return 0;
-    return tc::ws_gb_layout(B, D, P).total;
+    const size_t a = tc::ws_gb_layout(B, D, P).total, b = tc::ws_gb_lean_layout(B, D, P).total;
+    return a > b ? a : b;
+}
+
+// Lean backward (a == p, signed, no other flag; GEMM-sized): ONE fused recompute GEMM whose epilogue turns <x,p> and the
+// upstream gradient (TMA-loaded) into CP = dL/d<x,p> (bf16) + row / column partial sums, then the two gradient GEMMs
+// straight from CP - gx = CP p (contraction over P) and gp = CP^T x (contraction over B, both operands read MN-major: no
+// transposed copies) - and two light post-passes.  The (B, P) pre-activation <x,p> is never written.
+static int gyroplane_tc_bwd_lean(const float* x, const float* p, const float* gout, float* gx, float* gp, int64_t B, int64_t D,
+                                 int64_t P, float c, void* workspace, cudaStream_t s) {
+    const tc::WsGbLean L = tc::ws_gb_lean_layout(B, D, P);
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* x16 = (__nv_bfloat16*)(ws + L.x16);
+    auto* p16 = (__nv_bfloat16*)(ws + L.p16);
+    auto* pt16 = (__nv_bfloat16*)(ws + L.pt16);
+    float* x2 = (float*)(ws + L.x2);
+    float* p2 = (float*)(ws + L.p2);
+    float* u = (float*)(ws + L.u);
+    float* du = (float*)(ws + L.du);
+    float* dv = (float*)(ws + L.dv);
+    auto* cp16 = (__nv_bfloat16*)(ws + L.cp16);
+    float* srow = (float*)(ws + L.srow);
+    float* vcol = (float*)(ws + L.vcol);
+    float* vsum = (float*)(ws + L.vsum);
+    float* part = (float*)(ws + L.part);
+    const Ball bl = make_ball(c);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, x16, x2, B, D);
+    tc::k_rows_to_bf16<<<(unsigned)((P + 7) / 8), 256, 0, s>>>(p, p16, p2, P, D);
+    tc::k_gyro_lean_colconst<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(p2, u, du, dv, P, bl.c, bl.sc);
+    int rc;
+    {   // recompute <x,p> + fused pair gradients
+        tc2::Params2 q{};
+        q.M = B; q.N = P; q.K = D; q.splits = 1;
+        q.x2 = x2; q.p2 = p2; q.g = gout; q.D16 = cp16; q.srow = srow; q.vcol = vcol;
+        q.gp.c = bl.c; q.gp.sc = bl.sc; q.gp.rsc = bl.rsc; q.gp.maxnorm = bl.maxnorm; q.gp.flags = HVAE_GYRO_SIGNED;
+        rc = tc2::launch_gemm2(tc2::EPI_GYRO_BWD, x16, p16, nullptr, q, s);
+        if (rc != HVAE_OK) return rc;
+    }
+    if (gx) {   // gx = CP p (+ row post-pass)
+        dim3 grid((unsigned)((P + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+        tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(p, pt16, (int)P, (int)D);  // (P, D) -> (D, P)
+        tc2::Params2 q{};
+        q.D = gx; q.M = B; q.N = D; q.K = P; q.splits = 1;
+        rc = tc2::launch_gemm2(tc2::EPI_PLAIN, cp16, pt16, nullptr, q, s);
+        if (rc != HVAE_OK) return rc;
+        tc::k_gyro_lean_rowpost<<<kNumSMs * 8, 256, 0, s>>>(x, x2, srow, tc2::row_partials(P), gx, B, D, bl.c);
+    }
+    if (gp) {   // gp = CP^T x16 (contraction over B; both operands MN-major, split-K) (+ column post-pass)
+        int S = tc::kGbSplits;
+        const int64_t kblocks = (B + 63) / 64;
+        if (S > kblocks) S = (int)kblocks;
+        tc2::Params2 q{};
+        q.D = S > 1 ? part : gp; q.M = P; q.N = D; q.K = B; q.splits = S; q.a_mn = 1; q.b_mn = 1;
+        rc = tc2::launch_gemm2(tc2::EPI_PLAIN, cp16, x16, nullptr, q, s);
+        if (rc != HVAE_OK) return rc;
+        if (S > 1) {
+            const int64_t n = P * D;
+            const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
+            tc::k_splitk_reduce<<<grid, 256, 0, s>>>(part, nullptr, gp, P, D, S, 0);
+        }
+        rc = hvae_colsum_f32(vcol, vsum, (B + 31) / 32, P, ws + L.csws, hvae_colsum_workspace_bytes(P), (void*)s);
+        if (rc != HVAE_OK) return rc;
+        tc::k_gyro_lean_colpost<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(p, u, du, dv, vsum, gp, P, D);
+    }
+    return check_launch();
 }
 
 // gx (B,D), gp (P,D) of out = gyroplane(x, p, a = p) given gout (B,P); bf16 tensor-core GEMMs, fp32 pair math.
@@ -1402,8 +1561,9 @@ extern "C" int hvae_gyroplane_tc_bwd_f32(const float* x, const float* p, const f
                                          size_t workspace_bytes, void* stream) {
     if (B <= 0 || D <= 0 || P <= 0 || (B % 8) || (D % 8) || (P % 8)) return HVAE_ESHAPE;
     if (!x || !p || !gout || !workspace || (!gx && !gp)) return HVAE_EARG;
+    if (workspace_bytes < hvae_gyroplane_tc_bwd_workspace_bytes(B, D, P)) return HVAE_EARG;
+    if (tc::gyro_lean_eligible(B, D, P, flags)) return gyroplane_tc_bwd_lean(x, p, gout, gx, gp, B, D, P, c, workspace, (cudaStream_t)stream);
     const tc::WsGb L = tc::ws_gb_layout(B, D, P);
-    if (workspace_bytes < L.total) return HVAE_EARG;
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)workspace;
     auto* a16 = (__nv_bfloat16*)(ws + L.a16);

@@ -44,7 +44,8 @@ constexpr uint32_t TILE_A_BYTES = BMC * BK * 2, TILE_B_BYTES = BNH * BK * 2;
 constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
 constexpr uint32_t COLC_BYTES = ACC_STAGES * kTileN * 16;  // per-column float4 constants
 constexpr uint32_t STG_BYTES = 32 * 128;                   // per-warp staging box of the TMA store: 32 rows x 32 fp32
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLC_BYTES;
+constexpr uint32_t BAR_BYTES = 512;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + COLC_BYTES;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory");
 // A-resident schedule (K <= 512): a CTA keeps its 128 x K panel of A for ALL n-tiles of the m-block and streams only its
 // half of the B tiles.  The streaming schedule moves 512 KB from L2 per 256x256x512 tile - 12 TB/s at the measured mainloop
@@ -54,7 +55,7 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory");
 constexpr int ARES_KB = 8;                                 // k-blocks of the resident panel: K <= 512
 constexpr int ARES_NSB = 3;                                // B ring
 constexpr uint32_t STG_BYTES_ARES = 32 * 64;
-constexpr uint32_t SMEM_BYTES_ARES = ARES_KB * TILE_A_BYTES + ARES_NSB * TILE_B_BYTES + EPI_WARPS * STG_BYTES_ARES + 1024 + 256 + COLC_BYTES;
+constexpr uint32_t SMEM_BYTES_ARES = ARES_KB * TILE_A_BYTES + ARES_NSB * TILE_B_BYTES + EPI_WARPS * STG_BYTES_ARES + 1024 + BAR_BYTES + COLC_BYTES;
 static_assert(SMEM_BYTES_ARES <= 232448, "exceeds the 227 KB per-CTA shared memory");
 constexpr uint32_t TMEM_COLS = ACC_STAGES * kTileN;  // 512: the whole tensor memory
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 256 (the pair), N = 256
@@ -117,10 +118,17 @@ __device__ __forceinline__ void tmem_ld16x(uint32_t addr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// accumulator columns of n-tile nt of an N-column problem: 256, or the ragged remainder rounded up to the MMA's N step (16)
+__device__ __forceinline__ int tile_cols(int64_t N, int64_t nt) {
+    const int64_t rem = N - nt * kTileN;
+    return rem >= kTileN ? kTileN : (int)((rem + 15) & ~(int64_t)15);
+}
+
 template <int EPI, bool ARES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-           const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_d, Params2 prm) {
+           const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_d,
+           const __grid_constant__ CUtensorMap map_g, Params2 prm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // 128B swizzle wants 1024-byte aligned tiles (same offset in both CTAs)
@@ -130,15 +138,16 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     constexpr int SB_COLS = ARES ? 16 : 32;                               // its width in fp32 columns
     const uint32_t stg_base = base + RING_BYTES;                          // 1024-byte aligned (swizzle atom)
     const uint32_t bars = stg_base + EPI_WARPS * SBYTES;
-    const uint32_t colc_base = bars + 256u;
+    const uint32_t colc_base = bars + BAR_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (NSTG + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * NSTG + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * NSTG + ACC_STAGES + s); };
     auto afull_bar = [&](int kb) { return bars + 8u * (2 * NSTG + 2 * ACC_STAGES + kb); };             // ARES: panel slice kb landed
     auto aempty_bar = [&](int kb) { return bars + 8u * (2 * NSTG + 2 * ACC_STAGES + ARES_KB + kb); };  // ARES: ... may be overwritten
-    const uint32_t tmem_slot = bars + 8u * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB);
-    static_assert(8 * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB) + 4 <= 256, "barrier block");
+    auto gload_bar = [&](int w) { return bars + 8u * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB + w); };     // GYRO_BWD: per-warp g box landed
+    const uint32_t tmem_slot = bars + 8u * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB + EPI_WARPS);
+    static_assert(8 * (2 * NSTG + 2 * ACC_STAGES + 2 * ARES_KB + EPI_WARPS) + 4 <= BAR_BYTES, "barrier block");
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
     // streaming: [stage][A | B];  A-resident: [A panel: kb][B ring: stage]
     auto a_tile = [&](int stage_or_kb) { return ARES ? base + (uint32_t)stage_or_kb * TILE_A_BYTES : base + (uint32_t)stage_or_kb * STAGE_BYTES; };
@@ -161,9 +170,11 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         if (EPI == EPI_GEO) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b2) : "memory");
         if (EPI != EPI_ROWDOT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
+        if (EPI == EPI_GYRO_BWD) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
         for (int s = 0; s < NSTG; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EPI_WARPS); }
         for (int kb = 0; kb < ARES_KB; ++kb) { mbar_init(afull_bar(kb), 1); mbar_init(aempty_bar(kb), 1); }
+        for (int w = 0; w < EPI_WARPS; ++w) mbar_init(gload_bar(w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // the same warp of both CTAs allocates (and later frees) the pair's tensor memory
@@ -190,7 +201,9 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
                 const int m0 = (int)(mt * kPairM + rank * BMC);
                 for (int64_t nt = nt0; nt < nt1; ++nt) {
-                    const int n0 = (EPI == EPI_GEO) ? (int)(nt * TN) : (int)(nt * kTileN + rank * BNH);
+                    // a ragged last n-tile is issued as a narrower MMA (N rounded up to 16): each CTA stages N/2 of its columns
+                    const int ncols = (EPI == EPI_GEO) ? kTileN : tile_cols(prm.N, nt);
+                    const int n0 = (EPI == EPI_GEO) ? (int)(nt * TN) : (int)(nt * kTileN + rank * (ncols >> 1));
                     for (int kb = kb0; kb < kb1; ++kb) {
                         if (ARES && nt == 0) {
                             // slice kb of this m-block's panel, as soon as the previous m-block's last n-tile is done with it
@@ -200,8 +213,21 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         }
                         mbar_wait(empty_bar(stage), phase ^ 1u);   // this CTA's copy of the stage has been consumed
                         if (rank == 0) mbar_expect_tx(full_bar(stage), ARES ? 2u * TILE_B_BYTES : 2u * STAGE_BYTES);
-                        if (!ARES) tma_load_2d_2sm(a_tile(stage), &map_a, lead_full + 8u * stage, kb * BK, m0);
-                        tma_load_2d_2sm(b_tile(stage), mb, lead_full + 8u * stage, kb * BK, n0);
+                        // K-major: one {64 k, 128 rows} box; MN-major: two {64 MN, 64 k-rows} boxes (8 KB each)
+                        if (!ARES) {
+                            if (prm.a_mn) {
+                                tma_load_2d_2sm(a_tile(stage), &map_a, lead_full + 8u * stage, m0, kb * BK);
+                                tma_load_2d_2sm(a_tile(stage) + 8192u, &map_a, lead_full + 8u * stage, m0 + 64, kb * BK);
+                            } else {
+                                tma_load_2d_2sm(a_tile(stage), &map_a, lead_full + 8u * stage, kb * BK, m0);
+                            }
+                        }
+                        if (!ARES && prm.b_mn) {
+                            tma_load_2d_2sm(b_tile(stage), mb, lead_full + 8u * stage, n0, kb * BK);
+                            tma_load_2d_2sm(b_tile(stage) + 8192u, mb, lead_full + 8u * stage, n0 + 64, kb * BK);
+                        } else {
+                            tma_load_2d_2sm(b_tile(stage), mb, lead_full + 8u * stage, kb * BK, n0);
+                        }
                         if (++stage == NSTG) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -223,6 +249,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     mbar_wait(tempty_bar(as), aphase ^ 1u);   // the epilogues of BOTH CTAs have drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * kTileN);
+                    const int ncols = (EPI == EPI_GEO) ? kTileN : tile_cols(prm.N, nt);
+                    const uint32_t idesc_n = (kIdesc2 & ~(0x3Fu << 17)) | ((uint32_t)(ncols >> 3) << 17);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         if (ARES && nt == 0) {
                             mbar_wait(afull_bar(kb), pphase);     // both CTAs' slices kb of the panel have landed
@@ -230,10 +258,16 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         }
                         mbar_wait(full_bar(stage), phase);    // both CTAs' tiles of this stage have landed
                         tc_fence_after();
-                        const uint64_t da = make_desc(a_tile(ARES ? kb : stage)), db = make_desc(b_tile(stage));
+                        const bool amn = !ARES && prm.a_mn, bmn = !ARES && prm.b_mn;
+                        const uint64_t da = amn ? make_desc_mn(a_tile(stage)) : make_desc(a_tile(ARES ? kb : stage));
+                        const uint64_t db = bmn ? make_desc_mn(b_tile(stage)) : make_desc(b_tile(stage));
+                        // k-step in the (addr >> 4) field: K-major 16 bf16 = 32 B inside the swizzle atom (+2);
+                        // MN-major 16 contraction rows = 2048 B (+128)
+                        const uint64_t sa = amn ? 128u : 2u, sb = bmn ? 128u : 2u;
+                        const uint32_t idesc = idesc_n | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma2(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (uint32_t)(((kb - kb0) | k) != 0));
+                            umma2(tmem_d, da + sa * (uint64_t)k, db + sb * (uint64_t)k, idesc, (uint32_t)(((kb - kb0) | k) != 0));
                         umma_commit2(empty_bar(stage));       // frees the stage in both CTAs when these MMAs retire
                         if (ARES && nt == nt1 - 1) umma_commit2(aempty_bar(kb));   // last use of the panel slice
                         if (++stage == NSTG) { stage = 0; phase ^= 1u; }
@@ -259,7 +293,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         const uint32_t stage_buf = stg_base + (uint32_t)(warp - 2) * SBYTES;      // this warp's staging box
         const uint32_t lead_tempty = mapa(tempty_bar(0), 0);
         int as = 0;
-        uint32_t aphase = 0;
+        uint32_t aphase = 0, gphase = 0;
         constexpr int COLS = TN / kCG;   // 64 (32 for GEO)
         for (int64_t u = pair; u < units; u += npairs) {
           const int64_t tile = ARES ? u : u / S;
@@ -271,23 +305,25 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           const bool rok = grow < prm.M;
           float rs = 1.0f, x2r = 0.0f, cf = 0.0f;
           if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && rok) rs = __ldg(prm.rowscale + grow);
-          if ((EPI == EPI_GYRO || EPI == EPI_GEO) && rok) x2r = __ldg(prm.x2 + grow);
+          if ((EPI == EPI_GYRO || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) && rok) x2r = __ldg(prm.x2 + grow);
           const bool axpy = (EPI == EPI_PLAIN) && prm.axpy_x != nullptr;
           if (axpy && rok) cf = __ldg(prm.axpy_coef + grow);
           for (int64_t nt = nt0; nt < nt1; ++nt) {
             float accr = 0.0f;
-            if (EPI == EPI_GYRO || EPI == EPI_GEO) {
+            if (EPI == EPI_GYRO || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) {
                 // per-column constants of this tile, once per tile
                 if (et < TN) {
                     const int64_t n = nt * TN + et;
                     const bool in = n < prm.N;
                     const float p2 = in ? __ldg(prm.p2 + n) : 0.0f;
                     const float bb = (prm.bias && in) ? __ldg(prm.bias + n) : 0.0f;
-                    if (EPI == EPI_GYRO) {
+                    if (EPI == EPI_GYRO || EPI == EPI_GYRO_BWD) {
                         // lean path constants (see below): u = r (1 + c|p|^2), v = r |p|^2, r = 2 sqrt(c) / ((1 - c|p|^2)|p|)
                         const float c = prm.gp.c, pn = sqrtf(p2);
                         const float rcol = 2.0f * prm.gp.sc / ((1.0f - c * p2) * pn + kMinNorm);
-                        colc[as * kTileN + et] = make_float4(rcol * (1.0f + c * p2), rcol * p2, bb, p2);
+                        // z: the bias (forward) / v/u = |p|^2 / (1 + c|p|^2) (backward: weight of the row sums)
+                        colc[as * kTileN + et] = make_float4(rcol * (1.0f + c * p2), rcol * p2,
+                                                             EPI == EPI_GYRO_BWD ? p2 / (1.0f + c * p2) : bb, p2);
                     } else {
                         colc[as * kTileN + et] = make_float4(p2, in ? __ldg(prm.pa + n) : 0.0f, in ? __ldg(prm.an + n) : 0.0f, bb);
                     }
@@ -306,8 +342,18 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     continue;
                 }
 #endif
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN + cb), v);
                 const int64_t n0 = nt * TN + cb;
+                const bool inb = row_w < prm.M && n0 < prm.N;   // (warp-uniform) the box touches the matrix
+                if (EPI == EPI_GYRO_BWD && inb) {
+                    // the upstream-gradient box of this chunk: TMA -> this warp's staging buffer (its previous store has
+                    // been read out), overlapping the accumulator load below
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_expect_tx(gload_bar(warp - 2), STG_BYTES);
+                        tma_load_2d(stage_buf, &map_g, gload_bar(warp - 2), (int)n0, (int)row_w);
+                    }
+                }
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN + cb), v);
                 const float4* cc4 = colc + as * kTileN + cb;
                 if (EPI == EPI_GEO) {
                     // columns cb .. cb+31 hold <x,p_j>, columns 128 + cb .. hold <x,a_j> of the same planes; in two halves
@@ -336,7 +382,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 if (EPI == EPI_PLAIN) {
                     if (prm.rowsq) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) accr = fmaf(v[i], v[i], accr);   // out-of-range columns are zero-filled
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < prm.N) accr = fmaf(v[i], v[i], accr);   // (columns past a ragged tile's MMA width are stale)
                     }
                     if (prm.rowscale) {
 #pragma unroll
@@ -392,6 +439,74 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         }
                     }
                 }
+                if (EPI == EPI_GYRO_BWD) {
+                    // Backward of the lean forward above (a == p, signed, no other flag): with y = a_b (px u_j + w_b v_j),
+                    //   dL/dpx = g rsc a_b u_j / sqrt(1 + y^2)      (bf16: the A operand of the two gradient GEMMs).
+                    // Everything else follows from CP = dL/dpx by linear algebra (tc_gemm.cu, hvae_gyroplane_tc_bwd_f32):
+                    // the row term sum_j dL/dy (y - v_j) = <x_b, (CP p)_b> - 2 (CP (v/u))_b and the column terms
+                    // sum_b dL/dy a_b px = <p_j, (CP^T x)_j> / u_j,  sum_b dL/dy a_b w_b = (CP^T w)_j / u_j  ride on the
+                    // gradient GEMMs as augmented columns - the epilogue does no reductions.
+                    uint32_t pk[16];
+                    if (inb) {
+                        mbar_wait(gload_bar(warp - 2), gphase);
+                        gphase ^= 1u;
+                        const float ar = 1.0f / fmaxf(1.0f - prm.gp.c * x2r, 1e-30f);
+                        const float wr = -(1.0f + prm.gp.c * x2r);
+                        const float ra = prm.gp.rsc * ar;
+                        const uint32_t rowp = stage_buf + (uint32_t)lane * 128u;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float g0, g1, g2, g3;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
+                                         : "r"(rowp + (uint32_t)((c ^ (lane & 7)) << 4))
+                                         : "memory");
+                            const float gg[4] = {g0, g1, g2, g3};
+                            float o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 cc = cc4[4 * c + e];  // {u, v, bias, p2}
+                                const float y = ar * fmaf(v[4 * c + e], cc.x, wr * cc.y);
+                                o[e] = (gg[e] * rsqrtf(fmaf(y, y, 1.0f))) * (ra * cc.x);
+                                accr = fmaf(o[e], cc.z, accr);        // row sum of CP v/u
+                                v[4 * c + e] = o[e] * wr;             // column-sum term CP w_b (reduced across the warp below)
+                            }
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+                            pk[2 * c] = *reinterpret_cast<uint32_t*>(&lo);
+                            pk[2 * c + 1] = *reinterpret_cast<uint32_t*>(&hi);
+                        }
+                        // column sums over the warp's 32 rows: butterfly transpose-reduce, lane l ends with column n0 + l
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            const bool up = (lane & sft) != 0;
+#pragma unroll
+                            for (int i = 0; i < sft; ++i) {
+                                const float send = up ? v[i] : v[i + sft];
+                                const float keep = up ? v[i + sft] : v[i];
+                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                            }
+                        }
+                        if (n0 + lane < prm.N) prm.vcol[(row_w >> 5) * prm.N + n0 + lane] = v[0];
+                        __syncwarp();   // every lane has read its g row: the buffer may be overwritten
+                        // bf16 box: 32 rows x 64 B, 16-byte chunk c at position c ^ ((row / 2) % 4)  (SWIZZLE_64B)
+                        const uint32_t rowq = stage_buf + (uint32_t)lane * 64u;
+                        const int swz = (lane >> 1) & 3;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowq + (uint32_t)((c ^ swz) << 4)), "r"(pk[4 * c]),
+                                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                                         : "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                         ::"l"(&map_d), "r"(stage_buf), "r"((int)n0), "r"((int)row_w), "r"(0)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                    continue;
+                }
                 if (EPI != EPI_ROWDOT) {
 #ifdef HVAE_EXPERIMENT
                     if (prm.dbg & 1) {
@@ -432,8 +547,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 }
             }
             // per-(row, n-tile, column-group) partials: [(nt * kCG + cg)][M]
-            if ((EPI == EPI_PLAIN && prm.rowsq) || EPI == EPI_ROWDOT) {
-                float* dstp = (EPI == EPI_PLAIN) ? prm.rowsq : prm.rowdot;
+            if ((EPI == EPI_PLAIN && prm.rowsq) || EPI == EPI_ROWDOT || EPI == EPI_GYRO_BWD) {
+                float* dstp = (EPI == EPI_PLAIN) ? prm.rowsq : (EPI == EPI_ROWDOT ? prm.rowdot : prm.srow);
                 if (rok) dstp[(nt * kCG + cg) * prm.M + grow] = accr;
             }
             if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
@@ -463,22 +578,50 @@ static bool make_map_out(CUtensorMap* m, float* D, int64_t S, int64_t M, int64_t
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// GYRO_BWD: bf16 (M, N) output through {32, 32, 1} boxes (64-byte rows, 64B swizzle) and the fp32 (M, N) upstream
+// gradient read through {32, 32} boxes (128-byte rows, 128B swizzle)
+static bool make_map_bwd(CUtensorMap* md, CUtensorMap* mg, __nv_bfloat16* D16, const float* g, int64_t M, int64_t N) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, 1};
+        const cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * (cuuint64_t)M * 2};
+        const cuuint32_t box[3] = {32, 32, 1};
+        if (enc(md, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, D16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+    const cuuint32_t box[2] = {32, 32};
+    return enc(mg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int EPI>
 static int launch_t(const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_bfloat16* B2, const Params2& prm, cudaStream_t s) {
-    CUtensorMap ma, mb, mb2, md;
-    if (!make_map(&ma, A, prm.M, prm.K, BMC) || !make_map(&mb, B, prm.N, prm.K, BNH)) return HVAE_ELAUNCH;
-    if (!make_map(&mb2, B2 ? B2 : B, prm.N, prm.K, BNH)) return HVAE_ELAUNCH;
+    CUtensorMap ma, mb, mb2, md, mg;
+    // K-major operand: (rows, K) buffer, {64 k, 128 rows} boxes; MN-major: (K, rows) buffer, {64, 64} boxes
+    const bool okA = prm.a_mn ? make_map(&ma, A, prm.K, prm.M, 64, prm.a_pitch) : make_map(&ma, A, prm.M, prm.K, BMC, prm.a_pitch);
+    const bool okB = prm.b_mn ? make_map(&mb, B, prm.K, prm.N, 64, prm.b_pitch) : make_map(&mb, B, prm.N, prm.K, BNH, prm.b_pitch);
+    if (!okA || !okB) return HVAE_ELAUNCH;
+    if (!make_map(&mb2, B2 ? B2 : B, prm.N, prm.K, BNH, prm.b_pitch)) return HVAE_ELAUNCH;
     constexpr int TN = (EPI == EPI_GEO) ? kTileN / 2 : kTileN;
     const int64_t m_tiles = (prm.M + kPairM - 1) / kPairM, n_tiles = (prm.N + TN - 1) / TN;
     const int S = prm.splits > 1 ? prm.splits : 1;
     // A-resident when the panel fits (K <= 512), there are several n-tiles to amortise it over and enough m-blocks to
     // keep every pair busy (the unit of work becomes a whole m-block)
-    bool ares = S == 1 && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 && m_tiles >= 2 * (kNumSMs / 2);
+    bool ares = S == 1 && !prm.a_mn && !prm.b_mn && EPI != EPI_GYRO_BWD && prm.K <= (int64_t)ARES_KB * BK && n_tiles >= 4 &&
+                m_tiles >= 2 * (kNumSMs / 2);
 #ifdef HVAE_EXPERIMENT
     if (prm.dbg & 4) ares = false;
 #endif
     // output: fp32 (S, M, N), boxes of 32 rows x 32 (16) columns through swizzled staging; ROWDOT writes no matrix
-    if (EPI != EPI_ROWDOT) {
+    mg = ma;
+    if (EPI == EPI_GYRO_BWD) {
+        if (!make_map_bwd(&md, &mg, prm.D16, prm.g, prm.M, prm.N)) return HVAE_ELAUNCH;
+    } else if (EPI != EPI_ROWDOT) {
         if (!make_map_out(&md, prm.D, S, prm.M, prm.N, ares)) return HVAE_ELAUNCH;
     } else {
         md = ma;
@@ -489,9 +632,9 @@ static int launch_t(const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_b
     const int64_t units = ares ? m_tiles : m_tiles * n_tiles * S;
     const int pairs = (int)(units < kNumSMs / 2 ? units : kNumSMs / 2);
     if (ares)
-        k_tc_gemm2<EPI, true><<<2 * pairs, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, mb2, md, prm);
+        k_tc_gemm2<EPI, true><<<2 * pairs, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, mb2, md, mg, prm);
     else
-        k_tc_gemm2<EPI, false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(ma, mb, mb2, md, prm);
+        k_tc_gemm2<EPI, false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(ma, mb, mb2, md, mg, prm);
     return check_launch();
 }
 
@@ -499,6 +642,7 @@ int launch_gemm2(int epi, const __nv_bfloat16* A, const __nv_bfloat16* B, const 
                  cudaStream_t s) {
     if (prm.M <= 0 || prm.N <= 0 || prm.K <= 0 || (prm.K % 8) != 0) return HVAE_ESHAPE;
     if (epi != EPI_ROWDOT && (prm.N % 4) != 0) return HVAE_ESHAPE;   // TMA store: 16-byte row pitch
+    if ((prm.a_mn && (prm.M % 8)) || (prm.b_mn && (prm.N % 8))) return HVAE_ESHAPE;   // MN-major buffers: 16-byte row pitch
     const int k_blocks = (int)((prm.K + BK - 1) / BK);
     if (prm.splits > k_blocks) return HVAE_EARG;
     if (prm.splits > 1 && (epi != EPI_PLAIN || prm.rowsq || prm.axpy_x || prm.rowscale)) return HVAE_EARG;
@@ -508,6 +652,8 @@ int launch_gemm2(int epi, const __nv_bfloat16* A, const __nv_bfloat16* B, const 
         case EPI_ROWDOT: return launch_t<EPI_ROWDOT>(A, B, nullptr, prm, s);
         case EPI_MOBIUS: return launch_t<EPI_MOBIUS>(A, B, nullptr, prm, s);
         case EPI_GEO: return B2 ? launch_t<EPI_GEO>(A, B, B2, prm, s) : HVAE_EARG;
+        case EPI_GYRO_BWD:
+            return (prm.g && prm.D16 && prm.srow && prm.vcol && (prm.N % 8) == 0) ? launch_t<EPI_GYRO_BWD>(A, B, nullptr, prm, s) : HVAE_EARG;
     }
     return HVAE_EARG;
 }

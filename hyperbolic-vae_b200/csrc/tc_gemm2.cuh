@@ -9,7 +9,7 @@
 namespace hvae {
 namespace tc2 {
 
-enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4 };
+enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4, EPI_GYRO_BWD = 5 };
 
 constexpr int kPairM = 256;   // output rows per CTA pair (128 per CTA)
 constexpr int kTileN = 256;   // accumulator columns per tile
@@ -19,6 +19,12 @@ struct Params2 {
     float* D;               // (M, N) row-major output (split-K: S partial planes of M x N)
     int64_t M, N, K;        // N = output columns (GEO: planes; the B operand then has 2N rows in two maps)
     int splits;             // > 1: split-K, unit (tile, s) writes its partial tile to D + s * M * N
+    int a_mn, b_mn;         // operand stored contraction-major-OUTER: buffer rows = contraction index, columns = M / N index
+    int64_t a_pitch, b_pitch;  // row pitch of the operand buffers in elements (0 = dense)
+    const float* g;         // GYRO_BWD: (M, N) upstream gradient (read by TMA);  D16: (M, N) bf16 output CP = dL/d<x,p>
+    __nv_bfloat16* D16;
+    float* srow;            // GYRO_BWD: [n_tiles * kCG][M] partial row sums of CP * (v_j / u_j)
+    float* vcol;            // GYRO_BWD: [ceil(M / 32)][N] partial column sums of CP * w_b  (one row per 32-row block)
     const float* rowscale;  // PLAIN: optional (M,); MOBIUS: required (M,)
     const float* axpy_x;    // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
     const float* axpy_coef; //        (M,)

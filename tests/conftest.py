@@ -41,6 +41,13 @@ def golden_models():
     return torch.load(os.path.join(ROOT, "tests", "golden", "models_golden.pt"), weights_only=False)
 
 
+@pytest.fixture(scope="session")
+def golden_riemannian():
+    import torch
+
+    return torch.load(os.path.join(ROOT, "tests", "golden", "riemannian_golden.pt"), weights_only=False)
+
+
 def pytest_sessionfinish(session, exitstatus):
     """Write the strict-1e-5 audit of every parity comparison made in this session (tests/util_parity.py)."""
     try:
@@ -50,25 +57,16 @@ def pytest_sessionfinish(session, exitstatus):
 
         if not U.AUDIT:
             return
-        tot = dict(comparisons=len(U.AUDIT), elements=sum(r["n"] for r in U.AUDIT),
-                   strict_fail=sum(r["strict_fail"] for r in U.AUDIT), well_elements=sum(r["n_well"] for r in U.AUDIT),
-                   strict_fail_well=sum(r["strict_fail_well"] for r in U.AUDIT),
-                   worst_well=max(r["worst_well"] for r in U.AUDIT), worst_all=max(r["worst_all"] for r in U.AUDIT))
+        keys = ("n", "fail32", "fail64", "unexplained", "n_well", "unexplained_well")
+        tot = {k: sum(r[k] for r in U.AUDIT) for k in keys}
+        tot.update(comparisons=len(U.AUDIT), worst_well=max(r["worst_well"] for r in U.AUDIT), worst_all=max(r["worst_all"] for r in U.AUDIT))
         out = os.path.join(ROOT, "gpurun_out")
         os.makedirs(out, exist_ok=True)
-        worst = sorted(U.AUDIT, key=lambda r: -r["worst_all"])[:40]
         with open(os.path.join(out, "parity_audit_%d.json" % os.getpid()), "w") as f:
-            json.dump(dict(total=tot, worst=worst, strict_rtol=U.STRICT_RTOL,
-                           all=[[r["what"], r["n"], r["strict_fail"], r["n_well"], r["strict_fail_well"], round(r["worst_well"], 2),
-                                 round(r["worst_all"], 2)] for r in U.AUDIT]), f)
-        print("\n[parity audit] %(comparisons)d comparisons, %(elements)d elements: %(strict_fail)d fail plain 1e-5*scale "
-              "(%(strict_fail_well)d of %(well_elements)d well-conditioned); worst ratio well %(worst_well).3g / all %(worst_all).3g" % tot)
+            json.dump(dict(total=tot, strict_rtol=U.STRICT_RTOL, columns=["what"] + list(keys) + ["worst_well", "worst_all"],
+                           all=[[r["what"]] + [r[k] for k in keys] + [round(r["worst_well"], 2), round(r["worst_all"], 2)] for r in U.AUDIT]), f)
+        print("\n[parity audit] %(comparisons)d comparisons, %(n)d elements; plain 1e-5*scale: %(fail32)d fail vs the fp32 reference, "
+              "%(fail64)d vs float64, %(unexplained)d vs both; well-conditioned: %(unexplained_well)d of %(n_well)d fail both "
+              "(worst ratio %(worst_well).3g)" % tot)
     except Exception as ex:  # the audit never breaks a run
         print("[parity audit] not written: %s" % ex)
-
-
-@pytest.fixture(scope="session")
-def golden_riemannian():
-    import torch
-
-    return torch.load(os.path.join(ROOT, "tests", "golden", "riemannian_golden.pt"), weights_only=False)

@@ -52,7 +52,8 @@ def _cuda_run(model, sd, x, use_graph=True, **noise):
     return loss, L, grads
 
 
-def _compare(tag, loss, L, grads, o32, o64, loss_rtol=1e-5, loss_atol=1e-4, grad_rtol=5e-5):
+def _compare(tag, loss, L, grads, o32, o64, loss_rtol=3e-5, loss_atol=1e-4, grad_rtol=5e-5):
+    # (loss terms: cancelling batch sums, fp32 summation order alone moves them by ~1e-5; see tests/test_gpu_models.py)
     L32, G32 = o32
     L64, G64 = o64
     assert_parity(loss.reshape(1), L32["loss_total"].reshape(1), L64["loss_total"].reshape(1), what=tag + " loss_total (TrainStep)",

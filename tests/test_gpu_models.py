@@ -73,7 +73,9 @@ def test_model_step_matches_reference(golden_models, name, fused):
     l64, g64 = _oracle64(name, g)
     for k, v in g["losses"].items():
         # the KL is a batch sum of (log q - log p): a cancelling sum of O(1..10) terms per row -> absolute floor
-        assert_parity(losses[k].reshape(1), v.reshape(1), l64[k].reshape(1), what="%s %s" % (name, k), rtol=1e-5,
+        # (loss terms are cancelling batch sums of thousands of O(1) terms: fp32 summation order alone moves them by ~1e-5,
+        #  torch's own GPU fp32 ops included - they are reported by the strict audit but not counted as well-conditioned)
+        assert_parity(losses[k].reshape(1), v.reshape(1), l64[k].reshape(1), what="%s %s" % (name, k), rtol=3e-5,
                       atol=1e-5 if "kl" in k else 1e-6, row_relative=False, slack_mult=2.0)
     grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(grads) == set(g["grads"]), set(grads) ^ set(g["grads"])
