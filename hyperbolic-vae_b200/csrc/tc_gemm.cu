@@ -951,6 +951,59 @@ static int launch_gemm(const __nv_bfloat16* A, const __nv_bfloat16* Bm, const Pa
     return check_launch();
 }
 
+// ---- Mobius backward without the (B, P) pre-activation -------------------------------------------------------------------
+// With T = gy M (B x F, contraction over P), G = M^T M and mx_b = M x_b:
+//   <gy_b, mx_b> = <T_b, x_b>                       (the one row scalar the coefficients alpha, beta, gxc need)
+//   gx_b = alpha_b T_b + beta_b (x G)_b + gxc_b x_b          [gmx = alpha gy + beta mx,  gmx M = alpha T + beta x G]
+//   gM   = gy^T (alpha x) + M (x^T diag(beta) x)             [gmx^T x]
+// so neither y nor mx is read: the only (B, P)-sized traffic is gy -> bf16 once, then bf16 gy twice (the two GEMMs).
+// Row pass: one warp per row; writes gx and the bf16 operands alpha x, beta x of the two contraction-over-B GEMMs.
+__global__ void __launch_bounds__(256)
+k_mobius_bwd_rowpost(const float* __restrict__ x, const float* __restrict__ T, const float* __restrict__ XG,
+                     const float* __restrict__ mxsq, float* __restrict__ gx, __nv_bfloat16* __restrict__ ax16,
+                     __nv_bfloat16* __restrict__ bx16, int64_t B, int64_t F, Ball ball) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nw) {
+        float x2 = 0.0f, gdm = 0.0f;
+        for (int64_t i = lane * 4; i < F; i += 128) {   // F % 4 == 0
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + b * F + i));
+            const float4 t = __ldg(reinterpret_cast<const float4*>(T + b * F + i));
+            x2 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            gdm += a.x * t.x + a.y * t.y + a.z * t.z + a.w * t.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+            gdm += __shfl_xor_sync(0xffffffffu, gdm, o);
+        }
+        const float mx2 = mxsq[b];
+        float alpha, beta, gxc;
+        mob_bwd_coefs(x2, mx2, gdm, mx2 == 0.0f, ball, alpha, beta, gxc);
+        for (int64_t i = lane * 4; i < F; i += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + b * F + i));
+            const float4 t = __ldg(reinterpret_cast<const float4*>(T + b * F + i));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(XG + b * F + i));
+            if (gx) {
+                float4 o;
+                o.x = fmaf(alpha, t.x, fmaf(beta, g.x, gxc * a.x));
+                o.y = fmaf(alpha, t.y, fmaf(beta, g.y, gxc * a.y));
+                o.z = fmaf(alpha, t.z, fmaf(beta, g.z, gxc * a.z));
+                o.w = fmaf(alpha, t.w, fmaf(beta, g.w, gxc * a.w));
+                *reinterpret_cast<float4*>(gx + b * F + i) = o;
+            }
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(alpha * a.x, alpha * a.y), p1 = __floats2bfloat162_rn(alpha * a.z, alpha * a.w);
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(beta * a.x, beta * a.y), q1 = __floats2bfloat162_rn(beta * a.z, beta * a.w);
+            uint2 pa, pb;
+            pa.x = *reinterpret_cast<uint32_t*>(&p0); pa.y = *reinterpret_cast<uint32_t*>(&p1);
+            pb.x = *reinterpret_cast<uint32_t*>(&q0); pb.y = *reinterpret_cast<uint32_t*>(&q1);
+            *reinterpret_cast<uint2*>(ax16 + b * F + i) = pa;
+            *reinterpret_cast<uint2*>(bx16 + b * F + i) = pb;
+        }
+    }
+}
+
 // ---- lean gyroplane backward (a == p, signed): post-passes of the two gradient GEMMs -----------------------------------
 // reference: autograd of geoopt dist2plane (hyperbolic_vae/layers.py:193-210); algebra in tc_gemm2.cu (EPI_GYRO_BWD).
 // per-plane constants of the lean form: u = r (1 + c p2), r = 2 sqrt(c) / ((1 - c p2) |p| + MIN_NORM), and the
@@ -1077,9 +1130,126 @@ static WsBwd ws_bwd_layout(int64_t B, int64_t F, int64_t P) {
 
 using namespace hvae;
 
+namespace hvae { namespace tc {
+constexpr int kMbSplitsM = 9;    // gM GEMM: 16 x 2 tiles x 9 = 288 units on 74 CTA pairs
+constexpr int kMbSplitsC = 18;   // C GEMM: 2 x 2 tiles x 18 = 72 units
+struct WsMb { size_t gy16, x16, ax16, bx16, mt16, m16, g32, g16, T, XG, part, gm1, part2, c32, c16, total; };
+static WsMb ws_mb_layout(int64_t B, int64_t F, int64_t P) {
+    WsMb w;
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 255) / 256 * 256; return at; };
+    w.gy16 = take((size_t)B * P * 2);
+    w.x16 = take((size_t)B * F * 2);
+    w.ax16 = take((size_t)B * F * 2);
+    w.bx16 = take((size_t)B * F * 2);
+    w.mt16 = take((size_t)F * P * 2);
+    w.m16 = take((size_t)P * F * 2);
+    w.g32 = take((size_t)F * F * 4);
+    w.g16 = take((size_t)F * F * 2);
+    w.T = take((size_t)B * F * 4);
+    w.XG = take((size_t)B * F * 4);
+    w.part = take((size_t)kMbSplitsM * P * F * 4);
+    w.gm1 = take((size_t)P * F * 4);
+    w.part2 = take((size_t)kMbSplitsC * F * F * 4);
+    w.c32 = take((size_t)F * F * 4);
+    w.c16 = take((size_t)F * F * 2);
+    w.total = o;
+    return w;
+}
+static bool mobius_lean_eligible(int64_t B, int64_t F, int64_t P) {
+    return B >= 1024 && P >= 256 && F >= 128 && (B % 8) == 0 && (F % 8) == 0 && (P % 8) == 0;
+}
+}}  // namespace hvae::tc
+
 extern "C" size_t hvae_mobius_tc_bwd_workspace_bytes(int64_t B, int64_t F, int64_t P) {
     if (B <= 0 || F <= 0 || P <= 0) return 0;
-    return tc::ws_bwd_layout(B, F, P).total;
+    const size_t a = tc::ws_bwd_layout(B, F, P).total, b = tc::ws_mb_layout(B, F, P).total;
+    return a > b ? a : b;
+}
+
+// GEMM-sized Mobius backward: see k_mobius_bwd_rowpost for the algebra.  All contraction-over-B operands are read
+// MN-major (no transposed copies); gM's two terms are one split-K GEMM + one small GEMM that adds M C in its epilogue.
+static int mobius_tc_bwd_lean(const float* x, const float* M, const float* mxsq, const float* gy, float* gx, float* gM, int64_t B,
+                              int64_t F, int64_t P, float c, void* workspace, cudaStream_t s) {
+    const tc::WsMb L = tc::ws_mb_layout(B, F, P);
+    uint8_t* ws = (uint8_t*)workspace;
+    auto* gy16 = (__nv_bfloat16*)(ws + L.gy16);
+    auto* x16 = (__nv_bfloat16*)(ws + L.x16);
+    auto* ax16 = (__nv_bfloat16*)(ws + L.ax16);
+    auto* bx16 = (__nv_bfloat16*)(ws + L.bx16);
+    auto* mt16 = (__nv_bfloat16*)(ws + L.mt16);
+    auto* m16 = (__nv_bfloat16*)(ws + L.m16);
+    float* g32 = (float*)(ws + L.g32);
+    auto* g16 = (__nv_bfloat16*)(ws + L.g16);
+    float* T = (float*)(ws + L.T);
+    float* XG = (float*)(ws + L.XG);
+    float* part = (float*)(ws + L.part);
+    float* gm1 = (float*)(ws + L.gm1);
+    float* part2 = (float*)(ws + L.part2);
+    float* c32 = (float*)(ws + L.c32);
+    auto* c16 = (__nv_bfloat16*)(ws + L.c16);
+    const unsigned pgrid = (unsigned)((P + 7) / 8);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(gy, gy16, nullptr, B, P);
+    tc::k_rows_to_bf16<<<kNumSMs * 8, 256, 0, s>>>(x, x16, nullptr, B, F);
+    tc::k_rows_to_bf16<<<pgrid, 256, 0, s>>>(M, m16, nullptr, P, F);
+    {
+        dim3 grid((unsigned)((P + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+        tc::k_transpose_to_bf16<<<grid, block, 0, s>>>(M, mt16, (int)P, (int)F);  // (P, F) -> (F, P)
+    }
+    int rc;
+    {   // T = gy M : (B, F), contraction over P
+        tc2::Params2 q{};
+        q.D = T; q.M = B; q.N = F; q.K = P; q.splits = 1;
+        rc = tc2::launch_gemm2(tc2::EPI_PLAIN, gy16, mt16, nullptr, q, s);
+        if (rc != HVAE_OK) return rc;
+    }
+    {   // G = M^T M : (F, F), contraction over P;  XG = x G : (B, F)
+        tc::Params prm{};
+        prm.D = g32; prm.M = F; prm.N = F; prm.K = P;
+        rc = tc::launch_auto<tc::EPI_PLAIN>(mt16, mt16, prm, s);
+        if (rc != HVAE_OK) return rc;
+        tc::k_rows_to_bf16<<<(unsigned)((F + 7) / 8), 256, 0, s>>>(g32, g16, nullptr, F, F);
+        tc2::Params2 q{};
+        q.D = XG; q.M = B; q.N = F; q.K = F; q.splits = 1;
+        rc = tc2::launch_gemm2(tc2::EPI_PLAIN, x16, g16, nullptr, q, s);   // (G is symmetric: its rows are the K-major B operand)
+        if (rc != HVAE_OK) return rc;
+    }
+    tc::k_mobius_bwd_rowpost<<<kNumSMs * 8, 256, 0, s>>>(x, T, XG, mxsq, gx, ax16, bx16, B, F, make_ball(c));
+    if (gM) {
+        const int64_t kblocks = (B + 63) / 64;
+        int S = tc::kMbSplitsM < kblocks ? tc::kMbSplitsM : (int)kblocks;
+        {   // gM1 = gy^T (alpha x) : (P, F), contraction over B, both operands MN-major
+            tc2::Params2 q{};
+            q.D = S > 1 ? part : gm1; q.M = P; q.N = F; q.K = B; q.splits = S; q.a_mn = 1; q.b_mn = 1;
+            rc = tc2::launch_gemm2(tc2::EPI_PLAIN, gy16, ax16, nullptr, q, s);
+            if (rc != HVAE_OK) return rc;
+            if (S > 1) {
+                const int64_t n = P * F;
+                const unsigned grid = (unsigned)((n + 255) / 256 < (int64_t)kNumSMs * 16 ? (n + 255) / 256 : (int64_t)kNumSMs * 16);
+                tc::k_splitk_reduce<<<grid, 256, 0, s>>>(part, nullptr, gm1, P, F, S, 0);
+            }
+        }
+        int S2 = tc::kMbSplitsC < kblocks ? tc::kMbSplitsC : (int)kblocks;
+        {   // C = x^T (beta x) : (F, F), contraction over B
+            tc2::Params2 q{};
+            q.D = S2 > 1 ? part2 : c32; q.M = F; q.N = F; q.K = B; q.splits = S2; q.a_mn = 1; q.b_mn = 1;
+            rc = tc2::launch_gemm2(tc2::EPI_PLAIN, x16, bx16, nullptr, q, s);
+            if (rc != HVAE_OK) return rc;
+            if (S2 > 1) {
+                const int64_t n = F * F;
+                const unsigned grid = (unsigned)((n + 255) / 256);
+                tc::k_splitk_reduce<<<grid, 256, 0, s>>>(part2, nullptr, c32, F, F, S2, 0);
+            }
+            tc::k_rows_to_bf16<<<(unsigned)((F + 7) / 8), 256, 0, s>>>(c32, c16, nullptr, F, F);
+        }
+        {   // gM = M C + gM1   (C = sum_b beta_b x_b x_b^T is symmetric: its rows are the K-major B operand)
+            tc2::Params2 q{};
+            q.D = gM; q.M = P; q.N = F; q.K = F; q.splits = 1; q.axpy_x = gm1; q.axpy_coef = nullptr;
+            rc = tc2::launch_gemm2(tc2::EPI_PLAIN, m16, c16, nullptr, q, s);
+            if (rc != HVAE_OK) return rc;
+        }
+    }
+    return check_launch();
 }
 
 extern "C" size_t hvae_tc_workspace_bytes(int64_t B, int64_t K, int64_t P) {
@@ -1159,8 +1329,9 @@ extern "C" int hvae_mobius_matvec_tc_bwd_f32(const float* x, const float* M, con
                                              void* workspace, size_t workspace_bytes, void* stream) {
     if (B <= 0 || F <= 0 || P <= 0 || (B % 8) != 0 || (F % 8) != 0 || (P % 8) != 0) return HVAE_ESHAPE;
     if (!x || !M || !y || !mxsq || !gy || !workspace || (!gx && !gM)) return HVAE_EARG;
+    if (workspace_bytes < hvae_mobius_tc_bwd_workspace_bytes(B, F, P)) return HVAE_EARG;
+    if (tc::mobius_lean_eligible(B, F, P)) return mobius_tc_bwd_lean(x, M, mxsq, gy, gx, gM, B, F, P, c, workspace, (cudaStream_t)stream);
     const tc::WsBwd L = tc::ws_bwd_layout(B, F, P);
-    if (workspace_bytes < L.total) return HVAE_EARG;
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)workspace;
     auto* gmx16 = (__nv_bfloat16*)(ws + L.gmx16);

@@ -307,7 +307,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && rok) rs = __ldg(prm.rowscale + grow);
           if ((EPI == EPI_GYRO || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) && rok) x2r = __ldg(prm.x2 + grow);
           const bool axpy = (EPI == EPI_PLAIN) && prm.axpy_x != nullptr;
-          if (axpy && rok) cf = __ldg(prm.axpy_coef + grow);
+          if (axpy && rok) cf = prm.axpy_coef ? __ldg(prm.axpy_coef + grow) : 1.0f;
           for (int64_t nt = nt0; nt < nt1; ++nt) {
             float accr = 0.0f;
             if (EPI == EPI_GYRO || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) {

@@ -27,7 +27,7 @@ struct Params2 {
     float* vcol;            // GYRO_BWD: [ceil(M / 32)][N] partial column sums of CP * w_b  (one row per 32-row block)
     const float* rowscale;  // PLAIN: optional (M,); MOBIUS: required (M,)
     const float* axpy_x;    // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
-    const float* axpy_coef; //        (M,)
+    const float* axpy_coef; //        (M,) or NULL (= 1)
     float* rowsq;           // PLAIN: optional [n_tiles * kCG][M] partial sums of acc^2
     const float* x2;        // GYRO / GEO: (M,) |x|^2
     const float* p2;        // GYRO / GEO: (N,) |p|^2
