@@ -104,6 +104,16 @@ __device__ __forceinline__ void umma_commit2(uint32_t bar) {
                  ::"r"(bar), "h"(mask)
                  : "memory");
 }
+// asinh for the bf16-operand epilogues: sign(y) log2(|y| + sqrt(y^2 + 1)) * ln2 with two MUFU ops and no small-|y| branch.
+// Absolute error ~1e-7 (relative 1e-7 / |y| for tiny y): far inside the 1e-2 budget of the bf16 mode, whose inputs
+// <x,p> already carry 4e-3; the fp32 kernels keep asinh_fast (polynomial below 0.25).  Returns asinh(y) / ln 2.
+__device__ __forceinline__ float asinh_lg2(float y) {
+    const float ay = fabsf(y);
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(ay, ay, 1.0f)));
+    return copysignf(__log2f(ay + s), y);
+}
+
 // 32 lanes x 16 consecutive columns (thread = TMEM lane)
 __device__ __forceinline__ void tmem_ld16x(uint32_t addr, float (&v)[16]) {
     uint32_t r[16];
@@ -424,7 +434,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     // (the clamps of the reference only bind for |p| ~ 1e-15, kept via the + MIN_NORM in u, v).  Other flag
                     // combinations take the general pair function.
                     const bool lean = (prm.gp.flags & ~(uint32_t)HVAE_GYRO_SIGNED) == 0u && (prm.gp.flags & HVAE_GYRO_SIGNED);
-                    const float rsc = prm.gp.rsc;
+                    const float rsc = prm.gp.rsc, rsc_ln2 = prm.gp.rsc * 0.693147180559945f;
                     const float ar = 1.0f / fmaxf(1.0f - prm.gp.c * x2r, 1e-30f);
                     const float wr = -(1.0f + prm.gp.c * x2r);
 #pragma unroll
@@ -432,7 +442,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         const float4 cc = cc4[i];  // {u, v, bias, p2}: the same address in every lane (broadcast)
                         if (lean) {
                             const float y = ar * fmaf(v[i], cc.x, wr * cc.y);
-                            v[i] = fmaf(asinh_fast(y), rsc, cc.z);
+                            v[i] = fmaf(asinh_lg2(y), rsc_ln2, cc.z);
                         } else {
                             GyroPairCtx kk;
                             v[i] = gyro_pair_fwd(v[i], v[i], x2r, cc.w, cc.w, sqrtf(cc.w), prm.gp, kk) + cc.z;
