@@ -482,7 +482,12 @@ def run_step(args, name, wl):
     # batch-SUM losses (model B, pvae objective) -> SUM all-reduce reproduces the single-GPU gradient; batch-MEAN losses
     # (models A, C) -> each rank's mean is over its shard: SUM then divide by the world size
     n0 = C.launch_count
-    ts = TrainStep(model, x_dev, average_grads=wl["average"], use_graph=False)
+    opt = None
+    if args.optimizer:
+        from hvae.optim import RiemannianAdam
+
+        opt = RiemannianAdam(model.parameters(), lr=1e-3)   # the reference's configure_optimizers (lr = 1e-3)
+    ts = TrainStep(model, x_dev, average_grads=wl["average"], use_graph=False, optimizer=opt)
     launches_per_step = (C.launch_count - n0) // 3  # TrainStep runs 3 eager warm-up steps
     if not args.no_graph:
         ts._capture()
@@ -542,6 +547,8 @@ def run_step(args, name, wl):
     if rank == 0:
         pk, pk_kind = peaks()
         extra = {"cuda_graph": graph_on, "exchange": exchange, "grad_bucket_bytes": ts.bucket.nbytes,
+                 "optimizer": "fused RiemannianAdam step inside the timed step (hvae.optim, one launch)" if opt is not None else
+                              "none (the metric is fwd+bwd; --optimizer adds the fused Riemannian Adam step)",
                  "l2": "256 MiB buffer written between timed steps (L2 flush)",
                  "trunk": "hvae.layers.Linear -> tcgen05 split-bf16 GEMM (fp32-accurate, own kernel) for GEMM-sized layers; "
                           "small layers and the conv stack of model B run on cuBLAS / cuDNN with TF32 off"}
@@ -708,6 +715,7 @@ def main():
     ap.add_argument("--tc-logB", type=int, default=20, help="rows (log2) of the tc_rooflines section of the cfg2 line")
     ap.add_argument("--cpu-rows", type=int, default=1024, help="rows per CPU-baseline step of our arm (bounded sample)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--optimizer", action="store_true", help="include the fused Riemannian Adam step in every timed step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc-rooflines", action="store_true")
     args = ap.parse_args()

@@ -42,7 +42,7 @@ constexpr int EPI_WARPS = 4 * kCG;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TILE_A_BYTES = BMC * BK * 2, TILE_B_BYTES = BNH * BK * 2;
 constexpr uint32_t STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
-constexpr uint32_t COLC_BYTES = ACC_STAGES * kTileN * 16;  // per-column float4 constants
+constexpr uint32_t COLC_BYTES = EPI_WARPS * (kTileN / kCG) * 16;  // per-warp slices of per-column float4 constants
 constexpr uint32_t STG_BYTES = 32 * 128;                   // per-warp staging box of the TMA store: 32 rows x 32 fp32
 constexpr uint32_t BAR_BYTES = 512;
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align slack*/ + BAR_BYTES + COLC_BYTES;
@@ -108,10 +108,10 @@ __device__ __forceinline__ void umma_commit2(uint32_t bar) {
 // Absolute error ~1e-7 (relative 1e-7 / |y| for tiny y): far inside the 1e-2 budget of the bf16 mode, whose inputs
 // <x,p> already carry 4e-3; the fp32 kernels keep asinh_fast (polynomial below 0.25).  Returns asinh(y) / ln 2.
 __device__ __forceinline__ float asinh_lg2(float y) {
-    const float ay = fabsf(y);
-    float s;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(ay, ay, 1.0f)));
-    return copysignf(__log2f(ay + s), y);
+    float s, l;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(y, y, 1.0f)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fabsf(y) + s));            // argument >= 1: never denormal, l >= 0
+    return __uint_as_float(__float_as_uint(l) | (__float_as_uint(y) & 0x80000000u));   // copysign(l, y)
 }
 
 // 32 lanes x 16 consecutive columns (thread = TMEM lane)
@@ -298,13 +298,12 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         // L1 wavefront / L2 tag lookup per 32 bytes and added 0.54 ms to a 0.74 ms mainloop on config 5.)
         const int q = warp & 3;
         const int cg = (warp - 2) >> 2;
-        const int et = threadIdx.x - 64;
-        float4* colc = reinterpret_cast<float4*>(smem_raw + (colc_base - raw));   // [ACC_STAGES][kTileN]
         const uint32_t stage_buf = stg_base + (uint32_t)(warp - 2) * SBYTES;      // this warp's staging box
         const uint32_t lead_tempty = mapa(tempty_bar(0), 0);
         int as = 0;
         uint32_t aphase = 0, gphase = 0;
         constexpr int COLS = TN / kCG;   // 64 (32 for GEO)
+        const uint32_t colc_w = colc_base + (uint32_t)(warp - 2) * (uint32_t)(kTileN / kCG) * 16u;   // this warp's column constants
         for (int64_t u = pair; u < units; u += npairs) {
           const int64_t tile = ARES ? u : u / S;
           const int sp = ARES ? 0 : (int)(u % S);
@@ -315,30 +314,35 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           const bool rok = grow < prm.M;
           float rs = 1.0f, x2r = 0.0f, cf = 0.0f;
           if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && rok) rs = __ldg(prm.rowscale + grow);
-          if ((EPI == EPI_GYRO || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) && rok) x2r = __ldg(prm.x2 + grow);
+          if ((EPI == EPI_GYRO || EPI == EPI_GYRO_LEAN || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) && rok) x2r = __ldg(prm.x2 + grow);
           const bool axpy = (EPI == EPI_PLAIN) && prm.axpy_x != nullptr;
           if (axpy && rok) cf = prm.axpy_coef ? __ldg(prm.axpy_coef + grow) : 1.0f;
           for (int64_t nt = nt0; nt < nt1; ++nt) {
             float accr = 0.0f;
-            if (EPI == EPI_GYRO || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) {
-                // per-column constants of this tile, once per tile
-                if (et < TN) {
-                    const int64_t n = nt * TN + et;
+            if (EPI == EPI_GYRO || EPI == EPI_GYRO_LEAN || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) {
+                // per-column constants of this warp's COLS columns of the tile, in the warp's OWN shared-memory slice: no
+                // block-wide barrier (a bar.sync of all 16 epilogue warps per tile was 2 of ~11 stall cycles per issue)
+                __syncwarp();   // (the warp's previous tile no longer reads the slice)
+                for (int j = lane; j < COLS; j += 32) {
+                    const int64_t n = nt * TN + cg * COLS + j;
                     const bool in = n < prm.N;
                     const float p2 = in ? __ldg(prm.p2 + n) : 0.0f;
                     const float bb = (prm.bias && in) ? __ldg(prm.bias + n) : 0.0f;
-                    if (EPI == EPI_GYRO || EPI == EPI_GYRO_BWD) {
+                    float4 cv;
+                    if (EPI == EPI_GYRO || EPI == EPI_GYRO_LEAN || EPI == EPI_GYRO_BWD) {
                         // lean path constants (see below): u = r (1 + c|p|^2), v = r |p|^2, r = 2 sqrt(c) / ((1 - c|p|^2)|p|)
                         const float c = prm.gp.c, pn = sqrtf(p2);
                         const float rcol = 2.0f * prm.gp.sc / ((1.0f - c * p2) * pn + kMinNorm);
                         // z: the bias (forward) / v/u = |p|^2 / (1 + c|p|^2) (backward: weight of the row sums)
-                        colc[as * kTileN + et] = make_float4(rcol * (1.0f + c * p2), rcol * p2,
-                                                             EPI == EPI_GYRO_BWD ? p2 / (1.0f + c * p2) : bb, p2);
+                        cv = make_float4(rcol * (1.0f + c * p2), rcol * p2, EPI == EPI_GYRO_BWD ? p2 / (1.0f + c * p2) : bb, p2);
                     } else {
-                        colc[as * kTileN + et] = make_float4(p2, in ? __ldg(prm.pa + n) : 0.0f, in ? __ldg(prm.an + n) : 0.0f, bb);
+                        cv = make_float4(p2, in ? __ldg(prm.pa + n) : 0.0f, in ? __ldg(prm.an + n) : 0.0f, bb);
                     }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(colc_w + 16u * (uint32_t)j), "f"(cv.x), "f"(cv.y),
+                                 "f"(cv.z), "f"(cv.w)
+                                 : "memory");
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                __syncwarp();
             }
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
@@ -364,7 +368,13 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     }
                 }
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN + cb), v);
-                const float4* cc4 = colc + as * kTileN + cb;
+                // per-column constants: explicit shared-space loads on a 32-bit address (every lane reads the same entry)
+                const uint32_t cc_addr = colc_w + (uint32_t)(cb - cg * COLS) * 16u;
+                auto ldcc = [&](int i) {
+                    float4 r;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(cc_addr + 16u * (uint32_t)i));
+                    return r;
+                };
                 if (EPI == EPI_GEO) {
                     // columns cb .. cb+31 hold <x,p_j>, columns 128 + cb .. hold <x,a_j> of the same planes; in two halves
                     // of 16 planes to bound the live registers
@@ -379,7 +389,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float4 cc = cc4[16 * hf + i];  // {p2, <p,a>, |a|, bias}
+                            const float4 cc = ldcc(16 * hf + i);  // {p2, <p,a>, |a|, bias}
                             GyroPairCtx kk;
                             v[16 * hf + i] = gyro_pair_fwd(v[16 * hf + i], w[i], x2r, cc.x, cc.y, cc.z, prm.gp, kk) + cc.w;
                         }
@@ -426,24 +436,30 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             }
                         }
                     }
-                } else if (EPI == EPI_GYRO) {
+                } else if (EPI == EPI_GYRO || EPI == EPI_GYRO_LEAN) {
                     // geoopt signed distance with a == p.  With z = (-p) (+) x,
                     //   <z, p> = (Bc <x,p> - A |p|^2) / den   and   1 - c|z|^2 = Bc (1 - c|x|^2) / den     (Bc = 1 - c|p|^2)
                     // so den cancels and asinh's argument separates into row and column factors around <x,p>:
                     //   y = 2 sqrt(c) [<x,p>(1 + c|p|^2) - |p|^2 (1 + c|x|^2)] / (Bc |p| (1 - c|x|^2)) = a_b (px u_j - w_b v_j)
                     // (the clamps of the reference only bind for |p| ~ 1e-15, kept via the + MIN_NORM in u, v).  Other flag
                     // combinations take the general pair function.
-                    const bool lean = (prm.gp.flags & ~(uint32_t)HVAE_GYRO_SIGNED) == 0u && (prm.gp.flags & HVAE_GYRO_SIGNED);
-                    const float rsc = prm.gp.rsc, rsc_ln2 = prm.gp.rsc * 0.693147180559945f;
+                    constexpr bool lean = EPI == EPI_GYRO_LEAN;   // (two instantiations: the general pair function costs registers)
+                    const float rsc_ln2 = prm.gp.rsc * 0.693147180559945f;
                     const float ar = 1.0f / fmaxf(1.0f - prm.gp.c * x2r, 1e-30f);
                     const float wr = -(1.0f + prm.gp.c * x2r);
+                    if (lean) {
+                        // row factors folded: out = log2(|y| + sqrt(y^2 + 1)) sign(y) (ln2 / sqrt(c)) + bias,  y = px (a_b u_j) + (a_b w_b) v_j
+                        const float aw = ar * wr;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float4 cc = cc4[i];  // {u, v, bias, p2}: the same address in every lane (broadcast)
-                        if (lean) {
-                            const float y = ar * fmaf(v[i], cc.x, wr * cc.y);
+                        for (int i = 0; i < 32; ++i) {
+                            const float4 cc = ldcc(i);  // {u, v, bias, p2}
+                            const float y = fmaf(v[i] * ar, cc.x, aw * cc.y);
                             v[i] = fmaf(asinh_lg2(y), rsc_ln2, cc.z);
-                        } else {
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int i = 0; i < 32; ++i) {
+                            const float4 cc = ldcc(i);
                             GyroPairCtx kk;
                             v[i] = gyro_pair_fwd(v[i], v[i], x2r, cc.w, cc.w, sqrtf(cc.w), prm.gp, kk) + cc.z;
                         }
@@ -475,7 +491,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             float o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float4 cc = cc4[4 * c + e];  // {u, v, bias, p2}
+                                const float4 cc = ldcc(4 * c + e);  // {u, v, bias, p2}
                                 const float y = ar * fmaf(v[4 * c + e], cc.x, wr * cc.y);
                                 o[e] = (gg[e] * rsqrtf(fmaf(y, y, 1.0f))) * (ra * cc.x);
                                 accr = fmaf(o[e], cc.z, accr);        // row sum of CP v/u
@@ -658,7 +674,9 @@ int launch_gemm2(int epi, const __nv_bfloat16* A, const __nv_bfloat16* B, const 
     if (prm.splits > 1 && (epi != EPI_PLAIN || prm.rowsq || prm.axpy_x || prm.rowscale)) return HVAE_EARG;
     switch (epi) {
         case EPI_PLAIN: return launch_t<EPI_PLAIN>(A, B, nullptr, prm, s);
-        case EPI_GYRO: return launch_t<EPI_GYRO>(A, B, nullptr, prm, s);
+        case EPI_GYRO:
+            if (prm.gp.flags == (uint32_t)HVAE_GYRO_SIGNED) return launch_t<EPI_GYRO_LEAN>(A, B, nullptr, prm, s);
+            return launch_t<EPI_GYRO>(A, B, nullptr, prm, s);
         case EPI_ROWDOT: return launch_t<EPI_ROWDOT>(A, B, nullptr, prm, s);
         case EPI_MOBIUS: return launch_t<EPI_MOBIUS>(A, B, nullptr, prm, s);
         case EPI_GEO: return B2 ? launch_t<EPI_GEO>(A, B, B2, prm, s) : HVAE_EARG;

@@ -9,7 +9,9 @@
 namespace hvae {
 namespace tc2 {
 
-enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4, EPI_GYRO_BWD = 5 };
+// EPI_GYRO: any flag combination of the a == p gyroplane (launch_gemm2 picks the lean instantiation EPI_GYRO_LEAN for the
+// plain signed distance, the general pair function otherwise)
+enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4, EPI_GYRO_BWD = 5, EPI_GYRO_LEAN = 6 };
 
 constexpr int kPairM = 256;   // output rows per CTA pair (128 per CTA)
 constexpr int kTileN = 256;   // accumulator columns per tile

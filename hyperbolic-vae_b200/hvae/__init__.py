@@ -15,7 +15,7 @@ _torch.backends.cuda.matmul.allow_tf32 = False
 
 from . import _cabi  # noqa: F401,E402
 from . import ops  # noqa: F401,E402
-from . import manifolds, layers, distributions  # noqa: F401,E402
+from . import manifolds, layers, distributions, optim  # noqa: F401,E402
 from .manifolds import PoincareBall, PoincareBallWithExtras, ManifoldParameter  # noqa: F401,E402
 
 __version__ = "0.1.0"

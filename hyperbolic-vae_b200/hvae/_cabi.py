@@ -19,7 +19,7 @@ _TYPES = {
     "int64_t": _C.c_int64, "float": _C.c_float, "int": _C.c_int, "uint32_t": _C.c_uint32,
     "uint64_t": _C.c_uint64, "size_t": _C.c_size_t, "double": _C.c_double,
 }
-_RET = {"int": _C.c_int, "size_t": _C.c_size_t, "const char*": _C.c_char_p}
+_RET = {"int": _C.c_int, "size_t": _C.c_size_t, "const char*": _C.c_char_p, "int64_t": _C.c_int64}
 
 
 def declared_functions(header_path=HEADER_PATH):
@@ -27,7 +27,7 @@ def declared_functions(header_path=HEADER_PATH):
     src = open(header_path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"^\s*(int|size_t|const char\*)\s+(hvae_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S | re.M):
+    for m in re.finditer(r"^\s*(int|int64_t|size_t|const char\*)\s+(hvae_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S | re.M):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argt = []
         if args and args != "void":

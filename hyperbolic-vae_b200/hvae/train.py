@@ -19,12 +19,16 @@ from .parallel import FlatGradBucket
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, example_input: torch.Tensor, average_grads: bool = False,
-                 use_graph: bool = True, loss_key: str = "loss_total", noise_shard="auto", **loss_kwargs):
+                 use_graph: bool = True, loss_key: str = "loss_total", noise_shard="auto", optimizer=None, **loss_kwargs):
         """noise_shard: (first_global_row, global_rows) of this rank's shard for the in-kernel samplers, "auto" =
         rank * B_local of a world * B_local batch in a multi-rank job (every rank then draws its own rows' noise, the
         rows a single-GPU run of the global batch would draw), None = leave the process-wide setting alone."""
         self.model, self.loss_key, self.loss_kwargs = model, loss_key, loss_kwargs
         self.average = average_grads
+        # optimizer: an hvae.optim.RiemannianAdam (one fused launch over the reduced bucket) stepped at the end of every
+        # step, inside the captured graph; None = forward + backward only (the BASELINE metric)
+        self.optimizer = optimizer
+        self._opt_on = False   # warm-up and capture rehearsal steps do not update the parameters
         if noise_shard == "auto":
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 from . import ops
@@ -59,8 +63,11 @@ class TrainStep:
         for _ in range(3):
             self.loss = self._step()
         torch.cuda.synchronize()
+        if self.optimizer is not None:
+            self.optimizer.prepare()   # state + launch plan allocated now, outside any capture
         if use_graph:
             self._capture()
+        self._opt_on = True
 
     # ---- data-parallel overlap: the early segment's all-reduce runs under the rest of the backward -------------
     def _plan_overlap(self, early_fraction: float = 0.35):
@@ -117,10 +124,13 @@ class TrainStep:
         else:
             self.bucket.adopt()
             self.bucket.all_reduce(average=self.average)
+        if self.optimizer is not None and self._opt_on:
+            self.optimizer.step()
         return out[self.loss_key].detach()
 
     def _capture(self):
         try:
+            self._opt_on = False   # rehearsal steps below must not move the parameters
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -129,13 +139,16 @@ class TrainStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            self._opt_on = True
             with torch.cuda.graph(g):
                 loss = self._step()
-            g.replay()
+            if self.optimizer is None:   # (with an optimizer a validating replay would be a hidden training step)
+                g.replay()
             torch.cuda.synchronize()
             self.graph, self.loss = g, loss
         except Exception as ex:
             self.graph = None
+            self._opt_on = True
             sys.stderr.write("hvae.TrainStep: CUDA graph capture failed (%s); running eagerly\n" % (str(ex).splitlines()[0],))
             torch.cuda.synchronize()
 

@@ -226,6 +226,19 @@ int hvae_allreduce_p2p_slots(int world);
 int hvae_allreduce_p2p_f32(const void* buf_ptrs_dev, const void* pad_ptrs_dev, int rank, int world, int64_t offset,
                            int64_t n, int pad_slot_base, float scale, int blocks, void* stream);
 
+/* ---- f-1: geoopt.optim.RiemannianAdam as ONE multi-tensor kernel (reference call sites models/vae_hyperbolic.py:235-243,
+ * ...gyroplane_decoder.py:173, ...rnaseq.py:139, vae_one_b.py:270).  The caller builds a HOST table of n descriptors
+ * (hvae_riemannian_adam_desc_bytes each) with hvae_riemannian_adam_describe - parameter, gradient (e.g. its view in the
+ * all-reduced flat bucket), exp_avg, exp_avg_sq, all fp32 contiguous; c > 0 marks Poincare-ball rows of length `cols`
+ * (ManifoldParameter), c == 0 a Euclidean tensor - copies it to the device and launches one step.  describe returns the
+ * tensor's block count (the next tensor's first_block is the running sum; the total is total_blocks) or -1.
+ * hyper_dev: 6 floats in device memory {lr, beta1, beta2, eps, weight_decay, step}, step = 1-based count of this update. */
+size_t hvae_riemannian_adam_desc_bytes(void);
+size_t hvae_riemannian_adam_hyper_bytes(void);
+int64_t hvae_riemannian_adam_describe(void* host_table, int index, float* p, const float* g, float* m, float* v, int64_t numel,
+                                      int64_t cols, float c, int first_block);
+int hvae_riemannian_adam_step_f32(const void* table_dev, int n_tensors, int total_blocks, const void* hyper_dev, void* stream);
+
 /* column sums of a row-major (R, C) matrix: the bias gradient of a dense layer (autograd of nn.Linear's bias). */
 size_t hvae_colsum_workspace_bytes(int64_t C);
 int hvae_colsum_f32(const float* x, float* out, int64_t R, int64_t C, void* workspace, size_t workspace_bytes,

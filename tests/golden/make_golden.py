@@ -251,6 +251,41 @@ def make_riemannian():
     return cases
 
 
+def make_optim():
+    """f-1: the optimizer the reference configures (models/vae_hyperbolic.py:235-243: geoopt.optim.RiemannianAdam over ALL
+    parameters, Euclidean and ManifoldParameter alike) stepped 3 times on model B (Mobius encoder + gyroplane decoder:
+    the gyroplane `points` are a ManifoldParameter) with seeded noise: initial state_dict, the batch, the noise of every
+    step, and the state_dict + optimizer moments after every step."""
+    rl.load()
+    mB = importlib.import_module("hyperbolic_vae.models.vae_hyperbolic")
+    from torch.distributions.utils import _standard_normal
+
+    torch.manual_seed(42)
+    B = 16
+    model = mB.VAEHyperbolicExperiment((1, 16, 16), 2, 1.0, "mobius", "geoopt_gyroplane", loss_recon="mse")
+    opt = model.configure_optimizers()["optimizer"]
+    x = torch.rand(B, 1, 16, 16)
+    rec = dict(x=x, lr=opt.param_groups[0]["lr"], betas=opt.param_groups[0]["betas"], eps_adam=opt.param_groups[0]["eps"],
+               weight_decay=opt.param_groups[0]["weight_decay"],
+               state_dict0={k: plain(v) for k, v in model.state_dict().items()}, steps=[])
+    names = {id(p): k for k, p in model.named_parameters()}
+    for it in range(3):
+        seed = 900 + it
+        torch.manual_seed(seed)
+        eps = _standard_normal(torch.Size((1, B, 2)), dtype=torch.float32, device=torch.device("cpu"))
+        torch.manual_seed(seed)
+        opt.zero_grad()
+        loss = model.loss((x, None))["loss_total"]
+        loss.backward()
+        grads = {k: plain(p.grad) for k, p in model.named_parameters() if p.grad is not None}
+        opt.step()
+        rec["steps"].append(dict(eps=eps, loss=plain(loss), grads=grads,
+                                 state_dict={k: plain(v) for k, v in model.state_dict().items()},
+                                 exp_avg={names[id(p)]: plain(st["exp_avg"]) for p, st in opt.state.items()},
+                                 exp_avg_sq={names[id(p)]: plain(st["exp_avg_sq"]) for p, st in opt.state.items()}))
+    return rec
+
+
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     if only in ("", "ops"):
