@@ -1,37 +1,34 @@
 #!/usr/bin/env python
-"""Diagnostic (GPU): where does logmap0's gradient leave the plain 1e-5 band on well-conditioned rows?"""
+"""Diagnostic (GPU): the worst well-conditioned element of one gyroplane parity case against the fp32 / float64 oracle."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "hyperbolic-vae_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch
-import hvae
-from test_gpu_row_ops import _oracle_ball, _run_oracle
+import test_gpu_layers as T
+from util_parity import pair_kappa
 
-for D, c, s in ((512, 1.0, 1e-3), (512, 1.0, 0.3), (64, 0.5, 1e-3), (10, 1.0, 0.3)):
-    torch.manual_seed(D * 7 + 1)
-    B = 257
-    u = torch.randn(B, D) * s / (D ** 0.5)
-    u[0].zero_()
-    y = _oracle_ball(c, torch.float32).expmap0(u).detach()
-    g = torch.Generator().manual_seed(0)
-    gout = torch.randn(B, D, generator=g)
-    ball = hvae.PoincareBall(c)
-    yc = y.cuda().requires_grad_(True)
-    out = ball.logmap0(yc)
-    out.backward(gout.cuda())
-    o32, (g32,) = _run_oracle(lambda a: _oracle_ball(c, torch.float32).logmap0(a), [y], gout, torch.float32)
-    o64, (g64,) = _run_oracle(lambda a: _oracle_ball(c, torch.float64).logmap0(a), [y], gout, torch.float64)
-    gc = yc.grad.double().cpu()
-    sc = g64.abs().amax(-1, keepdim=True)
-    e64 = ((gc - g64).abs() / sc)
-    e32 = ((gc - g32.double()).abs() / sc)
-    r32 = ((g32.double() - g64).abs() / sc)
-    worst = e64.amax(-1)
-    idx = worst.argsort(descending=True)[:4]
-    print("D=%d c=%g s=%g: rows failing both: %d; kernel-vs-64 max %.3g, ref32-vs-64 max %.3g" % (D, c, s, int(((e64 > 1e-5) & (e32 > 1e-5)).any(-1).sum()), float(e64.max()), float(r32.max())))
-    for i in idx.tolist():
-        j = int(e64[i].argmax())
-        print("   row %d |y|=%.4g  worst elem %d: cuda=%.8g o32=%.8g o64=%.8g  rowscale=%.4g  gdot=%.4g" % (i, float(y[i].norm()), j, float(gc[i, j]), float(g32[i, j]), float(g64[i, j]), float(sc[i]), float((gout[i].double() * y[i].double()).sum())))
-    fo = ((out.double().cpu() - o64).abs() / o64.abs().amax(-1, keepdim=True).clamp_min(1e-30))
-    print("   fwd kernel-vs-64 max %.3g (row %d)" % (float(fo.max()), int(fo.amax(-1).argmax())))
+kind, D, P, B = "unsigned", 2, 512, 77
+c = 1.0
+torch.manual_seed(D * 1000 + P)
+layer, make_o, names = T._gyro_layers(kind, D, P, c)
+ob = T._oball(c)
+x = ob.expmap0(torch.randn(B, D) * 0.8 / D ** 0.5).detach()
+params = {k: getattr(layer, k).detach().clone() for k in names}
+x[2] = params["points"][1] * (1 + 1e-4)
+x[3] = ob.expmap0(torch.randn(D) * 50.0)
+params["points"][min(3, P - 1)] *= 1e-9
+gout = torch.randn(B, P)
+cu = T._cuda_layer_run(layer, params, x, gout)
+o32 = T._oracle_layer_run(make_o, params, x, gout, torch.float32)
+o64 = T._oracle_layer_run(make_o, params, x, gout, torch.float64)
+pk = pair_kappa(float(ob.c), x, params["points"])
+out, r32, r64 = cu[0].double().cpu(), o32[0].double(), o64[0]
+g = r32.abs().max()
+b = 1e-5 * r64.abs() + 1e-6 * g
+e64, e32 = (out - r64).abs(), (out - r32).abs()
+ratio = torch.minimum(e64, e32) / b
+ratio[pk >= 2] = 0
+for idx in ratio.flatten().argsort(descending=True)[:5].tolist():
+    i, j = divmod(idx, P)
+    print("(%d,%d) ratio %.2f pk %.3f cuda %.9g o32 %.9g o64 %.9g | x %s p %s" % (i, j, float(ratio[i, j]), float(pk[i, j]), float(out[i, j]), float(r32[i, j]), float(r64[i, j]), x[i].tolist(), params["points"][j].tolist()))

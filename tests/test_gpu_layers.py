@@ -5,7 +5,7 @@ verbatim) and the float32/float64 oracle on seeded inputs incl. the edge rows th
 import pytest
 import torch
 
-from util_parity import assert_parity, kappa, pair_kappa, rtol_grad, rtol_val
+from util_parity import assert_parity, full_kappa, kappa, pair_kappa, rtol_grad, rtol_val
 
 pytestmark = pytest.mark.gpu
 
@@ -45,7 +45,7 @@ def _cuda_layer_run(layer, params, x, gout):
     return out.detach(), xx.grad, {k: getattr(layer, k).grad for k in params}
 
 
-def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5, pk=None, squared=False):
+def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5, pk=None, squared=False, fk=None):
     """pk: (B,P) pair condition factors 1/(1-c|diff|^2).  out = asinh(.../(1-c|diff|^2))/sqrt(c): an fp32
     error eps in (1-c|diff|^2) moves the output by eps*pk (absolute) and the gradients by eps*pk (relative)."""
     if pk is not None:
@@ -56,8 +56,11 @@ def _check(tag, cuda, o32, o64, rtol=1e-5, atol=2e-6, pg_tol=3e-5, pk=None, squa
         pg_rows = torch.clamp(1e-5 * pk.amax(dim=0), min=pg_tol, max=5e-2)  # per plane
     else:
         atol_out, rg = atol, rtol
-    assert_parity(cuda[0], o32[0], o64[0], what=tag + " out", rtol=rtol, atol=atol_out, row_relative=False, slack_mult=2.0)
-    assert_parity(cuda[1], o32[1], o64[1], what=tag + " gx", rtol=rg, atol=atol, slack_mult=2.0)
+    # strict audit: well-conditioned = pair AND point condition factors < 2 (fk, util_parity.full_kappa)
+    k_out = fk if fk is not None else pk
+    k_row = k_out.amax(dim=1, keepdim=True) if k_out is not None else None
+    assert_parity(cuda[0], o32[0], o64[0], what=tag + " out", rtol=rtol, atol=atol_out, row_relative=False, slack_mult=2.0, kap=k_out)
+    assert_parity(cuda[1], o32[1], o64[1], what=tag + " gx", rtol=rg, atol=atol, slack_mult=2.0, kap=k_row)
     for k in cuda[2]:
         # parameter grads are sums over the batch: judge on the tensor's scale
         tol = pg_tol
@@ -114,7 +117,8 @@ def test_golden_gyroplane_and_geodesic(golden_ops):
                 with torch.no_grad():
                     lay._weight.copy_(g["_weight"]); lay._bias.copy_(g["_bias"])
                     pk = pair_kappa(rec["c"], g["x"], lay.weight)
-            _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64, pk=pk, squared=(kind == "squared"))
+            fk = full_kappa(rec["c"], g["x"], g["points"] if kind != "geodesic" else lay.weight)
+            _check("golden %s c=%s D=%d" % (key, c, D), cu, gold, o64, pk=pk, squared=(kind == "squared"), fk=fk)
 
 
 @pytest.mark.parametrize("kind", ["bias", "geoopt", "squared", "unsigned", "geodesic", "geodesic_wn"])
@@ -143,7 +147,8 @@ def test_gyroplane_seeded(kind, D, P, B):
         with torch.no_grad():
             lay._weight.copy_(params["_weight"]); lay._bias.copy_(params["_bias"])
             pk = pair_kappa(float(_oball(c).c), x, lay.weight)
-    _check("%s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64, pk=pk, squared=(kind == "squared"))
+    fk = full_kappa(float(_oball(c).c), x, params["points"] if "points" in params else lay.weight)
+    _check("%s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64, pk=pk, squared=(kind == "squared"), fk=fk)
 
 
 def _mobius_layers(F, P, c):

@@ -42,7 +42,7 @@ def _scale_of(t, kind, ok_mask):
     return t.abs()
 
 
-def _strict_audit(what, cuda, o32, o64, scale_kind, caller_bound, ok_mask):
+def _strict_audit(what, cuda, o32, o64, scale_kind, caller_bound, ok_mask, kap=None):
     ref = o32 if o32 is not None else o64
     g = torch.nan_to_num(ref, nan=0.0).abs().max() if ref.numel() else torch.tensor(0.0, dtype=torch.float64)
     # exact-zero rows / entries; scalars that are differences of O(tensor scale) terms get the usual fp32 absolute floor
@@ -54,7 +54,10 @@ def _strict_audit(what, cuda, o32, o64, scale_kind, caller_bound, ok_mask):
     fail32, fail64 = (e32 > b32) & ok_mask, (e64 > b64) & ok_mask
     unexpl = fail32 & fail64
     cb = caller_bound if torch.is_tensor(caller_bound) else torch.full_like(ref, float(caller_bound))
-    well = (cb.expand_as(ref) <= 2.0 * b64 + 1e-6) & ok_mask
+    if kap is not None:
+        well = (torch.as_tensor(kap).detach().double().cpu().expand_as(ref) < 2.0) & ok_mask
+    else:
+        well = (cb.expand_as(ref) <= 2.0 * b64 + 1e-6) & ok_mask
     if o32 is not None:
         # ... and the reference agrees with ITSELF: where its fp32 and float64 evaluations differ by more than 1e-4 of the
         # scale the formula is ill-conditioned in the reference's own arithmetic whatever kappa says (e.g. an exactly-zero
@@ -70,8 +73,9 @@ def _strict_audit(what, cuda, o32, o64, scale_kind, caller_bound, ok_mask):
     return rec
 
 
-def assert_parity(cuda, o32, o64, rtol=RTOL, atol=ATOL, what="", norm_relative=False, row_relative=True, slack_mult=1.0):
-    """rtol may be a tensor broadcastable to the output (per-row conditioning)."""
+def assert_parity(cuda, o32, o64, rtol=RTOL, atol=ATOL, what="", norm_relative=False, row_relative=True, slack_mult=1.0, kap=None):
+    """rtol may be a tensor broadcastable to the output (per-row conditioning).  kap: optional condition factors
+    (broadcastable to the output); when given, the strict audit's "well-conditioned" set is kap < 2 exactly."""
     cuda = cuda.detach().double().cpu()
     o32 = torch.Tensor(o32.detach()).double().cpu() if o32 is not None else None
     o64 = torch.Tensor(o64.detach()).double().cpu()
@@ -93,7 +97,7 @@ def assert_parity(cuda, o32, o64, rtol=RTOL, atol=ATOL, what="", norm_relative=F
         rtol = rtol.detach().double().cpu()
     bound = rtol * scale + atol + slack
     kind = "norm" if norm_relative else ("row" if (row_relative and o64.dim() >= 2 and o64.shape[-1] > 1) else "elem")
-    rec = _strict_audit(what, cuda, o32, o64, kind, rtol * scale + atol, ok_mask)
+    rec = _strict_audit(what, cuda, o32, o64, kind, rtol * scale + atol, ok_mask, kap)
     bad = (err > bound) & ok_mask
     if bad.any():
         i = torch.nonzero(bad)[0].tolist()
@@ -141,3 +145,12 @@ def pair_kappa(c, x, p):
     den = (1 - 2 * c * px + c * c * p2 * x2).clamp_min(1e-15)
     dn2 = (A * A * p2 - 2 * A * Bc * px + Bc * Bc * x2) / (den * den)
     return 1.0 / (1.0 - c * dn2).abs().clamp_min(1e-7)
+
+
+def full_kappa(c, x, p):
+    """(B,P) condition factor of a gyroplane output for the strict audit: the pair factor AND the two points' own factors
+    1/(1 - c|x|^2), 1/(1 - c|p|^2) (a pair can have a tame (-p)(+)x while both points sit at the ball's edge)."""
+    pk = pair_kappa(c, x, p)
+    kx = kappa(c, x).view(-1, 1)
+    kp = kappa(c, p).view(1, -1)
+    return torch.maximum(pk, torch.maximum(kx, kp).expand_as(pk))
