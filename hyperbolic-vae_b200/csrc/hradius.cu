@@ -93,6 +93,34 @@ __device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
     return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
 
+// ---- HypersphericalUniform.sample in the kernel (pvae: normalise a standard normal vector; App. A.2) -------------------
+// Row i (sample s of batch row b, i = s * B + b) draws its D normals from Philox counters (cnt_i, chunk, 0xa1fa) - a
+// stream disjoint from the radius sampler's (.., iter, 0x5ad1) - so a row's direction depends only on (seed, cnt_i):
+// a data-parallel shard reproduces the rows a single-GPU run would draw.  One thread per row.
+__global__ void k_sphere_sample(float* __restrict__ out, int64_t rows, int D, uint64_t seed, uint64_t offset,
+                                const int64_t* __restrict__ offset_dev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t cnt = offset + (offset_dev ? (uint64_t)__ldg(offset_dev) : 0ull) + (uint64_t)i;
+    float* o = out + i * D;
+    float n2 = 0.0f;
+    for (int d0 = 0; d0 < D; d0 += 4) {
+        const uint4 rn = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)(d0 >> 2), 0xa1fau), key);
+        // two Box-Muller pairs
+        const float r0 = sqrtf(-2.0f * logf(u01(rn.x))), r1 = sqrtf(-2.0f * logf(u01(rn.z)));
+        float s0, c0, s1, c1;
+        sincospif(2.0f * u01(rn.y), &s0, &c0);
+        sincospif(2.0f * u01(rn.w), &s1, &c1);
+        const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (d0 + e < D) { o[d0 + e] = z[e]; n2 = fmaf(z[e], z[e], n2); }
+    }
+    const float rn_ = rsqrtf(fmaxf(n2, 1e-30f));
+    for (int d = 0; d < D; ++d) o[d] *= rn_;
+}
+
 // log-density (unnormalised) and derivative, float32 is enough for the accept test
 __device__ __forceinline__ float rad_h(float r, float inv2s2, float sc, float n) {
     const float x = sc * r;
@@ -341,5 +369,15 @@ extern "C" int hvae_expmap_polar_bwd_f32(const float* mu, const float* alpha, co
     if (S == 0 || B == 0) return HVAE_OK;
     if (!mu || !alpha || !r || !gz) return HVAE_EARG;
     HVAE_ROW_DISPATCH(k_expmap_polar_bwd, D, B, (cudaStream_t)stream, mu, alpha, r, gz, gmu, gr, S, B, (int)D, make_ball(c));
+    return check_launch();
+}
+
+// alpha (rows, D) ~ U(S^{D-1}): normalised standard normals, Philox4x32-10 in the kernel.  Counters as for
+// hvae_hradius_sample_f32: row i uses offset + *offset_dev + i (offset_dev may be NULL).
+extern "C" int hvae_sphere_sample_f32(float* out, int64_t rows, int64_t D, uint64_t seed, uint64_t offset,
+                                      const int64_t* offset_dev, void* stream) {
+    if (rows <= 0 || D <= 0 || D > 65536) return HVAE_ESHAPE;
+    if (!out) return HVAE_EARG;
+    k_sphere_sample<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(out, rows, (int)D, seed, offset, offset_dev);
     return check_launch();
 }

@@ -36,7 +36,14 @@ class HypersphericalUniform(torch.distributions.Distribution):
         return self._dim
 
     def sample(self, shape=torch.Size()):
-        v = torch.randn(*torch.Size(shape), self._dim + 1, device=self._device)
+        """(*shape, dim + 1) unit vectors.  On CUDA the normals are drawn in the kernel (Philox, ops.sphere_sample): one
+        launch instead of randn + norm + divide, graph-replay safe, and reproducible per row under data parallelism."""
+        shape = torch.Size(shape)
+        dev = torch.device(self._device)
+        if dev.type == "cuda" and len(shape) >= 1:
+            S = int(shape[:-1].numel()) if len(shape) > 1 else 1
+            return ops.sphere_sample(S, int(shape[-1]), self._dim + 1, dev).view(*shape, self._dim + 1)
+        v = torch.randn(*shape, self._dim + 1, device=self._device)
         return v / v.norm(dim=-1, keepdim=True)
 
     def _log_normalizer(self) -> float:

@@ -756,6 +756,31 @@ def hradius_sample(sigma: Tensor, S: int, dim: int, c: float, seed: Optional[int
     return r
 
 
+def sphere_sample(S: int, B: int, D: int, device, seed: Optional[int] = None, offset: Optional[int] = None) -> Tensor:
+    """alpha (S,B,D) ~ U(S^{D-1}) drawn in the kernel (Philox).  Same counter rules as hradius_sample: by default the
+    per-device counter (graph-replay safe) and this rank's noise shard - sample s of global row g uses counter
+    s * global_rows + g - on a stream disjoint from the radii's.  No gradient."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("hvae ops run only on CUDA (sm_100a) tensors; there is no CPU fallback")
+    if seed is None:
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    out = torch.empty(S, B, D, dtype=torch.float32, device=dev)
+    if offset is not None:
+        C.call("hvae_sphere_sample_f32", C.ptr(out), S * B, D, seed, offset, None, C.stream())
+        return out
+    ctr = philox_counter(dev)
+    lo, grows = _noise_shard
+    if grows is None or grows == B:
+        C.call("hvae_sphere_sample_f32", C.ptr(out), S * B, D, seed, lo, C.ptr(ctr), C.stream())
+        ctr.add_(S * B)
+    else:
+        for s_ in range(S):
+            C.call("hvae_sphere_sample_f32", C.ptr(out[s_]), B, D, seed, s_ * grows + lo, C.ptr(ctr), C.stream())
+        ctr.add_(S * grows)
+    return out
+
+
 @_op("hvae::hradius_reparam", mutates_args=())
 def hradius_reparam(r: Tensor, sigma: Tensor, dim: int, c: float) -> Tuple[Tensor, Tensor]:
     """Identity on r (S,B) carrying the implicit-reparameterisation gradient dr/dsigma (pvae impl_rsample)."""

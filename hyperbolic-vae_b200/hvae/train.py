@@ -39,7 +39,7 @@ class TrainStep:
         elif noise_shard is not None:
             from . import ops
 
-            ops.set_noise_shard(int(noise_shard[0]), int(noise_shard[1]))
+            ops.set_noise_shard(int(noise_shard[0]), noise_shard[1])
         self.bucket = FlatGradBucket(model.parameters())
         self._hooks, self._order, self._fired = [], [], 0
         self._side = torch.cuda.Stream()

@@ -136,6 +136,10 @@ int hvae_hradius_lognorm_fwd_f32(const float* sigma, float* logZ, float* dlogZ_d
  * fresh noise on every replay (the caller bumps it in-graph). */
 int hvae_hradius_sample_f32(const float* sigma, float* r, int64_t S, int64_t B, int64_t dim, float c,
                             uint64_t seed, uint64_t offset, const int64_t* offset_dev, void* stream);
+/* alpha (rows, D) ~ U(S^{D-1}) (pvae HypersphericalUniform.sample: a normalised standard normal vector), Philox in the
+ * kernel; row i draws from counters offset + *offset_dev + i, a stream disjoint from the radius sampler's. */
+int hvae_sphere_sample_f32(float* out, int64_t rows, int64_t D, uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                           void* stream);
 /* implicit reparameterisation: dr/dsigma = -(dF/dsigma)/(dF/dr) at the given (r, sigma); cdf optional */
 int hvae_hradius_rgrad_f32(const float* sigma, const float* r, float* dr_dsigma, float* cdf,
                            int64_t S, int64_t B, int64_t dim, float c, void* stream);
