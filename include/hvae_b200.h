@@ -243,6 +243,14 @@ int64_t hvae_riemannian_adam_describe(void* host_table, int index, float* p, con
                                       int64_t cols, float c, int first_block);
 int hvae_riemannian_adam_step_f32(const void* table_dev, int n_tensors, int total_blocks, const void* hyper_dev, void* stream);
 
+/* ---- f-4: on-device input normalisation of the RNA-seq pipeline (hyperbolic_vae/datasets/jerby_arnon.py:97-106,
+ * normalize_rnaseq): rows divided by their sum (x target: 1 = "sum_to_one", 1e6 = "sum_to_million"), or the per-column
+ * z-score scipy.stats.zscore computes (population std; a constant column gives NaN as scipy does).  out may alias x. */
+int hvae_rows_sum_normalize_f32(const float* x, float* out, int64_t R, int64_t C, float target, void* stream);
+size_t hvae_cols_zscore_workspace_bytes(int64_t C);
+int hvae_cols_zscore_f32(const float* x, float* out, float* mean_out, float* std_out, int64_t R, int64_t C, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* column sums of a row-major (R, C) matrix: the bias gradient of a dense layer (autograd of nn.Linear's bias). */
 size_t hvae_colsum_workspace_bytes(int64_t C);
 int hvae_colsum_f32(const float* x, float* out, int64_t R, int64_t C, void* workspace, size_t workspace_bytes,

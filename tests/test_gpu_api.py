@@ -181,3 +181,25 @@ def test_recon_heads_match_torch(S, B, N):
         out.backward(g.cuda())
         torch.testing.assert_close(out.double().cpu(), o_ref, rtol=2e-5, atol=2e-5 * float(o_ref.abs().max()))
         torch.testing.assert_close(lc.grad.double().cpu(), g_ref, rtol=2e-5, atol=2e-5 * float(g_ref.abs().max()))
+
+
+@pytest.mark.parametrize("R,G", [(1024, 20000), (77, 333), (5, 1)])
+def test_normalize_rnaseq_matches_reference_recipe(R, G):
+    """hvae.data.normalize_rnaseq against the reference's pandas / scipy recipe (datasets/jerby_arnon.py:97-106) in float64."""
+    from hvae.data import normalize_rnaseq
+
+    torch.manual_seed(R + G)
+    counts = torch.poisson(torch.full((R, G), 100.0)) + torch.rand(R, G)
+    xd = counts.double()
+    ref_z = (xd - xd.mean(0, keepdim=True)) / xd.std(0, unbiased=False, keepdim=True)     # scipy.stats.zscore per column, ddof=0
+    ref_m = xd / xd.sum(1, keepdim=True) * 1e6
+    xc = counts.cuda()
+    z = normalize_rnaseq(xc, "z_score").double().cpu()
+    m = normalize_rnaseq(xc, "sum_to_million").double().cpu()
+    o = normalize_rnaseq(xc, "sum_to_one").double().cpu()
+    if R > 1 and G > 1:
+        assert float((z - ref_z).abs().max()) < 2e-5
+    assert float(((m - ref_m).abs() / ref_m.abs().clamp_min(1e-30)).max()) < 1e-6
+    assert float((o.sum(1) - 1).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        normalize_rnaseq(xc, "nope")
