@@ -12,8 +12,9 @@ Workloads (BASELINE.json `configs`; `--workload`, default cfg2 = the configurati
   cfg5   MobiusLayer + gyroplane microbench: 2^20 rows x 512 -> 4096, forward + backward, bf16 tensor-core mode
 fp32 (cfg5: bf16 GEMM operands), synthetic data, random-init weights.  One "step" = one forward + loss + backward over
 one batch; for N > 1 each rank owns its own batch (weak scaling) and the step ends with ONE exchange of the flat
-gradient bucket: the repo's own peer-memory all-reduce kernel when the ranks can map each other (`config.exchange` =
-"p2p"), else NCCL ("nccl").
+gradient bucket: the repo's own all-reduce kernel over symmetric memory when the ranks can map each other - in-switch
+reduction with multimem.ld_reduce / multimem.st when the NVSwitch offers a multicast mapping (`config.exchange` = "nvls"),
+else peer loads / stores ("p2p") - else NCCL ("nccl").
 
 Prints ONE JSON line (rank 0).  `value` = device-timed whole-job samples/s with the batch resident in HBM (CUDA-graph
 replay of the step, per-step CUDA events, L2 flushed between steps); `e2e` = the same step through the public API with
@@ -492,7 +493,7 @@ def run_step(args, name, wl):
     if not args.no_graph:
         ts._capture()
     graph_on = ts.graph is not None
-    exchange = "none" if world == 1 else ("p2p" if ts.bucket._symm is not None else "nccl")
+    exchange = "none" if world == 1 else (("nvls" if ts.bucket.nvls else "p2p") if ts.bucket._symm is not None else "nccl")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def barrier():

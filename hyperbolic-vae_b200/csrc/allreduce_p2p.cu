@@ -104,6 +104,54 @@ k_allreduce_p2p(float* const* __restrict__ bufs, uint32_t* const* __restrict__ p
     block_sync_remote(pads, rank, world, slot);  // every rank's stores into this copy have landed
 }
 
+// ---- NVLS variant: the NVSwitch does the sum -----------------------------------------------------------------------
+// With the bucket also mapped at a MULTICAST address (torch symmetric memory's multicast_ptr), one
+// multimem.ld_reduce returns the sum of all W copies of a 16-byte word (reduced inside the switch) and one multimem.st
+// writes a word into all W copies: rank r handles slice r with 1/W of the loads of the peer-loop kernel above and ONE
+// NVLink round trip instead of W dependent ones.  Same barriers, same in-place/race-free slicing.
+__device__ __forceinline__ float4 mm_ld_reduce(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kArThreads)
+k_allreduce_nvls(float* __restrict__ mc, uint32_t* const* __restrict__ pads, int rank, int world, int64_t off, int64_t n,
+                 int slot_base, float scale) {
+    const int slot = slot_base + blockIdx.x * world;
+    block_sync_remote(pads, rank, world, slot);  // every rank's gradients are complete
+    const int64_t n4 = n >> 2;
+    const int64_t per = (n4 + world - 1) / world;
+    const int64_t lo = (int64_t)rank * per, hi = (lo + per < n4) ? lo + per : n4;
+    float* base = mc + off;
+    const int64_t stride = (int64_t)gridDim.x * kArThreads;
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += stride * kArUnroll) {
+        float4 acc[kArUnroll];
+#pragma unroll
+        for (int u = 0; u < kArUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < hi) acc[u] = mm_ld_reduce(base + 4 * i);
+        }
+#pragma unroll
+        for (int u = 0; u < kArUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < hi) {
+                float4 a = acc[u];
+                a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+                mm_st(base + 4 * i, a);
+            }
+        }
+    }
+    block_sync_remote(pads, rank, world, slot);  // every rank's multicast stores have landed in this copy
+}
+
 }  // namespace hvae
 
 using namespace hvae;
@@ -125,5 +173,20 @@ extern "C" int hvae_allreduce_p2p_f32(const void* buf_ptrs_dev, const void* pad_
     if (pad_slot_base < 1) return HVAE_EARG;  // word 0 is the error word
     k_allreduce_p2p<<<blocks, kArThreads, 0, (cudaStream_t)stream>>>((float* const*)buf_ptrs_dev, (uint32_t* const*)pad_ptrs_dev,
                                                                         rank, world, offset, n, pad_slot_base, scale);
+    return check_launch();
+}
+
+// NVLS flavour: mc_ptr = the bucket's MULTICAST address on this rank (one pointer, not a table); the switch reduces.
+// Everything else as hvae_allreduce_p2p_f32.  Requires NVSwitch multicast support (the caller checks that the
+// symmetric-memory handle has a multicast pointer).
+extern "C" int hvae_allreduce_nvls_f32(void* mc_ptr, const void* pad_ptrs_dev, int rank, int world, int64_t offset, int64_t n,
+                                       int pad_slot_base, float scale, int blocks, void* stream) {
+    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || n <= 0 || (n & 3) || (offset & 3) || offset < 0)
+        return HVAE_ESHAPE;
+    if (!mc_ptr || !pad_ptrs_dev) return HVAE_EARG;
+    if (blocks == 0) blocks = 32;
+    if (blocks < 1 || blocks > kArBlocks || pad_slot_base < 1) return HVAE_EARG;
+    k_allreduce_nvls<<<blocks, kArThreads, 0, (cudaStream_t)stream>>>((float*)mc_ptr, (uint32_t* const*)pad_ptrs_dev, rank, world,
+                                                                       offset, n, pad_slot_base, scale);
     return check_launch();
 }

@@ -51,12 +51,18 @@ class FlatGradBucket:
                          and os.environ.get("HVAE_DP_P2P", "1") != "0")
         self._symm = None
         self.p2p_blocks = 64  # grid of the peer-memory kernel; agreed across ranks below (block b meets block b)
+        self.nvls = False     # in-switch reduction (multimem) instead of the peer-load loop
         if symmetric:
             self.buffer, self._symm = self._alloc_symmetric(total, dev)
             if self._symm is not None:
                 nb = torch.tensor([int(os.environ.get("HVAE_AR_BLOCKS", "64"))], device=dev)
                 dist.all_reduce(nb, op=dist.ReduceOp.MIN)  # one value for the whole job, whatever each process's env says
                 self.p2p_blocks = max(1, min(128, int(nb.item())))
+                # NVLS (in-switch reduction) when the handle has a multicast mapping on EVERY rank; HVAE_DP_NVLS=0 turns it off
+                mc = torch.tensor([1 if (getattr(self._symm, "multicast_ptr", 0) and os.environ.get("HVAE_DP_NVLS", "1") != "0") else 0],
+                                  device=dev)
+                dist.all_reduce(mc, op=dist.ReduceOp.MIN)
+                self.nvls = bool(int(mc.item()))
         if self._symm is None:
             self.buffer = torch.zeros(total, device=dev, dtype=dt)
         for p, off in zip(self.params, self.offsets):
@@ -151,6 +157,11 @@ class FlatGradBucket:
         h = self._symm
         W = h.world_size
         base = 64 + site * C.lib().hvae_allreduce_p2p_slots(W)
+        if self.nvls:
+            # the NVSwitch reduces: multimem.ld_reduce / multimem.st on the bucket's multicast address
+            C.call("hvae_allreduce_nvls_f32", h.multicast_ptr, h.signal_pad_ptrs_dev, h.rank, W, offset, n, base,
+                   1.0 / W if average else 1.0, min(self.p2p_blocks, 32), C.stream())
+            return
         C.call("hvae_allreduce_p2p_f32", h.buffer_ptrs_dev, h.signal_pad_ptrs_dev, h.rank, W, offset, n, base,
                1.0 / W if average else 1.0, self.p2p_blocks, C.stream())
 

@@ -99,11 +99,18 @@ def _p2p_vs_nccl(rank, world):
         assert float((bucket.buffer - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
     bucket.check()   # no barrier timed out
     res["ok"] = True
+    res["path"] = "nvls" if bucket.nvls else "p2p"
     return res
 
 
-def test_p2p_allreduce_equals_nccl():
-    assert _spawn(_p2p_vs_nccl).get("ok")
+@pytest.mark.parametrize("nvls", ["1", "0"])
+def test_p2p_allreduce_equals_nccl(nvls, monkeypatch):
+    """nvls=1: in-switch reduction (multimem) when the box offers a multicast mapping, else it falls back to the peer loop;
+    nvls=0: the peer-load kernel."""
+    monkeypatch.setenv("HVAE_DP_NVLS", nvls)
+    res = _spawn(_p2p_vs_nccl)
+    assert res.get("ok")
+    print("exchange path:", res.get("path"))
 
 
 def _sharded_step(rank, world):
