@@ -131,16 +131,19 @@ k_allreduce_nvls(float* __restrict__ mc, uint32_t* const* __restrict__ pads, int
     const int64_t per = (n4 + world - 1) / world;
     const int64_t lo = (int64_t)rank * per, hi = (lo + per < n4) ? lo + per : n4;
     float* base = mc + off;
+    // latency-bound (a few MB): every thread puts kNvlsUnroll in-switch reductions in flight before it touches a result, and
+    // the grid is sized so that the slice is ONE such pass where it can be (128 blocks x 512 threads x 8 words = 8 MB)
+    constexpr int kNvlsUnroll = 8;
     const int64_t stride = (int64_t)gridDim.x * kArThreads;
-    for (int64_t i0 = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += stride * kArUnroll) {
-        float4 acc[kArUnroll];
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += stride * kNvlsUnroll) {
+        float4 acc[kNvlsUnroll];
 #pragma unroll
-        for (int u = 0; u < kArUnroll; ++u) {
+        for (int u = 0; u < kNvlsUnroll; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < hi) acc[u] = mm_ld_reduce(base + 4 * i);
         }
 #pragma unroll
-        for (int u = 0; u < kArUnroll; ++u) {
+        for (int u = 0; u < kNvlsUnroll; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < hi) {
                 float4 a = acc[u];
@@ -184,7 +187,11 @@ extern "C" int hvae_allreduce_nvls_f32(void* mc_ptr, const void* pad_ptrs_dev, i
     if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || n <= 0 || (n & 3) || (offset & 3) || offset < 0)
         return HVAE_ESHAPE;
     if (!mc_ptr || !pad_ptrs_dev) return HVAE_EARG;
-    if (blocks == 0) blocks = 32;
+    if (blocks == 0) {   // one pass of 8 words per thread over this rank's slice where 128 blocks allow it
+        const int64_t per4 = ((n >> 2) + world - 1) / world;
+        const int64_t want = (per4 + (int64_t)kArThreads * 8 - 1) / ((int64_t)kArThreads * 8);
+        blocks = (int)(want < 4 ? 4 : (want > kArBlocks ? kArBlocks : want));
+    }
     if (blocks < 1 || blocks > kArBlocks || pad_slot_base < 1) return HVAE_EARG;
     k_allreduce_nvls<<<blocks, kArThreads, 0, (cudaStream_t)stream>>>((float*)mc_ptr, (uint32_t* const*)pad_ptrs_dev, rank, world,
                                                                        offset, n, pad_slot_base, scale);

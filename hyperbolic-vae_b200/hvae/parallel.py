@@ -52,6 +52,7 @@ class FlatGradBucket:
         self._symm = None
         self.p2p_blocks = 64  # grid of the peer-memory kernel; agreed across ranks below (block b meets block b)
         self.nvls = False     # in-switch reduction (multimem) instead of the peer-load loop
+        self.nvls_blocks = 0  # 0: the kernel sizes its grid from the element count (identical on every rank)
         if symmetric:
             self.buffer, self._symm = self._alloc_symmetric(total, dev)
             if self._symm is not None:
@@ -112,8 +113,10 @@ class FlatGradBucket:
             g = p.grad
             if g is not None and g.data_ptr() != view.data_ptr():
                 if g.numel() >= (1 << 16):
-                    view.copy_(g)  # big tensors: a plain copy kernel fills the GPU; the multi-tensor kernel gives each
-                                   # tensor only numel/64K blocks (measured 10 us per 1.9 MB weight)
+                    # big tensors: an elementwise KERNEL that fills the GPU (the multi-tensor copy gives each tensor only
+                    # numel/64K blocks: 10 us per 1.9 MB weight).  Not Tensor.copy_: into symmetric memory torch issues it as a
+                    # DtoD memcpy, and three copy-engine nodes in the captured graph cost the step ~29 us of node hand-overs.
+                    torch.mul(g, 1.0, out=view)
                 else:
                     src.append(g if g.is_contiguous() else g.contiguous())
                     dst.append(view)
@@ -160,7 +163,7 @@ class FlatGradBucket:
         if self.nvls:
             # the NVSwitch reduces: multimem.ld_reduce / multimem.st on the bucket's multicast address
             C.call("hvae_allreduce_nvls_f32", h.multicast_ptr, h.signal_pad_ptrs_dev, h.rank, W, offset, n, base,
-                   1.0 / W if average else 1.0, min(self.p2p_blocks, 32), C.stream())
+                   1.0 / W if average else 1.0, self.nvls_blocks, C.stream())
             return
         C.call("hvae_allreduce_p2p_f32", h.buffer_ptrs_dev, h.signal_pad_ptrs_dev, h.rank, W, offset, n, base,
                1.0 / W if average else 1.0, self.p2p_blocks, C.stream())

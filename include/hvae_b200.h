@@ -231,7 +231,7 @@ int hvae_allreduce_p2p_f32(const void* buf_ptrs_dev, const void* pad_ptrs_dev, i
                            int64_t n, int pad_slot_base, float scale, int blocks, void* stream);
 /* NVLS flavour of the same exchange: mc_ptr is the bucket's NVSwitch MULTICAST address on this rank; rank r sums slice r
  * with multimem.ld_reduce (the switch adds the W copies) and writes it to all copies with multimem.st: 1/W of the loads
- * and one NVLink round trip instead of W dependent ones.  blocks: 0 = default 32; same on every rank. */
+ * and one NVLink round trip instead of W dependent ones.  blocks: 0 = sized from n (the same on every rank). */
 int hvae_allreduce_nvls_f32(void* mc_ptr, const void* pad_ptrs_dev, int rank, int world, int64_t offset, int64_t n,
                             int pad_slot_base, float scale, int blocks, void* stream);
 
