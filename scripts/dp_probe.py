@@ -20,25 +20,42 @@ def main():
     from hvae.parallel import FlatGradBucket
 
     out = {}
-    for nelem in (950_000, 4_000_000):
+    for nelem in (4096, 950_000, 4_000_000):
         params = [torch.nn.Parameter(torch.zeros(nelem, device=dev))]
         for path in ("nvls", "p2p", "nccl"):
             os.environ["HVAE_DP_NVLS"] = "1" if path == "nvls" else "0"
             b = FlatGradBucket(params, symmetric=None if path != "nccl" else False)
-            for blocks in ((8, 16, 32) if path == "nvls" else (32, 64, 128) if path == "p2p" else (0,)):
+            for blocks in ((8, 32, 128) if path == "nvls" else (32, 128) if path == "p2p" else (0,)):
                 if blocks:
                     b.p2p_blocks = blocks
-                for _ in range(20):
+                if path == "nvls":
+                    b.nvls_blocks = blocks
+                for _ in range(5):
                     b.all_reduce(average=False)
+                dist.barrier(device_ids=[local])
+                torch.cuda.synchronize()
+                # 50 exchanges captured in ONE CUDA graph: the replay is free of per-call host overhead
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    b.all_reduce(average=False)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    for _ in range(50):
+                        b.all_reduce(average=False)
+                g.replay()
                 dist.barrier(device_ids=[local])
                 torch.cuda.synchronize()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                for _ in range(200):
-                    b.all_reduce(average=False)
+                for _ in range(4):
+                    g.replay()
                 e.record()
                 e.synchronize()
                 out["%s_%d_b%d" % (path, nelem, blocks)] = round(s.elapsed_time(e) / 200 * 1e3, 2)
+                del g
             del b
     if rank == 0:
         print(json.dumps(out))

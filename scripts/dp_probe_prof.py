@@ -19,9 +19,11 @@ from hvae.train import TrainStep
 
 x = torch.rand(4096, 1, 28, 28, generator=torch.Generator().manual_seed(1000 + rank)).clamp(1e-5, 1 - 1e-5).to(dev)
 res = {}
-HP.FlatGradBucket.all_reduce = lambda self, average, group=None, async_op=False: None
-HP.FlatGradBucket.all_reduce_segment = lambda self, which, average, group=None: None
-for mode in ("plain", "symm"):
+EXCH = os.environ.get("PROBE_EXCHANGE", "0") == "1"
+if not EXCH:
+    HP.FlatGradBucket.all_reduce = lambda self, average, group=None, async_op=False: None
+    HP.FlatGradBucket.all_reduce_segment = lambda self, which, average, group=None: None
+for mode in (("symm",) if EXCH else ("plain", "symm")):
     os.environ["HVAE_DP_P2P"] = "0" if mode == "plain" else "1"
     os.environ["HVAE_DP_OVERLAP"] = "0"
     torch.manual_seed(42)
@@ -43,6 +45,10 @@ for mode in ("plain", "symm"):
     res[mode + "_total"] = round(sum(v[0] for v in agg.values()), 1)
     ts.graph = None
     del ts, m
+if EXCH:
+    ar = {k: v for k, v in res["symm"].items() if "allreduce" in k}
+    print("rank", rank, "kernel-time total", res["symm_total"], "all-reduce kernel:", ar, flush=True)
+    dist.barrier(device_ids=[local]); torch.cuda.synchronize(); os._exit(0)
 if rank == 0:
     print("totals", res["plain_total"], res["symm_total"])
     keys = set(res["plain"]) | set(res["symm"])
