@@ -291,3 +291,90 @@ extern "C" int hvae_recon_rows_bwd_f32(const float* in, const float* x, const fl
     }
     return check_launch();
 }
+
+// ---- loss tail of the pvae objective (training/old_pvae_train.py:53-58 with K samples): from the per-(sample, row)
+// negative log-likelihood and KL terms to the three scalars the step reports, in ONE launch per direction
+//   recon = sum_b mean_s nll[s,b],  kl = sum_b mean_s kld[s,b],  total = recon + beta kl
+// (torch: neg, mean, sum, neg, mean, sum, mul, add forward and as many small kernels backward - ~24 launches on 16 KB)
+namespace hvae {
+__global__ void __launch_bounds__(1024)
+k_pvae_loss_fwd(const float* __restrict__ nll, const float* __restrict__ kld, float* __restrict__ out, int64_t n, float inv_s,
+                float beta) {
+    __shared__ double sa[32], sb[32];
+    double a = 0.0, b = 0.0;   // 4096+ terms of O(1e3): keep the batch sums exact to fp32 rounding
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { a += (double)nll[i]; b += (double)kld[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double A = 0.0, B = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { A += sa[w]; B += sb[w]; }
+        const float recon = (float)(A * inv_s), kl = (float)(B * inv_s);
+        out[0] = recon + beta * kl;
+        out[1] = recon;
+        out[2] = kl;
+    }
+}
+// gout: upstream gradients of (total, recon, kl) (NULL entries = 0 are passed as zeros by the caller)
+__global__ void k_pvae_loss_bwd(const float* __restrict__ gout, float* __restrict__ gnll, float* __restrict__ gkld, int64_t n,
+                                float inv_s, float beta) {
+    const float ga = (gout[0] + gout[1]) * inv_s, gb = (beta * gout[0] + gout[2]) * inv_s;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        gnll[i] = ga;
+        gkld[i] = gb;
+    }
+}
+}  // namespace hvae
+
+// nll, kld: (S, B) -> out[3] = {total, recon, kl}
+extern "C" int hvae_pvae_loss_fwd_f32(const float* nll, const float* kld, float* out, int64_t S, int64_t B, float beta, void* stream) {
+    if (S <= 0 || B <= 0) return HVAE_ESHAPE;
+    if (!nll || !kld || !out) return HVAE_EARG;
+    hvae::k_pvae_loss_fwd<<<1, 1024, 0, (cudaStream_t)stream>>>(nll, kld, out, S * B, 1.0f / (float)S, beta);
+    return check_launch();
+}
+extern "C" int hvae_pvae_loss_bwd_f32(const float* gout, float* gnll, float* gkld, int64_t S, int64_t B, float beta, void* stream) {
+    if (S <= 0 || B <= 0) return HVAE_ESHAPE;
+    if (!gout || !gnll || !gkld) return HVAE_EARG;
+    const int64_t n = S * B;
+    hvae::k_pvae_loss_bwd<<<(unsigned)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64), 256, 0, (cudaStream_t)stream>>>(gout, gnll, gkld, n,
+                                                                                                               1.0f / (float)S, beta);
+    return check_launch();
+}
+
+// ---- posterior scale head of the pvae encoder (scripts/_9_pvae_replicate.py: softplus(fc22(e)) + 1e-5) together with the
+// clamp RiemannianNormal applies to it (distributions/old_pvae_riemannian_normal.py:30: scale.clamp(0.1, 7)):
+//   sigma = clamp(softplus(h) + eps, lo, hi);  d sigma / d h = sigmoid(h) inside the clamp, 0 where it binds.
+namespace hvae {
+__global__ void k_sigma_head_fwd(const float* __restrict__ h, float* __restrict__ out, int64_t n, float eps, float lo, float hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = h[i];
+    const float sp = (v > 20.0f) ? v : log1pf(expf(v));   // torch.nn.functional.softplus (threshold 20)
+    out[i] = fminf(fmaxf(sp + eps, lo), hi);
+}
+__global__ void k_sigma_head_bwd(const float* __restrict__ h, const float* __restrict__ g, float* __restrict__ gh, int64_t n, float eps,
+                                 float lo, float hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = h[i];
+    const float sp = (v > 20.0f) ? v : log1pf(expf(v));
+    const float s = sp + eps;
+    const float d = (v > 20.0f) ? 1.0f : sigmoid_acc(v);
+    gh[i] = (s >= lo && s <= hi) ? g[i] * d : 0.0f;      // clamp passes the gradient on [lo, hi] (torch semantics)
+}
+}  // namespace hvae
+
+extern "C" int hvae_sigma_head_fwd_f32(const float* h, float* out, int64_t n, float eps, float lo, float hi, void* stream) {
+    if (n <= 0) return HVAE_ESHAPE;
+    if (!h || !out) return HVAE_EARG;
+    hvae::k_sigma_head_fwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, out, n, eps, lo, hi);
+    return check_launch();
+}
+extern "C" int hvae_sigma_head_bwd_f32(const float* h, const float* g, float* gh, int64_t n, float eps, float lo, float hi, void* stream) {
+    if (n <= 0) return HVAE_ESHAPE;
+    if (!h || !g || !gh) return HVAE_EARG;
+    hvae::k_sigma_head_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, g, gh, n, eps, lo, hi);
+    return check_launch();
+}

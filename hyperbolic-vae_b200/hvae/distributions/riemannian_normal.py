@@ -111,13 +111,15 @@ class RiemannianNormal(torch.distributions.Distribution):
     def mean(self):
         return self.loc
 
-    def __init__(self, loc: Tensor, scale: Tensor, manifold: PoincareBall, validate_args=None):
+    def __init__(self, loc: Tensor, scale: Tensor, manifold: PoincareBall, validate_args=None, *, scale_is_clamped: bool = False):
+        """scale_is_clamped (keyword-only extension): the caller already applied the reference's clamp(0.1, 7), e.g. inside
+        the fused scale head (ops.sigma_head) - it is not applied a second time."""
         if validate_args or RiemannianNormal.validate_loc:
             assert not (torch.isnan(loc).any() or torch.isnan(scale).any())
             manifold.assert_check_point_on_manifold(loc)
         self.manifold = manifold
         self.loc = loc
-        self.scale = scale.clamp(min=0.1, max=7.0)
+        self.scale = scale if scale_is_clamped else scale.clamp(min=0.1, max=7.0)
         D = loc.shape[-1]
         self.radius = HyperbolicRadius(D, manifold.c_value, self.scale)
         self.direction = HypersphericalUniform(D - 1, device=loc.device)

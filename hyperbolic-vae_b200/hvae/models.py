@@ -308,10 +308,14 @@ class PvaeMnist(nn.Module):
             self._prior_cache = (key, p)
         return p
 
-    def encode(self, x):
+    def encode(self, x, clamp_sigma=False):
+        """clamp_sigma: return sigma already clamped to RiemannianNormal's [0.1, 7] (one fused kernel with the softplus)."""
         e = self.enc(x.view(x.shape[0], -1))
         mu = self.manifold.expmap0(self.fc21(e))
-        return mu, F.softplus(self.fc22(e)) + 1e-5
+        h = self.fc22(e)
+        if clamp_sigma and h.is_cuda:
+            return mu, ops.sigma_head(h, 1e-5, 0.1, 7.0)
+        return mu, F.softplus(h) + 1e-5
 
     def decode(self, z):
         return self.fc31(F.relu(self.dec0(z)))
@@ -320,19 +324,18 @@ class PvaeMnist(nn.Module):
         from .distributions.riemannian_normal import RiemannianNormal
 
         B = x.shape[0]
-        mu, sigma = self.encode(x)
-        q = RiemannianNormal(mu, sigma, self.manifold)
+        mu, sigma = self.encode(x, clamp_sigma=self.fused)
+        q = RiemannianNormal(mu, sigma, self.manifold, scale_is_clamped=self.fused and sigma.is_cuda)
         zs = q.rsample(torch.Size([1]), alpha=alpha, r=r)  # (1,B,D)
         logits = self.decode(zs)
-        if self.fused:
-            lpx_z = -ops.bernoulli_nll_rows(logits, x.view(B, -1))  # one row kernel per direction
-        else:
-            lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
         p = self._prior()
         if self.fused:
+            nll = ops.bernoulli_nll_rows(logits, x.view(B, -1))  # one row kernel per direction
             kld = q.kl_mc(zs, p)  # one kernel: both log-densities and their difference
-        else:
-            kld = q.log_prob(zs).sum(-1) - p.log_prob(zs).sum(-1)
+            total, recon, kl = ops.pvae_loss(nll, kld, self.beta)   # the three scalars in one launch (double accumulation)
+            return dict(loss_total=total, recon_loss=recon, kl_loss=kl)
+        lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)
+        kld = q.log_prob(zs).sum(-1) - p.log_prob(zs).sum(-1)
         recon = -lpx_z.mean(0).sum()
         kl = kld.mean(0).sum()
         return dict(loss_total=recon + self.beta * kl, recon_loss=recon, kl_loss=kl)

@@ -1409,3 +1409,99 @@ def recon_rows(inp: Tensor, x: Tensor, kind: int, temperature: float = 1.0) -> T
     B, N = inp.shape[-2:]
     out = recon_rows_fwd(_c(inp).view(-1, B, N), _c(x.detach()).view(B, N), int(kind), float(temperature))
     return out.view(*lead, B)
+
+
+# ---------------------------------------------------------------------------------------------------
+# loss tail of the pvae objective: (S,B) nll and KL terms -> {total, recon, kl} in one launch per direction
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::pvae_loss_fwd", mutates_args=())
+def pvae_loss_fwd(nll: Tensor, kld: Tensor, beta: float) -> Tensor:
+    C.require_cuda(nll, kld)
+    S, B = nll.shape
+    out = nll.new_empty(3)
+    C.call("hvae_pvae_loss_fwd_f32", C.ptr(nll), C.ptr(kld), C.ptr(out), S, B, beta, C.stream())
+    return out
+
+
+@pvae_loss_fwd.register_fake
+def _(nll, kld, beta):
+    return nll.new_empty(3)
+
+
+@_op("hvae::pvae_loss_bwd", mutates_args=())
+def pvae_loss_bwd(gout: Tensor, S: int, B: int, beta: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(gout)
+    gnll, gkld = gout.new_empty(S, B), gout.new_empty(S, B)
+    C.call("hvae_pvae_loss_bwd_f32", C.ptr(gout), C.ptr(gnll), C.ptr(gkld), S, B, beta, C.stream())
+    return gnll, gkld
+
+
+@pvae_loss_bwd.register_fake
+def _(gout, S, B, beta):
+    return gout.new_empty(S, B), gout.new_empty(S, B)
+
+
+def _pl_setup(ctx, inputs, output):
+    ctx.S, ctx.B = inputs[0].shape
+    ctx.beta = inputs[2]
+
+
+def _pl_backward(ctx, g):
+    gnll, gkld = pvae_loss_bwd(_c(g), ctx.S, ctx.B, ctx.beta)
+    return gnll, gkld, None
+
+
+pvae_loss_fwd.register_autograd(_pl_backward, setup_context=_pl_setup)
+
+
+def pvae_loss(nll: Tensor, kld: Tensor, beta: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (loss_total, recon, kl) scalars: recon = sum_b mean_s nll, kl = sum_b mean_s kld, total = recon + beta kl."""
+    out = pvae_loss_fwd(_c(nll), _c(kld), float(beta))
+    return out[0], out[1], out[2]
+
+
+# ---------------------------------------------------------------------------------------------------
+# posterior scale head: clamp(softplus(h) + eps, lo, hi), one launch per direction
+# ---------------------------------------------------------------------------------------------------
+@_op("hvae::sigma_head_fwd", mutates_args=())
+def sigma_head_fwd(h: Tensor, eps: float, lo: float, hi: float) -> Tensor:
+    C.require_cuda(h)
+    out = torch.empty_like(h)
+    C.call("hvae_sigma_head_fwd_f32", C.ptr(h), C.ptr(out), h.numel(), eps, lo, hi, C.stream())
+    return out
+
+
+@sigma_head_fwd.register_fake
+def _(h, eps, lo, hi):
+    return torch.empty_like(h)
+
+
+@_op("hvae::sigma_head_bwd", mutates_args=())
+def sigma_head_bwd(h: Tensor, g: Tensor, eps: float, lo: float, hi: float) -> Tensor:
+    C.require_cuda(h, g)
+    gh = torch.empty_like(h)
+    C.call("hvae_sigma_head_bwd_f32", C.ptr(h), C.ptr(g), C.ptr(gh), h.numel(), eps, lo, hi, C.stream())
+    return gh
+
+
+@sigma_head_bwd.register_fake
+def _(h, g, eps, lo, hi):
+    return torch.empty_like(h)
+
+
+def _sh_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.args = inputs[1:]
+
+
+def _sh_backward(ctx, g):
+    (h,) = ctx.saved_tensors
+    return sigma_head_bwd(h, _c(g), *ctx.args), None, None, None
+
+
+sigma_head_fwd.register_autograd(_sh_backward, setup_context=_sh_setup)
+
+
+def sigma_head(h: Tensor, eps: float = 1e-5, lo: float = 0.1, hi: float = 7.0) -> Tensor:
+    """clamp(softplus(h) + eps, lo, hi): the pvae encoder's scale head and RiemannianNormal's clamp in one kernel."""
+    return sigma_head_fwd(_c(h), float(eps), float(lo), float(hi))

@@ -203,6 +203,16 @@ int hvae_bce_logits_rows_fwd_f32(const float* logits, const float* x, float* nll
 int hvae_bce_logits_rows_bwd_f32(const float* logits, const float* x, const float* gnll, float* glogits, int64_t S,
                                  int64_t B, int64_t N, void* stream);
 
+/* loss tail of the pvae objective (hyperbolic_vae/training/old_pvae_train.py:53-58): nll, kld (S,B) ->
+ * out[3] = {recon + beta kl, recon = sum_b mean_s nll, kl = sum_b mean_s kld}; backward from gout[3]. */
+int hvae_pvae_loss_fwd_f32(const float* nll, const float* kld, float* out, int64_t S, int64_t B, float beta, void* stream);
+int hvae_pvae_loss_bwd_f32(const float* gout, float* gnll, float* gkld, int64_t S, int64_t B, float beta, void* stream);
+
+/* posterior scale head: sigma = clamp(softplus(h) + eps, lo, hi) - the encoder's softplus(fc22(e)) + 1e-5
+ * (scripts/_9_pvae_replicate.py) fused with RiemannianNormal's scale.clamp(0.1, 7) (old_pvae_riemannian_normal.py:30). */
+int hvae_sigma_head_fwd_f32(const float* h, float* out, int64_t n, float eps, float lo, float hi, void* stream);
+int hvae_sigma_head_bwd_f32(const float* h, const float* g, float* gh, int64_t n, float eps, float lo, float hi, void* stream);
+
 /* ---- generic reconstruction heads, per-(sample,row) sums over the feature axis.  `in` (S,B,N) is the
  * decoder output (or its pre-sigmoid activation for the *_SIGMOID kinds: the decoder's final nn.Sigmoid is fused),
  * x (B,N) the target, broadcast over S; out (S,B).  reference: F.mse_loss(x_hat, x, "sum") models/vae_hyperbolic.py:219;
