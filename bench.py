@@ -258,49 +258,48 @@ def _time_flushed(fn, flush, reps=20, warm=3):
     return sum(mid) / len(mid)
 
 
-def x3_traffic():
-    """DRAM bytes per launch of the trunk GEMM from the committed ncu --set full capture (mean of the five launches)."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_x3_traffic.json")))["traffic_bytes_per_launch_mean"]
-    except Exception:
-        return None
-
-
 def trunk_roofline(gemms, device, pk, pk_kind, flush):
     """The fp32-accurate tensor-core GEMMs of one step, timed as GEMM launches on pre-split operands, next to cuBLAS
     fp32 (TF32 off) on the same shapes in the same run.  gemms: [(M, N, K)].  frac is on the ALGORITHMIC fp32 flops
-    (2MNK); the kernel executes 6x that as bf16 piece products (executed_*)."""
+    (2MNK); the kernel executes 3x that as fp16 piece products (executed_*)."""
+    import ctypes
+
     from hvae import _cabi as C
     from hvae import ops
 
     g = torch.Generator(device=device).manual_seed(2)
-    tc_ops, cb_ops = [], []
+    tc_ops, cb_ops, plans = [], [], []
+    bn, sp, st = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     for (m_, n_, k_) in gemms:
         a, b = torch.randn(m_, k_, device=device, generator=g), torch.randn(n_, k_, device=device, generator=g)
-        tc_ops.append((ops.split3(a), ops.split3(b), m_, n_, k_))
+        a_s, a_i, _, _ = ops.split2h_both(a, True, False)
+        b_s, b_i, _, _ = ops.split2h_both(b, True, False)
+        tc_ops.append((a_s, a_i, b_s, b_i, m_, n_, k_))
         cb_ops.append((a, b))
+        C.lib().hvae_gemm_x2s_plan(m_, n_, k_, ctypes.addressof(bn), ctypes.addressof(sp), ctypes.addressof(st))
+        plans.append({"tile": [128, bn.value], "split_k": sp.value, "stages": st.value})
 
-    def run_x3():
-        for a_s, b_s, m_, n_, k_ in tc_ops:
-            ops.gemm_x3s(a_s, False, b_s, False, None, False, m_, n_, k_)
+    def run_x2():
+        for a_s, a_i, b_s, b_i, m_, n_, k_ in tc_ops:
+            ops.gemm_x2s(a_s, a_i, b_s, b_i, None, False, m_, n_, k_)
 
     def run_cublas():
         for a, b in cb_ops:
             torch.mm(a, b.t())
 
-    t_g, t_c = _time_flushed(run_x3, flush), _time_flushed(run_cublas, flush)
+    t_g, t_c = _time_flushed(run_x2, flush), _time_flushed(run_cublas, flush)
     fl = sum(2.0 * m_ * n_ * k_ for (m_, n_, k_) in gemms)
-    n_g = sum(C.lib().hvae_gemm_x3s_num_launches(m_, n_, k_) for (m_, n_, k_) in gemms)
-    return {"bound": "tensor", "kernel": "k_tc_gemm<EPI_X3> (trunk dense layers: fp32-accurate split-bf16 tcgen05 GEMM)",
+    n_g = sum(C.lib().hvae_gemm_x2s_num_launches(m_, n_, k_) for (m_, n_, k_) in gemms)
+    return {"bound": "tensor", "kernel": "k_x2_gemm (trunk dense layers: fp32-accurate two-piece fp16 tcgen05 GEMM, power-of-two row scales)",
             "achieved": fl / t_g / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t_g / 1e12 / pk["bf16_tflops"],
-            "traffic": x3_traffic(), "peak_source": pk_kind, "launch_us": t_g / len(gemms) * 1e6, "launches_per_step": n_g,
-            "algorithmic_flops_per_step": fl, "executed_tflops": 6.0 * fl / t_g / 1e12,
-            "executed_frac": 6.0 * fl / t_g / 1e12 / pk["bf16_tflops"],
+            "traffic": None, "peak_source": pk_kind, "launch_us": t_g / len(gemms) * 1e6, "launches_per_step": n_g,
+            "algorithmic_flops_per_step": fl, "executed_tflops": 3.0 * fl / t_g / 1e12,
+            "executed_frac": 3.0 * fl / t_g / 1e12 / pk["bf16_tflops"],
             "cublas_fp32_same_shapes": {"us": t_c * 1e6, "tflops": fl / t_c / 1e12, "ours_over_cublas_time": t_g / t_c,
                                         "note": "torch.mm fp32, TF32 off, same run, same shapes, L2 flushed"},
-            "gemm_shapes_MNK": gemms,
+            "gemm_shapes_MNK": gemms, "plans": plans,
             "note": "achieved / frac = ALGORITHMIC fp32 flops (sum of 2MNK over the step's GEMMs) / launch time against the "
-                    "measured bf16 tensor peak; the kernel executes 6x that as bf16 piece products (3-way operand split, "
+                    "measured 16-bit tensor peak; the kernel executes 3x that as fp16 piece products (two-piece operand split, "
                     "executed_*: what the tensor pipe actually does; the B200 fp32 FMA peak is ~72 TFLOP/s)"}
 
 
@@ -551,7 +550,7 @@ def run_step(args, name, wl):
                  "optimizer": "fused RiemannianAdam step inside the timed step (hvae.optim, one launch)" if opt is not None else
                               "none (the metric is fwd+bwd; --optimizer adds the fused Riemannian Adam step)",
                  "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                 "trunk": "hvae.layers.Linear -> tcgen05 split-bf16 GEMM (fp32-accurate, own kernel) for GEMM-sized layers; "
+                 "trunk": "hvae.layers.Linear -> tcgen05 two-piece fp16 GEMM with power-of-two row scales (fp32-accurate, own kernel) for GEMM-sized layers; "
                           "small layers and the conv stack of model B run on cuBLAS / cuDNN with TF32 off"}
         line = {
             "metric": "train samples/sec (fwd+bwd)", "value": world * B * args.steps / dev_s, "unit": "samples/s",

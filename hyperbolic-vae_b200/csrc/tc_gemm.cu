@@ -1306,6 +1306,15 @@ extern "C" int hvae_mobius_matvec_tc_fwd_f32(const float* x, const float* M, flo
         if (rc != HVAE_OK) return rc;
         tc::k_rows_to_bf16<<<(unsigned)((F + 7) / 8), 256, 0, s>>>(g32, g16, nullptr, F, F);
     }
+    if (B >= 1024 && P >= 128 && (P % 4) == 0) {
+        // A-resident pair kernel: the x G tiles, the row factor and the scaled x M^T tiles of an m-block in ONE kernel
+        tc2::Params2 q{};
+        q.D = y; q.M = B; q.N = P; q.K = F; q.splits = 1; q.x2 = x2; q.mxsq_out = mxsq_out;
+        const Ball bl = make_ball(c);
+        q.gp.c = bl.c; q.gp.sc = bl.sc; q.gp.rsc = bl.rsc; q.gp.maxnorm = bl.maxnorm;
+        const int rc = tc2::launch_gemm2(tc2::EPI_MOBIUS_F, a16, b16, g16, q, s);
+        if (rc != HVAE_ESHAPE) return rc;   // (not eligible for the A-resident schedule: the three-kernel path below)
+    }
     int q_planes = 0;
     {   // q_b = <x_b G, x_b> partials
         tc::Params prm{};

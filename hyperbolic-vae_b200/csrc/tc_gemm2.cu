@@ -174,6 +174,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const int S = (!ARES && prm.splits > 1) ? prm.splits : 1;
     // work unit: one output tile (x split) when streaming, one m-block with all its n-tiles when A-resident
     const int64_t units = ARES ? m_tiles : m_tiles * n_tiles * S;
+    // MOBIUS_F (A-resident only): column tiles of the Gram operand ahead of every m-block's n-tiles
+    const int g_tiles = (EPI == EPI_MOBIUS_F) ? (int)((prm.K + kTileN - 1) / kTileN) : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -210,12 +212,15 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const int64_t mt = ARES ? u : tile / n_tiles;
                 const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
                 const int m0 = (int)(mt * kPairM + rank * BMC);
-                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                for (int64_t nt = nt0 - g_tiles; nt < nt1; ++nt) {
                     // a ragged last n-tile is issued as a narrower MMA (N rounded up to 16): each CTA stages N/2 of its columns
-                    const int ncols = (EPI == EPI_GEO) ? kTileN : tile_cols(prm.N, nt);
-                    const int n0 = (EPI == EPI_GEO) ? (int)(nt * TN) : (int)(nt * kTileN + rank * (ncols >> 1));
+                    // (MOBIUS_F: tiles nt < 0 are the column tiles of the (K, K) Gram operand)
+                    const bool gram = nt < 0;
+                    const int ncols = (EPI == EPI_GEO) ? kTileN : (gram ? tile_cols(prm.K, nt + g_tiles) : tile_cols(prm.N, nt));
+                    const int n0 = (EPI == EPI_GEO) ? (int)(nt * TN) : (int)((gram ? nt + g_tiles : nt) * kTileN + rank * (ncols >> 1));
+                    if (EPI == EPI_MOBIUS_F) mb = gram ? &map_b2 : &map_b;
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        if (ARES && nt == 0) {
+                        if (ARES && nt == nt0 - g_tiles) {
                             // slice kb of this m-block's panel, as soon as the previous m-block's last n-tile is done with it
                             mbar_wait(aempty_bar(kb), pphase ^ 1u);
                             if (rank == 0) mbar_expect_tx(afull_bar(kb), 2u * TILE_A_BYTES);
@@ -255,14 +260,14 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const int sp = ARES ? 0 : (int)(u % S);
                 const int kb0 = (int)((int64_t)sp * k_blocks / S), kb1 = (int)((int64_t)(sp + 1) * k_blocks / S);
                 const int64_t nt0 = ARES ? 0 : tile % n_tiles, nt1 = ARES ? n_tiles : nt0 + 1;
-                for (int64_t nt = nt0; nt < nt1; ++nt) {
+                for (int64_t nt = nt0 - g_tiles; nt < nt1; ++nt) {
                     mbar_wait(tempty_bar(as), aphase ^ 1u);   // the epilogues of BOTH CTAs have drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * kTileN);
-                    const int ncols = (EPI == EPI_GEO) ? kTileN : tile_cols(prm.N, nt);
+                    const int ncols = (EPI == EPI_GEO) ? kTileN : (nt < 0 ? tile_cols(prm.K, nt + g_tiles) : tile_cols(prm.N, nt));
                     const uint32_t idesc_n = (kIdesc2 & ~(0x3Fu << 17)) | ((uint32_t)(ncols >> 3) << 17);
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        if (ARES && nt == 0) {
+                        if (ARES && nt == nt0 - g_tiles) {
                             mbar_wait(afull_bar(kb), pphase);     // both CTAs' slices kb of the panel have landed
                             tc_fence_after();
                         }
@@ -300,7 +305,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         const int cg = (warp - 2) >> 2;
         const uint32_t stage_buf = stg_base + (uint32_t)(warp - 2) * SBYTES;      // this warp's staging box
         const uint32_t lead_tempty = mapa(tempty_bar(0), 0);
-        int as = 0;
+        int as = 0, mparity = 0;
         uint32_t aphase = 0, gphase = 0;
         constexpr int COLS = TN / kCG;   // 64 (32 for GEO)
         const uint32_t colc_w = colc_base + (uint32_t)(warp - 2) * (uint32_t)(kTileN / kCG) * 16u;   // this warp's column constants
@@ -314,7 +319,64 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           const bool rok = grow < prm.M;
           float rs = 1.0f, x2r = 0.0f, cf = 0.0f;
           if ((EPI == EPI_MOBIUS || (EPI == EPI_PLAIN && prm.rowscale)) && rok) rs = __ldg(prm.rowscale + grow);
-          if ((EPI == EPI_GYRO || EPI == EPI_GYRO_LEAN || EPI == EPI_GEO || EPI == EPI_GYRO_BWD) && rok) x2r = __ldg(prm.x2 + grow);
+          if ((EPI == EPI_GYRO || EPI == EPI_GYRO_LEAN || EPI == EPI_GEO || EPI == EPI_GYRO_BWD || EPI == EPI_MOBIUS_F) && rok)
+              x2r = __ldg(prm.x2 + grow);
+          if (EPI == EPI_MOBIUS_F) {
+              // |M x_b|^2 = x_b^T G x_b: accumulator rows of x G dotted with the row of x the MMAs read (the resident bf16
+              // panel: row r of k-block kb at a_tile(kb) + 128 r, 16-byte chunk ch at position ch ^ (r % 8)).  The 4 column
+              // groups x g_tiles partial sums of a row meet in shared memory (the column-constant slices, unused here; two
+              // buffers alternate between m-blocks) in a fixed order: deterministic.
+              float* part = reinterpret_cast<float*>(smem_raw + (colc_base - raw)) + (mparity ? 2 * kCG * BMC : 0);
+              const int rloc = q * 32 + lane;
+              for (int t = 0; t < g_tiles; ++t) {
+                  mbar_wait(tfull_bar(as), aphase);
+                  tc_fence_after();
+                  float accr = 0.0f;
+#pragma unroll 1
+                  for (int cb = cg * COLS; cb < (cg + 1) * COLS; cb += 32) {
+                      float v[32];
+                      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kTileN + cb), v);
+                      if (cb + 32 >= (cg + 1) * COLS) {
+                          tc_fence_before();
+                          __syncwarp();
+                          if (lane == 0) mbar_arrive_cluster(lead_tempty + 8u * as);
+                      }
+                      const int j0 = t * kTileN + cb;           // contraction index of the chunk's first column
+                      const uint32_t rowa = a_tile(j0 >> 6) + (uint32_t)rloc * 128u;
+                      const int ch0 = (j0 & 63) >> 3;
+#pragma unroll
+                      for (int cc = 0; cc < 4; ++cc) {
+                          if (j0 + 8 * cc < prm.K) {             // (K % 8 == 0; columns past K hold stale accumulators)
+                              uint32_t w0, w1, w2, w3;
+                              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                           : "r"(rowa + (uint32_t)(((ch0 + cc) ^ (lane & 7)) << 4)) : "memory");
+                              const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+                              for (int e = 0; e < 4; ++e) {
+                                  accr = fmaf(v[8 * cc + 2 * e], __uint_as_float(ww[e] << 16), accr);
+                                  accr = fmaf(v[8 * cc + 2 * e + 1], __uint_as_float(ww[e] & 0xffff0000u), accr);
+                              }
+                          }
+                      }
+                  }
+                  part[(t * kCG + cg) * BMC + rloc] = accr;
+                  if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
+              }
+              asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // the epilogue warps of this CTA only
+              float mx2 = 0.0f;
+              for (int i = 0; i < g_tiles * kCG; ++i) mx2 += part[i * BMC + rloc];
+              mx2 = fmaxf(mx2, 0.0f);
+              if (prm.mxsq_out && cg == 0 && rok) prm.mxsq_out[grow] = mx2;
+              // y_b = rs (M x_b): geoopt mobius_matvec's rescale, then project (k_mobius_rowscale's arithmetic)
+              const float xn = fmaxf(sqrtf(x2r), kMinNorm);
+              const float mxn_raw = sqrtf(mx2), mxn = fmaxf(mxn_raw, kMinNorm);
+              const float tt = tanh_c(mxn / xn * artanh_c(prm.gp.sc * xn));
+              rs = prm.gp.rsc * tt / mxn;
+              const float yn = fmaxf(prm.gp.rsc * tt * (mxn_raw / mxn), kMinNorm);
+              if (yn > prm.gp.maxnorm) rs = rs / yn * prm.gp.maxnorm;
+              if (mx2 == 0.0f) rs = 0.0f;
+              mparity ^= 1;
+          }
           const bool axpy = (EPI == EPI_PLAIN) && prm.axpy_x != nullptr;
           if (axpy && rok) cf = prm.axpy_coef ? __ldg(prm.axpy_coef + grow) : 1.0f;
           for (int64_t nt = nt0; nt < nt1; ++nt) {
@@ -422,7 +484,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             }
                         }
                     }
-                } else if (EPI == EPI_MOBIUS) {
+                } else if (EPI == EPI_MOBIUS || EPI == EPI_MOBIUS_F) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] *= rs;
                 } else if (EPI == EPI_ROWDOT) {
@@ -547,7 +609,44 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     // CU_TENSOR_MAP_SWIZZLE_128B (32 columns: c ^ (row % 8)) / SWIZZLE_64B (16 columns: c ^ ((row / 2) % 4))
 #pragma unroll
                     for (int sb = 0; sb < 32 / SB_COLS; ++sb) {
+#ifdef HVAE_EXPERIMENT
+                        if (prm.dbg & 8) {
+                            // experiment: the same staging box, drained by coalesced st.global instead of a TMA store
+                            constexpr int CPR = SB_COLS / 4, RPI = 32 / CPR;   // 16-byte chunks per row, rows per instruction
+                            __syncwarp();
+                            {
+                                const uint32_t rowp = stage_buf + (uint32_t)lane * (uint32_t)(SB_COLS * 4);
+                                const int swz = ARES ? ((lane >> 1) & 3) : (lane & 7);
+#pragma unroll
+                                for (int c = 0; c < CPR; ++c) {
+                                    const int e0 = sb * SB_COLS + 4 * c;
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (uint32_t)((c ^ swz) << 4)),
+                                                 "f"(v[e0]), "f"(v[e0 + 1]), "f"(v[e0 + 2]), "f"(v[e0 + 3]) : "memory");
+                                }
+                            }
+                            __syncwarp();
+                            const int64_t nb = n0 + sb * SB_COLS;
+                            float* dpl = prm.D + (int64_t)sp * prm.M * prm.N;
+#pragma unroll
+                            for (int it = 0; it < 32 / RPI; ++it) {
+                                const int r = it * RPI + lane / CPR, c = lane % CPR;
+                                const int swz = ARES ? ((r >> 1) & 3) : (r & 7);
+                                float4 o;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                                             : "r"(stage_buf + (uint32_t)r * (uint32_t)(SB_COLS * 4) + (uint32_t)((c ^ swz) << 4)) : "memory");
+                                const int64_t gr = row_w + r, gc = nb + 4 * c;
+                                if (gr < prm.M && gc + 4 <= prm.N) {
+                                    float4* dst = reinterpret_cast<float4*>(dpl + gr * prm.N + gc);
+                                    if (prm.dbg & 32) __stcs(dst, o); else *dst = o;
+                                }
+                            }
+                            continue;
+                        }
+#endif
                         // the previous box of this warp must have been read out of shared memory by its TMA store
+#ifdef HVAE_EXPERIMENT
+                        if (!(prm.dbg & 16))
+#endif
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         __syncwarp();
                         const uint32_t rowp = stage_buf + (uint32_t)lane * (uint32_t)(SB_COLS * 4);
@@ -643,6 +742,10 @@ static int launch_t(const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_b
 #ifdef HVAE_EXPERIMENT
     if (prm.dbg & 4) ares = false;
 #endif
+    if (EPI == EPI_MOBIUS_F) {
+        if (!ares) return HVAE_ESHAPE;
+        if (!make_map(&mb2, B2, prm.K, prm.K, BNH, 0)) return HVAE_ELAUNCH;   // G: (K, K) bf16
+    }
     // output: fp32 (S, M, N), boxes of 32 rows x 32 (16) columns through swizzled staging; ROWDOT writes no matrix
     mg = ma;
     if (EPI == EPI_GYRO_BWD) {
@@ -653,14 +756,16 @@ static int launch_t(const __nv_bfloat16* A, const __nv_bfloat16* B, const __nv_b
         md = ma;
     }
     // per-device attribute (a process may drive several GPUs): set on every launch, a cheap driver call
-    cudaFuncSetAttribute(k_tc_gemm2<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (EPI != EPI_MOBIUS_F)
+        cudaFuncSetAttribute(k_tc_gemm2 < EPI == EPI_MOBIUS_F ? EPI_MOBIUS : EPI, false >, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES);
     cudaFuncSetAttribute(k_tc_gemm2<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_ARES);
     const int64_t units = ares ? m_tiles : m_tiles * n_tiles * S;
     const int pairs = (int)(units < kNumSMs / 2 ? units : kNumSMs / 2);
     if (ares)
         k_tc_gemm2<EPI, true><<<2 * pairs, THREADS, SMEM_BYTES_ARES, s>>>(ma, mb, mb2, md, mg, prm);
-    else
-        k_tc_gemm2<EPI, false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(ma, mb, mb2, md, mg, prm);
+    else if (EPI != EPI_MOBIUS_F)
+        k_tc_gemm2 < EPI == EPI_MOBIUS_F ? EPI_MOBIUS : EPI, false ><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(ma, mb, mb2, md, mg, prm);
     return check_launch();
 }
 
@@ -678,7 +783,8 @@ int launch_gemm2(int epi, const __nv_bfloat16* A, const __nv_bfloat16* B, const 
             if (prm.gp.flags == (uint32_t)HVAE_GYRO_SIGNED) return launch_t<EPI_GYRO_LEAN>(A, B, nullptr, prm, s);
             return launch_t<EPI_GYRO>(A, B, nullptr, prm, s);
         case EPI_ROWDOT: return launch_t<EPI_ROWDOT>(A, B, nullptr, prm, s);
-        case EPI_MOBIUS: return launch_t<EPI_MOBIUS>(A, B, nullptr, prm, s);
+        case EPI_MOBIUS: return prm.rowscale ? launch_t<EPI_MOBIUS>(A, B, nullptr, prm, s) : HVAE_EARG;
+        case EPI_MOBIUS_F: return (B2 && prm.x2) ? launch_t<EPI_MOBIUS_F>(A, B, B2, prm, s) : HVAE_EARG;
         case EPI_GEO: return B2 ? launch_t<EPI_GEO>(A, B, B2, prm, s) : HVAE_EARG;
         case EPI_GYRO_BWD:
             return (prm.g && prm.D16 && prm.srow && prm.vcol && (prm.N % 8) == 0) ? launch_t<EPI_GYRO_BWD>(A, B, nullptr, prm, s) : HVAE_EARG;

@@ -11,7 +11,11 @@ namespace tc2 {
 
 // EPI_GYRO: any flag combination of the a == p gyroplane (launch_gemm2 picks the lean instantiation EPI_GYRO_LEAN for the
 // plain signed distance, the general pair function otherwise)
-enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4, EPI_GYRO_BWD = 5, EPI_GYRO_LEAN = 6 };
+// EPI_MOBIUS_F: the whole Mobius forward of an m-block in one unit of the A-resident schedule: first the tiles of x G
+// (G = M^T M, the B2 operand) whose epilogue dots them with the resident bf16 rows of x - |M x_b|^2 = x_b^T G x_b - then,
+// with the row's rescale + projection factor known, the tiles of x M^T scaled on the way out.  launch_gemm2 returns
+// HVAE_ESHAPE when the problem is not eligible for the A-resident schedule (the caller keeps the three-kernel path).
+enum { EPI_PLAIN = 0, EPI_GYRO = 1, EPI_ROWDOT = 2, EPI_MOBIUS = 3, EPI_GEO = 4, EPI_GYRO_BWD = 5, EPI_GYRO_LEAN = 6, EPI_MOBIUS_F = 7 };
 
 constexpr int kPairM = 256;   // output rows per CTA pair (128 per CTA)
 constexpr int kTileN = 256;   // accumulator columns per tile
@@ -31,7 +35,8 @@ struct Params2 {
     const float* axpy_x;    // PLAIN: optional (M, N) fp32;  D = acc * rowscale + axpy_coef[m] * axpy_x[m][n]
     const float* axpy_coef; //        (M,) or NULL (= 1)
     float* rowsq;           // PLAIN: optional [n_tiles * kCG][M] partial sums of acc^2
-    const float* x2;        // GYRO / GEO: (M,) |x|^2
+    const float* x2;        // GYRO / GEO / MOBIUS_F: (M,) |x|^2
+    float* mxsq_out;        // MOBIUS_F: optional (M,) |M x_b|^2 (the backward's saved row statistic);  gp = the ball
     const float* p2;        // GYRO / GEO: (N,) |p|^2
     const float* pa;        // GEO: (N,) <p_j, a_j>
     const float* an;        // GEO: (N,) |a_j|

@@ -15,7 +15,7 @@ _checked_devices = set()
 
 _C = ctypes
 _TYPES = {
-    "const float*": _C.c_void_p, "const int64_t*": _C.c_void_p, "float*": _C.c_void_p, "void*": _C.c_void_p, "const void*": _C.c_void_p,
+    "const float*": _C.c_void_p, "const int64_t*": _C.c_void_p, "float*": _C.c_void_p, "int*": _C.c_void_p, "void*": _C.c_void_p, "const void*": _C.c_void_p,
     "int64_t": _C.c_int64, "float": _C.c_float, "int": _C.c_int, "uint32_t": _C.c_uint32,
     "uint64_t": _C.c_uint64, "size_t": _C.c_size_t, "double": _C.c_double,
 }

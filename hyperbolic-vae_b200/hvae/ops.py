@@ -1110,14 +1110,15 @@ rn_kl_fwd.register_autograd(_rk_backward, setup_context=_rk_setup)
 # ---------------------------------------------------------------------------------------------------
 # Trunk dense layers: fp32-accurate GEMM on the tensor cores (three-way bf16 split, six products)
 # ---------------------------------------------------------------------------------------------------
-_trunk_mode = "x3"
+_trunk_mode = "x2"
 
 
 def set_trunk_mode(mode: str):
-    """'x3' (default): hvae.layers.Linear runs on the tcgen05 split-bf16 GEMM (fp32 accuracy, fp32 in/out);
-    'torch': it defers to torch.nn.functional.linear (cuBLAS fp32 FMA kernels)."""
+    """'x2' (default): hvae.layers.Linear runs on the tcgen05 fp16 two-piece GEMM (power-of-two row scales, three piece
+    products; fp32 accuracy, fp32 in/out);  'x3': the three-way bf16 split (six products);  'torch': it defers to
+    torch.nn.functional.linear (cuBLAS fp32 FMA kernels)."""
     global _trunk_mode
-    if mode not in ("x3", "torch"):
+    if mode not in ("x2", "x3", "torch"):
         raise ValueError(mode)
     _trunk_mode = mode
 
@@ -1127,7 +1128,8 @@ def get_trunk_mode() -> str:
 
 
 def trunk_x3_eligible(x: Tensor, weight: Tensor) -> bool:
-    return (_trunk_mode == "x3" and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+    """GEMM-sized fp32 CUDA problem and a tensor-core trunk mode ('x2' or 'x3')."""
+    return (_trunk_mode in ("x2", "x3") and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
             and x.numel() // x.shape[-1] >= 128 and weight.shape[0] >= 64 and weight.shape[1] >= 64)
 
 
@@ -1287,8 +1289,123 @@ def _lx3_backward(ctx, gy, _g1, _g2):
 linear_x3_fwd.register_autograd(_lx3_backward, setup_context=_lx3_setup)
 
 
+# ---- fp16 two-piece path (csrc/tc_x2.cu) ----
+@_op("hvae::split2h_both", mutates_args=())
+def split2h_both(x: Tensor, want_rows: bool, want_t: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(rows, cols) fp32 -> (rows split (rows, 2*Cp) fp16, its inverse row scales (rows,), transposed split (cols, 2*Rp)
+    scaled per column of x, its inverse scales (cols,)); a layout that is not wanted comes back empty."""
+    C.require_cuda(x)
+    rows, cols = x.shape
+    dev = x.device
+    r = torch.empty((rows, 2 * _cp64(cols)) if want_rows else (0,), dtype=torch.float16, device=dev)
+    ri = torch.empty(rows if want_rows else 0, dtype=torch.float32, device=dev)
+    t = torch.empty((cols, 2 * _cp64(rows)) if want_t else (0,), dtype=torch.float16, device=dev)
+    ti = torch.empty(cols if want_t else 0, dtype=torch.float32, device=dev)
+    if want_t:
+        ws = _workspace(C.lib().hvae_split2h_workspace_bytes(rows, cols), dev)
+        C.call("hvae_split2h_both_f32", C.ptr(x), C.ptr(r) if want_rows else None, C.ptr(ri) if want_rows else None, C.ptr(t),
+               C.ptr(ti), rows, cols, C.ptr(ws), ws.numel(), C.stream())
+        C.launch_count += 2
+    elif want_rows:
+        C.call("hvae_split2h_rows_f32", C.ptr(x), C.ptr(r), C.ptr(ri), rows, cols, C.stream())
+        C.launch_count += 1
+    return r, ri, t, ti
+
+
+@split2h_both.register_fake
+def _(x, want_rows, want_t):
+    rows, cols = x.shape
+    dev = x.device
+    return (torch.empty((rows, 2 * _cp64(cols)) if want_rows else (0,), dtype=torch.float16, device=dev),
+            torch.empty(rows if want_rows else 0, dtype=torch.float32, device=dev),
+            torch.empty((cols, 2 * _cp64(rows)) if want_t else (0,), dtype=torch.float16, device=dev),
+            torch.empty(cols if want_t else 0, dtype=torch.float32, device=dev))
+
+
+@_op("hvae::gemm_x2s", mutates_args=())
+def gemm_x2s(As: Tensor, inv_a: Tensor, Bs: Tensor, inv_b: Tensor, bias: Optional[Tensor], relu: bool, M: int, N: int,
+             K: int) -> Tensor:
+    """C (M,N) = A (M,K) . B (N,K)^T (+ bias) (ReLU) on split2h operands (rows = output index) and their inverse scales."""
+    C.require_cuda(inv_a, inv_b)
+    if not (As.is_cuda and Bs.is_cuda and As.dtype == torch.float16 and Bs.dtype == torch.float16):
+        raise RuntimeError("gemm_x2s: operands must be CUDA fp16 split2h buffers")
+    if As.shape != (M, 2 * _cp64(K)) or Bs.shape != (N, 2 * _cp64(K)) or inv_a.numel() != M or inv_b.numel() != N:
+        raise RuntimeError("gemm_x2s: operand shapes %s / %s do not match (M, N, K) = (%d, %d, %d)" % (tuple(As.shape), tuple(Bs.shape), M, N, K))
+    out = torch.empty(M, N, dtype=torch.float32, device=As.device)
+    ws = _workspace(C.lib().hvae_gemm_x2s_workspace_bytes(M, N), As.device)
+    C.call("hvae_gemm_x2s_f32", C.ptr(As), C.ptr(inv_a), C.ptr(Bs), C.ptr(inv_b), C.ptr(bias), int(relu), C.ptr(out), M, N, K,
+           C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += C.lib().hvae_gemm_x2s_num_launches(M, N, K)
+    return out
+
+
+@gemm_x2s.register_fake
+def _(As, inv_a, Bs, inv_b, bias, relu, M, N, K):
+    return torch.empty(M, N, dtype=torch.float32, device=As.device)
+
+
+@_op("hvae::linear_x2", mutates_args=())
+def linear_x2_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (y, split of x^T + its scales, split of W^T + its scales): as linear_x3, on the fp16 two-piece path."""
+    xs, xi, xts, xti = split2h_both(x, True, need_gw)
+    ws, wi, wts, wti = split2h_both(weight, True, need_gx)
+    y = gemm_x2s(xs, xi, ws, wi, bias, False, x.shape[0], weight.shape[0], x.shape[1])
+    return y, xts, xti, wts, wti
+
+
+@linear_x2_fwd.register_fake
+def _(x, weight, bias, need_gx, need_gw):
+    M, K = x.shape
+    N = weight.shape[0]
+    dev = x.device
+    return (x.new_empty(M, N),
+            torch.empty((K, 2 * _cp64(M)) if need_gw else (0,), dtype=torch.float16, device=dev),
+            torch.empty(K if need_gw else 0, dtype=torch.float32, device=dev),
+            torch.empty((K, 2 * _cp64(N)) if need_gx else (0,), dtype=torch.float16, device=dev),
+            torch.empty(K if need_gx else 0, dtype=torch.float32, device=dev))
+
+
+def _lx2_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    x, weight, bias, need_gx, need_gw = inputs
+    ctx.save_for_backward(output[1], output[2], output[3], output[4])
+    ctx.dims = (x.shape[0], weight.shape[0], x.shape[1])  # rows, out, in
+    ctx.has_bias = bias is not None
+    ctx.need = (need_gx, need_gw)
+
+
+def _lx2_backward(ctx, gy, *_unused):
+    if gy is None:
+        return None, None, None, None, None
+    xts, xti, wts, wti = ctx.saved_tensors
+    M, n_out, n_in = ctx.dims
+    need_gx, need_gw = ctx.need
+    gy = _c(gy)
+    gx = gw = gb = None
+    want_gx = ctx.needs_input_grad[0] and need_gx
+    want_gw = ctx.needs_input_grad[1] and need_gw
+    if want_gx or want_gw:
+        gs, gi, gts, gti = split2h_both(gy, want_gx, want_gw)
+        if want_gx:
+            gx = gemm_x2s(gs, gi, wts, wti, None, False, M, n_in, n_out)      # gy (M,out) . W (out,in)
+        if want_gw:
+            gw = gemm_x2s(gts, gti, xts, xti, None, False, n_out, n_in, M)    # gy^T (out,M) . x (M,in)
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        gb = colsum(gy)
+    return gx, gw, gb, None, None
+
+
+linear_x2_fwd.register_autograd(_lx2_backward, setup_context=_lx2_setup)
+
+
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     """torch.nn.functional.linear semantics; the tensor-core fp32 path for GEMM-sized CUDA inputs."""
+    if trunk_x3_eligible(x, weight) and _trunk_mode == "x2":
+        lead = x.shape[:-1]
+        grad_on = torch.is_grad_enabled()
+        y = linear_x2_fwd(_rows(x), _c(weight), None if bias is None else _c(bias), grad_on and x.requires_grad,
+                          grad_on and weight.requires_grad)[0]
+        return y.view(*lead, weight.shape[0])
     if trunk_x3_eligible(x, weight):
         lead = x.shape[:-1]
         grad_on = torch.is_grad_enabled()

@@ -294,6 +294,26 @@ int hvae_gemm_x3_num_launches(int64_t M, int64_t N, int64_t K);
 int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int b_trans, const float* bias, int relu, float* C,
                      int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the same dense layers on the fp16 tensor-core path: two-piece split with power-of-two row scales, three piece
+ * products (hyperbolic-vae_b200/csrc/tc_x2.cu; reference: the nn.Linear layers above).  fp32 in, fp32 out; per-term
+ * error <= 3 * 2^-22 (elements more than 2^28 below their row's largest magnitude keep an absolute error of 2^-39 of it).
+ *   hvae_split2h_rows_f32: src (rows, cols) fp32 -> dst (rows, 2*Cp) fp16 [hi | lo] of row r times 2^e_r, Cp = cols
+ *     rounded up to 64 (hvae_split2h_bytes); inv_scale (rows,) = 2^-e_r.
+ *   hvae_split2h_both_f32: that, and/or the split of src^T (cols, 2*Rp) scaled per COLUMN of src (inv_cols (cols,)) -
+ *     the layout a contraction over src's rows needs (weight gradients).  workspace: hvae_split2h_workspace_bytes.
+ *   hvae_gemm_x2s_f32: C (M,N) = A (M,K) . B (N,K)^T (+ bias[n]) (ReLU) on split operands and their inverse scales.
+ *   hvae_gemm_x2s_plan: the tile width (128..256), split-K factor and TMA ring depth chosen for a problem. */
+size_t hvae_split2h_bytes(int64_t rows, int64_t cols);
+size_t hvae_split2h_workspace_bytes(int64_t rows, int64_t cols);
+int hvae_split2h_rows_f32(const float* src, void* dst, float* inv_scale, int64_t rows, int64_t cols, void* stream);
+int hvae_split2h_both_f32(const float* src, void* dst_rows, float* inv_rows, void* dst_t, float* inv_cols, int64_t rows,
+                          int64_t cols, void* workspace, size_t workspace_bytes, void* stream);
+size_t hvae_gemm_x2s_workspace_bytes(int64_t M, int64_t N);
+int hvae_gemm_x2s_num_launches(int64_t M, int64_t N, int64_t K);
+int hvae_gemm_x2s_plan(int64_t M, int64_t N, int64_t K, int* bn, int* splits, int* stages);
+int hvae_gemm_x2s_f32(const void* As, const float* inv_a, const void* Bs, const float* inv_b, const float* bias, int relu,
+                      float* C, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,10 +52,21 @@ def main():
         torch.cuda.synchronize()
         return
     # dbg bits: 1 = no stores, 2 = no drain, 4 = force the streaming schedule (default: A-resident when eligible)
+    #           8 = drain the staging box with coalesced st.global instead of a TMA store (32: with .cs), 16 = TMA stores
+    #           without waiting for the previous box to be read (WRONG results: timing of the wait only)
     for name, epi, dbg in (("mobius_ares_full", 3, 0), ("mobius_ares_nostore", 3, 1), ("mobius_ares_nodrain", 3, 2),
-                           ("mobius_stream_full", 3, 4), ("mobius_stream_nodrain", 3, 6), ("plain_ares_full", 0, 0)):
+                           ("mobius_stream_full", 3, 4), ("mobius_stream_nodrain", 3, 6), ("plain_ares_full", 0, 0),
+                           ("mobius_ares_stg", 3, 8), ("mobius_ares_stg_cs", 3, 8 | 32), ("mobius_stream_stg", 3, 4 | 8),
+                           ("mobius_stream_stg_cs", 3, 4 | 8 | 32), ("mobius_ares_nowait", 3, 16), ("mobius_stream_nowait", 3, 4 | 16)):
         ms = timeit(lambda: run(epi, dbg))
         out[name] = {"ms": ms, "tflops": fl / ms / 1e9}
+        if dbg in (8, 12, 40):   # correctness of the experimental store path
+            D.zero_()
+            run(epi, dbg)
+            if M <= (1 << 18):
+                ref = (A.float() @ B.float().t()) * rs[:, None]
+                out[name]["max_rel_err"] = float((D - ref).abs().max() / ref.abs().max())
+                del ref
     # correctness of the full variant against cuBLAS
     run(3, 0)
     ref = (A.float() @ B.float().t()) * rs[:, None] if M <= (1 << 18) else None

@@ -93,7 +93,7 @@ def test_cfg1_step(which):
 
 @pytest.mark.parametrize("use_graph", [True, False])
 def test_cfg2_step_full_size(use_graph):
-    """The step bench.py times: B = 4096, H = 600, D = 10, X3 tensor-core trunk, fused heads, CUDA graph."""
+    """The step bench.py times: B = 4096, H = 600, D = 10, fp16 two-piece tensor-core trunk, fused heads, CUDA graph."""
     from hvae import models as HM
     from hvae import ops
     from oracle import ref_port as R
@@ -111,7 +111,7 @@ def test_cfg2_step_full_size(use_graph):
         r = R.RiemannianNormal(mu_, sg_, o.manifold).radius.sample(torch.Size([1]))   # the reference's own ARS radii
     o32 = _oracle_run(make_o, sd, x, torch.float32, alpha=alpha, r=r)
     o64 = _oracle_run(make_o, sd, x, torch.float64, alpha=alpha, r=r)
-    assert ops.get_trunk_mode() == "x3"   # the fp32-accurate tcgen05 trunk is what bench.py runs
+    assert ops.get_trunk_mode() == "x2"   # the fp32-accurate tcgen05 trunk (fp16 two-piece path) is what bench.py runs
     loss, L, grads = _cuda_run(HM.PvaeMnist(latent_dim=D, hidden_dim=H, c=1.0), sd, x, use_graph=use_graph, alpha=alpha, r=r)
     # losses are batch sums of O(2e6)
     _compare("cfg2 B=4096 H=600", loss, L, grads, o32, o64, loss_atol=0.5)

@@ -14,8 +14,10 @@ def _oball(c):
     return PoincareBall(c=c)
 
 
-# the last shape has >= 148 m-blocks, K <= 512 and >= 4 n-tiles: it runs the A-resident schedule (ragged M and N)
-@pytest.mark.parametrize("B,F,P", [(128, 64, 128), (256, 128, 256), (384, 256, 640), (1000, 512, 300), (4096, 512, 1024), (19000, 512, 600)])
+# the last two shapes have >= 148 m-blocks, K <= 512 and >= 4 n-tiles: they run the A-resident schedule - the forward-only
+# variant as ONE kernel (Gram tiles + row factor + scaled output tiles per m-block) - with ragged M, N and K
+@pytest.mark.parametrize("B,F,P", [(128, 64, 128), (256, 128, 256), (384, 256, 640), (1000, 512, 300), (4096, 512, 1024), (19000, 512, 600),
+                                   (37900, 512, 1000), (38100, 200, 1024)])
 def test_mobius_tc_forward(B, F, P):
     import hvae
     from hvae import ops
@@ -93,7 +95,8 @@ def test_mobius_tc_backward(B, F, P, scale):
     assert float(eMr.max()) < 3e-2, float(eMr.max())
 
 
-@pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024), (19000, 256, 520)])
+@pytest.mark.parametrize("B,D,P", [(128, 64, 128), (512, 128, 384), (300, 256, 200), (2048, 512, 1024), (19000, 256, 520),
+                                   (37900, 256, 1000)])
 def test_gyroplane_tc_forward(B, D, P):
     import hvae
     from hvae import ops
@@ -106,7 +109,9 @@ def test_gyroplane_tc_forward(B, D, P):
     p = ob.expmap0(torch.randn(P, D) * 0.6 / D ** 0.5).detach()
     bias = torch.randn(P)
     k = torch.tensor(-c, dtype=torch.float64)
-    ref = gm.dist2plane(x.double().unsqueeze(-1), p.double().t(), p.double().t(), k=k, signed=True, dim=-2) + bias.double()
+    # (the oracle broadcasts to (rows, D, P) float64: in row chunks)
+    ref = torch.cat([gm.dist2plane(xc.double().unsqueeze(-1), p.double().t(), p.double().t(), k=k, signed=True, dim=-2)
+                     for xc in x.split(4096)]) + bias.double()
     out = ops.gyroplane_tc_fwd(x.cuda(), p.cuda(), bias.cuda(), hvae.PoincareBall(c).c_value, ops.GYRO_SIGNED)
     torch.cuda.synchronize()
     pk = pair_kappa(c, x, p)

@@ -1,6 +1,7 @@
-"""GPU parity of the fp32-accurate tensor-core GEMM (three-way bf16 split, six piece products) that carries the trunk
-dense layers: against a float64 product its error must be that of an fp32 FMA GEMM (torch / cuBLAS fp32 with TF32 off),
-i.e. well inside the 1e-5 budget of the fp32 mode."""
+"""GPU parity of the fp32-accurate tensor-core GEMMs that carry the trunk dense layers - the fp16 two-piece path with
+power-of-two row scales (three piece products, the default) and the three-way bf16 split (six piece products): against a
+float64 product the error must be that of an fp32 FMA GEMM (torch / cuBLAS fp32 with TF32 off), i.e. well inside the
+1e-5 budget of the fp32 mode."""
 import pytest
 import torch
 
@@ -82,7 +83,118 @@ def test_split3_is_exact_to_24_bits():
     assert float(((rec - x.double()).abs() / x.double().abs()).max()) < 2.0 ** -23
 
 
-def test_linear_layer_forward_backward():
+def _split2h(x, want_rows=True, want_t=False):
+    from hvae import ops
+
+    return ops.split2h_both(x, want_rows, want_t)
+
+
+def test_split2h_scales_and_precision():
+    """rows on scales from 1e-30 to 1e30, an all-zero row, elements far below their row's maximum: hi + lo times the
+    inverse scale reproduces x to 2^-22 of the element (or 2^-38 of the row maximum), the padding is zero, the scales
+    are powers of two that bring the row maximum into [2^14, 2^15)."""
+    torch.manual_seed(0)
+    R, Cn = 300, 100
+    x = torch.randn(R, Cn, device="cuda") * torch.rand(R, 1, device="cuda").mul(138).sub(69).exp()
+    x[7] = 0.0
+    x[9, 1:] *= 1e-7            # a row dominated by one element
+    x[11, 3] = 3.0e38
+    r, ri, t, ti = _split2h(x, True, True)
+    torch.cuda.synchronize()
+    Cp, Rp = 128, 320
+    assert r.shape == (R, 2 * Cp) and t.shape == (Cn, 2 * Rp) and ri.shape == (R,) and ti.shape == (Cn,)
+    rv = r.float().view(R, 2, Cp)
+    assert torch.equal(rv[:, :, Cn:], torch.zeros_like(rv[:, :, Cn:]))
+    assert bool(torch.isfinite(rv).all())
+    rec = (rv[:, 0, :Cn].double() + rv[:, 1, :Cn].double()) * ri.double()[:, None]
+    rowmax = x.double().abs().amax(dim=1, keepdim=True)
+    err = (rec - x.double()).abs()
+    assert bool((err <= 2.0 ** -22 * x.double().abs() + 2.0 ** -38 * rowmax).all())
+    m, e = torch.frexp(ri)
+    assert torch.equal(m, torch.full_like(m, 0.5))      # powers of two
+    scaled = rowmax[:, 0] / ri.double()
+    nz = rowmax[:, 0] > 0
+    assert bool(((scaled[nz] >= 2.0 ** 14) & (scaled[nz] < 2.0 ** 15)).all())
+    assert float(ri[7]) == 1.0
+    # transposed layout: the split of x^T scaled per column of x
+    tv = t.float().view(Cn, 2, Rp)
+    assert torch.equal(tv[:, :, R:], torch.zeros_like(tv[:, :, R:]))
+    rect = (tv[:, 0, :R].double() + tv[:, 1, :R].double()) * ti.double()[:, None]
+    colmax = x.double().abs().amax(dim=0)
+    errt = (rect - x.double().t()).abs()
+    assert bool((errt <= 2.0 ** -22 * x.double().t().abs() + 2.0 ** -38 * colmax[:, None]).all())
+    # the rows-only entry point gives the same rows layout
+    r2, ri2, _, _ = _split2h(x, True, False)
+    assert torch.equal(r2, r) and torch.equal(ri2, ri)
+
+
+# (M, N, K): trunk shapes of config 2 fwd / dgrad / wgrad (the last two run split-K), config 3's 20000-wide layers, ragged
+# and tiny sizes, every tile width the planner can choose
+X2_CASES = [(4096, 600, 784), (4096, 784, 600), (600, 784, 4096), (784, 600, 4096), (1024, 100, 20000), (1024, 20000, 100),
+            (1000, 300, 100), (257, 601, 77), (130, 65, 1000), (128, 64, 64), (4096, 1000, 256), (300, 250, 513)]
+
+
+@pytest.mark.parametrize("M,N,K", X2_CASES)
+def test_gemm_x2s_matches_fp32_accuracy(M, N, K):
+    from hvae import ops
+
+    torch.manual_seed(M + N + K)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    A = torch.randn(M, K, device="cuda") * torch.rand(M, 1, device="cuda").mul(8).sub(4).exp()   # rows on different scales
+    B = torch.randn(N, K, device="cuda") * torch.rand(N, 1, device="cuda").mul(8).sub(4).exp()
+    A[:, ::7] *= 1e-4                                                                              # and columns
+    bias = torch.randn(N, device="cuda")
+    ref = A.double() @ B.double().t() + bias.double()
+    As, ai, _, _ = _split2h(A)
+    Bs, bi, _, _ = _split2h(B)
+    out = ops.gemm_x2s(As, ai, Bs, bi, bias, False, M, N, K)
+    torch.cuda.synchronize()
+    # element-wise: every output within fp32 accumulation error of its own scale sum_k |a_k b_k| (+ the bias)
+    scale = A.double().abs() @ B.double().abs().t() + bias.double().abs()
+    e_x2 = float(((out.double() - ref).abs() / scale).max())
+    e_t = float((((A @ B.t() + bias).double() - ref).abs() / scale).max())
+    assert e_x2 < 1e-6, e_x2
+    assert e_x2 < 3.0 * e_t + 2e-7, (e_x2, e_t)
+    outr = ops.gemm_x2s(As, ai, Bs, bi, bias, True, M, N, K)
+    assert torch.equal(outr, out.clamp_min(0))
+    # the contraction over the ROWS of two matrices (weight gradient): transposed splits with per-column scales
+    if M * N <= 4096 * 1000:
+        X = torch.randn(K, M, device="cuda") * torch.rand(1, M, device="cuda").mul(6).sub(3).exp()
+        Y = torch.randn(K, N, device="cuda") * torch.rand(1, N, device="cuda").mul(6).sub(3).exp()
+        _, _, Xt, xi = _split2h(X, False, True)
+        _, _, Yt, yi = _split2h(Y, False, True)
+        outw = ops.gemm_x2s(Xt, xi, Yt, yi, None, False, M, N, K)
+        refw = X.double().t() @ Y.double()
+        scalew = X.double().abs().t() @ Y.double().abs()
+        assert float(((outw.double() - refw).abs() / scalew).max()) < 1e-6
+
+
+def test_gemm_x2s_plan_fills_one_wave_at_config2():
+    import ctypes
+
+    from hvae import _cabi as C
+
+    bn, sp, st = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    for (M, N, K) in ((4096, 600, 784), (4096, 784, 600), (600, 784, 4096)):
+        assert C.lib().hvae_gemm_x2s_plan(M, N, K, ctypes.addressof(bn), ctypes.addressof(sp), ctypes.addressof(st)) == 0
+        units = -(-M // 128) * -(-N // bn.value) * sp.value
+        assert units <= 148 or sp.value > 1, (M, N, K, bn.value, sp.value)
+        assert bn.value % 32 == 0 and 128 <= bn.value <= 256 and 2 <= st.value <= 4
+
+
+@pytest.mark.parametrize("mode", ["x2", "x3"])
+def test_linear_layer_forward_backward(mode):
+    from hvae import layers, ops
+
+    assert ops.get_trunk_mode() == "x2"   # the default
+    ops.set_trunk_mode(mode)
+    try:
+        _linear_layer_forward_backward(mode)
+    finally:
+        ops.set_trunk_mode("x2")
+
+
+def _linear_layer_forward_backward(mode):
     from hvae import layers, ops
 
     torch.manual_seed(0)
@@ -105,7 +217,7 @@ def test_linear_layer_forward_backward():
     try:
         y_t = lin(x)
     finally:
-        ops.set_trunk_mode("x3")
+        ops.set_trunk_mode(mode)
     assert torch.allclose(y_t, ref_lin(x))
     assert _rel(y, y_t.detach().double()) < 2e-6
     # small shapes defer to torch
@@ -152,12 +264,12 @@ def test_cfg2_step_fused_heads_match_torch_heads():
     for mode in ("ours", "torch"):
         model.zero_grad(set_to_none=True)
         model.fused = mode == "ours"
-        ops.set_trunk_mode("x3" if mode == "ours" else "torch")
+        ops.set_trunk_mode("x2" if mode == "ours" else "torch")
         try:
             out = model.loss(x, alpha=alpha, r=r)
             out["loss_total"].backward()
         finally:
-            ops.set_trunk_mode("x3")
+            ops.set_trunk_mode("x2")
             model.fused = True
         res[mode] = (out["loss_total"].detach().double(), {n: p.grad.detach().double().clone() for n, p in model.named_parameters() if p.grad is not None})
     la, lb = res["ours"][0], res["torch"][0]
