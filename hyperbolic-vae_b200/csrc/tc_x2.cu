@@ -27,6 +27,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace hvae {
@@ -41,6 +43,21 @@ constexpr uint32_t TILE_A = BM * BK * 2;                 // 16 KB
 constexpr uint32_t SMEM_LIMIT = 232448, BAR_BYTES = 256;
 constexpr int MAX_STAGES = 4, MAX_SPLITS = 8;
 
+// 16 lanes x (4 repeats of 256 bits) -> 16 registers, complete on return
+__device__ __forceinline__ void tmem_ld16_sync(uint32_t addr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 struct Params {
     float* D;                 // (M, N) row-major (split-K: S partial planes)
     int64_t M, N;
@@ -51,11 +68,28 @@ struct Params {
     const float* sb;          // (N,) 2^-e of the B rows
     const float* bias;        // optional (N,), S == 1 only
     int relu;
+#ifdef HVAE_EXPERIMENT
+    int dbg;                  // experiment build: 1 = no global stores
+    long long* ts;            // experiment build: clock64 stamps of CTA 0 ([0,64) producer, [64,128) MMA, [128,192) epilogue warp 2)
+#endif
 };
+#ifdef HVAE_EXPERIMENT
+#define X2_STAMP(slot) do { if (prm.ts && blockIdx.x == 0 && (slot) < 64) prm.ts[(slot) + tsb] = clock64(); } while (0)
+#else
+#define X2_STAMP(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params prm) {
     extern __shared__ uint8_t smem_raw[];
+#ifdef HVAE_EXPERIMENT
+    if (prm.ts && threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        prm.ts[190] = (long long)t;       // first instruction of CTA 0
+        prm.ts[191] = clock64();
+    }
+#endif
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t tile_b = (uint32_t)prm.bn * (BK * 2);
@@ -72,9 +106,11 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     auto b_hi = [&](int s) { return base + (uint32_t)s * stage_bytes + 2u * TILE_A; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m_tiles = (prm.M + BM - 1) / BM, n_tiles = (prm.N + prm.bn - 1) / prm.bn;
+    // (32-bit unit arithmetic: 64-bit divisions are subroutine calls, ~1.3k cycles of them sat in front of the first TMA load;
+    //  the host checks that the unit count fits)
+    const int m_tiles = (int)((prm.M + BM - 1) / BM), n_tiles = (int)((prm.N + prm.bn - 1) / prm.bn);
     const int S = prm.splits > 1 ? prm.splits : 1;
-    const int64_t units = m_tiles * n_tiles * S;
+    const int units = m_tiles * n_tiles * S;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -82,6 +118,22 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first ring of loads leaves now, under the tensor-memory allocation and the block-wide sync below (the
+        // barriers it uses were initialised by this very thread; their other users arrive after the sync)
+        const int u = blockIdx.x;
+        if (u < units) {
+            const int tile = u / S, sp = u - tile * S;
+            const int p0 = sp * prm.kpos / S, p1 = (sp + 1) * prm.kpos / S;
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * prm.bn;
+            for (int kk = p0; kk < p1 && kk < p0 + NST; ++kk) {
+                const int stage = kk - p0;
+                mbar_expect_tx(full_bar(stage), stage_bytes);
+                tma_load_2d(a_hi(stage), &map_a, full_bar(stage), kk * BK, m0);
+                tma_load_2d(a_hi(stage) + TILE_A, &map_a, full_bar(stage), prm.a_lo + kk * BK, m0);
+                tma_load_2d(b_hi(stage), &map_b, full_bar(stage), kk * BK, n0);
+                tma_load_2d(b_hi(stage) + tile_b, &map_b, full_bar(stage), prm.b_lo + kk * BK, n0);
+            }
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(ACC_STAGES * ACC_COLS));
@@ -91,19 +143,37 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+#ifdef HVAE_EXPERIMENT
+    if (prm.ts && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        prm.ts[192 + 3 * blockIdx.x] = (long long)t;
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        prm.ts[192 + 3 * blockIdx.x + 2] = smid;
+    }
+#endif
 
     if (warp == 0) {
         // ===== TMA producer: {A hi, A lo, B hi, B lo} of one k-position per stage =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-                const int64_t tile = u / S;
-                const int sp = (int)(u % S);
-                const int p0 = (int)((int64_t)sp * prm.kpos / S), p1 = (int)((int64_t)(sp + 1) * prm.kpos / S);
-                const int m0 = (int)(tile / n_tiles) * BM, n0 = (int)(tile % n_tiles) * prm.bn;
+            [[maybe_unused]] const int tsb = 0;
+            [[maybe_unused]] int tsn = 0;
+            X2_STAMP(tsn++);
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int tile = u / S;
+                const int sp = u - tile * S;
+                const int p0 = sp * prm.kpos / S, p1 = (sp + 1) * prm.kpos / S;
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * prm.bn;
                 for (int kk = p0; kk < p1; ++kk) {
+                    if (u == (int)blockIdx.x && kk < p0 + NST) {   // issued in the prologue
+                        if (++stage == NST) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     mbar_wait(empty_bar(stage), phase ^ 1u);
+                    X2_STAMP(tsn++);
                     mbar_expect_tx(full_bar(stage), stage_bytes);
                     tma_load_2d(a_hi(stage), &map_a, full_bar(stage), kk * BK, m0);
                     tma_load_2d(a_hi(stage) + TILE_A, &map_a, full_bar(stage), prm.a_lo + kk * BK, m0);
@@ -121,9 +191,12 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             uint32_t phase = 0, aphase = 0;
             // kind::f16 instruction descriptor: D = f32, A = B = f16 (format 0), both K-major, M = 128, N = bn
             const uint32_t idesc = (1u << 4) | ((uint32_t)(prm.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-                const int sp = (int)(u % S);
-                const int p0 = (int)((int64_t)sp * prm.kpos / S), p1 = (int)((int64_t)(sp + 1) * prm.kpos / S);
+            [[maybe_unused]] const int tsb = 64;
+            [[maybe_unused]] int tsn = 0;
+            X2_STAMP(tsn++);
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sp = u % S;
+                const int p0 = sp * prm.kpos / S, p1 = (sp + 1) * prm.kpos / S;
                 int g = 0;
                 for (int kk = p0; kk < p1; ++kk) {
                     if (g == 0) {
@@ -133,6 +206,7 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+                    X2_STAMP(tsn++);
                     const uint64_t dah = make_desc(a_hi(stage)), dal = make_desc(a_hi(stage) + TILE_A);
                     const uint64_t dbh = make_desc(b_hi(stage)), dbl = make_desc(b_hi(stage) + tile_b);
                     // smallest products first
@@ -165,29 +239,51 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const bool n_even = (prm.N & 1) == 0;
         int as = 0;
         uint32_t aphase = 0;
-        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const int64_t tile = u / S;
-            const int sp = (int)(u % S);
-            const int p0 = (int)((int64_t)sp * prm.kpos / S), p1 = (int)((int64_t)(sp + 1) * prm.kpos / S);
-            const int64_t mt = tile / n_tiles, nt = tile % n_tiles;
+        [[maybe_unused]] const int tsb = 128;
+        [[maybe_unused]] int tsn = (warp == 2 && lane == 0) ? 0 : 64;
+        X2_STAMP(tsn++);
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int tile = u / S;
+            const int sp = u - tile * S;
+            const int p0 = sp * prm.kpos / S, p1 = (sp + 1) * prm.kpos / S;
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
             float acc[2][2][16];
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[j][0][i] = acc[j][1][i] = 0.0f;
+            // row / column constants of the finish, fetched while the first chunk is still being multiplied: lane l holds the
+            // inverse scale (and bias) of column l of each of the warp's chunks (shuffled to its users below) and the
+            // inverse scales of the thread's four rows
+            const bool fin = S == 1;
+            float sbl[2], bl[2], sar[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t col = (int64_t)nt * prm.bn + (cg + CG * j) * 32 + lane;
+                const bool in = (j == 0 || two) && col < prm.N;
+                sbl[j] = in ? __ldg(prm.sb + col) : 0.0f;
+                bl[j] = (in && fin && prm.bias) ? __ldg(prm.bias + col) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t row = (int64_t)mt * BM + q * 32 + 16 * (k >> 1) + 8 * (k & 1) + lr;
+                sar[k] = row < prm.M ? __ldg(prm.sa + row) : 0.0f;
+            }
             for (int c0 = p0; c0 < p1; c0 += prm.hand) {
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
+                X2_STAMP(tsn++);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     if (j == 1 && !two) break;
                     const uint32_t col = (uint32_t)(as * ACC_COLS + (cg + CG * j) * 32);
-                    float v0[16], v1[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col, v0);
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32 + 16) << 16) + col, v1);
-                    tmem_ld_wait(v0, v1);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { acc[j][0][i] += v0[i]; acc[j][1][i] += v1[i]; }
+                    for (int h = 0; h < 2; ++h) {   // one 16-row half at a time: 64 accumulators + 16 in flight fit the registers
+                        float v[16];
+                        tmem_ld16_sync(tmem_base + ((uint32_t)(q * 32 + 16 * h) << 16) + col, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[j][h][i] += v[i];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -196,45 +292,57 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             }
             // finish: undo the operand scales, bias, ReLU, store.  element (k = 2h + g, i, e): acc[j][h][4i + 2g + e]  <->
             // row 16h + 8g + lr of the warp's 32, column 8i + lc + e of chunk j
-            float* __restrict__ Dout = prm.D + (int64_t)sp * prm.M * prm.N;
-            const bool fin = S == 1;
+            // (one 64-bit base per thread - row lr of the warp's quarter, first column of the tile - and 32-bit offsets)
+            const int N32 = (int)prm.N;
+            const int64_t row0 = (int64_t)mt * BM + q * 32 + lr, col0 = (int64_t)nt * prm.bn;
+            float* __restrict__ Dt = prm.D + (int64_t)sp * prm.M * prm.N + row0 * prm.N + col0;
+            const bool interior = n_even && (int64_t)mt * BM + BM <= prm.M && col0 + prm.bn <= prm.N;   // (uniform) nothing to clip
+            X2_STAMP(tsn++);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j == 1 && !two) break;
-                const int64_t n0 = nt * prm.bn + (cg + CG * j) * 32;
+                const int cj = (cg + CG * j) * 32 + lc;   // this thread's first column of chunk j, relative to the tile
+                X2_STAMP(tsn++);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int64_t row = mt * BM + q * 32 + 16 * (k >> 1) + 8 * (k & 1) + lr;
-                    if (row >= prm.M) continue;
-                    const float sr = __ldg(prm.sa + row);
+                for (int i = 0; i < 4; ++i) {
+                    const float s0 = __shfl_sync(0xffffffffu, sbl[j], 8 * i + lc), s1 = __shfl_sync(0xffffffffu, sbl[j], 8 * i + lc + 1);
+                    const float b0 = __shfl_sync(0xffffffffu, bl[j], 8 * i + lc), b1 = __shfl_sync(0xffffffffu, bl[j], 8 * i + lc + 1);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int64_t col = n0 + 8 * i + lc;
-                        float t0 = acc[j][k >> 1][4 * i + 2 * (k & 1)], t1 = acc[j][k >> 1][4 * i + 2 * (k & 1) + 1];
-                        if (col < prm.N) {
-                            t0 *= sr * __ldg(prm.sb + col);
-                            if (fin && prm.bias) t0 += __ldg(prm.bias + col);
-                            if (fin && prm.relu) t0 = fmaxf(t0, 0.0f);
-                        }
-                        if (col + 1 < prm.N) {
-                            t1 *= sr * __ldg(prm.sb + col + 1);
-                            if (fin && prm.bias) t1 += __ldg(prm.bias + col + 1);
-                            if (fin && prm.relu) t1 = fmaxf(t1, 0.0f);
-                        }
-                        const int64_t off = row * prm.N + col;
-                        if (n_even && col + 2 <= prm.N) {
-                            *reinterpret_cast<float2*>(Dout + off) = make_float2(t0, t1);
-                        } else {
-                            if (col < prm.N) Dout[off] = t0;
-                            if (col + 1 < prm.N) Dout[off + 1] = t1;
+                    for (int k = 0; k < 4; ++k) {
+                        float t0 = fmaf(acc[j][k >> 1][4 * i + 2 * (k & 1)], sar[k] * s0, b0);
+                        float t1 = fmaf(acc[j][k >> 1][4 * i + 2 * (k & 1) + 1], sar[k] * s1, b1);
+                        if (fin && prm.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+                        const int off = (16 * (k >> 1) + 8 * (k & 1)) * N32 + cj + 8 * i;
+#ifdef HVAE_EXPERIMENT
+                        if (prm.dbg & 1) { if (t0 == 123.456f) Dt[0] = t1; continue; }
+#endif
+                        if (interior) {
+                            *reinterpret_cast<float2*>(Dt + off) = make_float2(t0, t1);
+                        } else if (row0 + 16 * (k >> 1) + 8 * (k & 1) < prm.M) {
+                            const int64_t col = col0 + cj + 8 * i;
+                            if (n_even && col + 2 <= prm.N) {
+                                *reinterpret_cast<float2*>(Dt + off) = make_float2(t0, t1);
+                            } else {
+                                if (col < prm.N) Dt[off] = t0;
+                                if (col + 1 < prm.N) Dt[off + 1] = t1;
+                            }
                         }
                     }
                 }
             }
+            X2_STAMP(tsn++);
         }
     }
     tc_fence_before();
     __syncthreads();
+#ifdef HVAE_EXPERIMENT
+    if (prm.ts && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        prm.ts[192 + 3 * blockIdx.x + 1] = (long long)t;
+        if (blockIdx.x == 0) prm.ts[189] = clock64();
+    }
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ACC_STAGES * ACC_COLS));
@@ -283,43 +391,52 @@ __global__ void __launch_bounds__(256) k_split2h_rows(const float* __restrict__ 
     }
 }
 
-// largest magnitude (as float bits) of every row and every column of an (R, C) matrix: a block owns 16 rows and all
-// their columns (row maxima exact in shared memory, column maxima by one atomicMax per column and block; colbits zeroed
-// by the caller)
-constexpr int kAbsmaxRows = 16;
+// largest magnitude (as float bits) of every row and every column of an (R, C) matrix: a block owns a 32-row x 128-column
+// tile (8 warps x 4 rows each, a lane reads 4 consecutive columns), row maxima by warp shuffle, column maxima through
+// shared memory, then one atomicMax per row / column and block (rowbits and colbits zeroed by the caller)
+constexpr int kAmRows = 32, kAmCols = 128;
 __global__ void __launch_bounds__(256) k_absmax_rc(const float* __restrict__ in, uint32_t* __restrict__ rowbits,
                                                    uint32_t* __restrict__ colbits, int64_t R, int64_t C) {
-    constexpr int RB = kAbsmaxRows;
-    __shared__ uint32_t rmax[RB];
-    if (threadIdx.x < RB) rmax[threadIdx.x] = 0u;
-    __syncthreads();
-    const int64_t r0 = (int64_t)blockIdx.x * RB;
-    const int nr = (int)(R - r0 < RB ? R - r0 : RB);
-    uint32_t mine[RB];
+    __shared__ uint32_t cmax[8][kAmCols];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * kAmRows, c0 = (int64_t)blockIdx.y * kAmCols + 4 * lane;
+    const bool vec = (C & 3) == 0;
+    uint32_t cm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < RB; ++i) mine[i] = 0u;
-    for (int64_t c = threadIdx.x; c < C; c += 256) {
-        uint32_t cm = 0u;
+    for (int i = 0; i < kAmRows / 8; ++i) {
+        const int64_t r = r0 + warp + 8 * i;
+        uint32_t b[4] = {0u, 0u, 0u, 0u};
+        if (r < R) {
+            if (vec && c0 + 4 <= C) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * C + c0));
+                b[0] = __float_as_uint(v.x); b[1] = __float_as_uint(v.y); b[2] = __float_as_uint(v.z); b[3] = __float_as_uint(v.w);
+            } else {
 #pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            if (i < nr) {
-                const uint32_t b = __float_as_uint(__ldg(in + (r0 + i) * C + c)) & 0x7fffffffu;
-                cm = max(cm, b);
-                mine[i] = max(mine[i], b);
+                for (int e = 0; e < 4; ++e)
+                    if (c0 + e < C) b[e] = __float_as_uint(__ldg(in + r * C + c0 + e));
             }
         }
-        if (colbits) atomicMax(colbits + c, cm);
-    }
-    if (rowbits) {
+        uint32_t rm = 0u;
 #pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            uint32_t m = mine[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if ((threadIdx.x & 31) == 0 && m) atomicMax(&rmax[i], m);
+        for (int e = 0; e < 4; ++e) {
+            b[e] &= 0x7fffffffu;
+            cm[e] = max(cm[e], b[e]);
+            rm = max(rm, b[e]);
         }
-        __syncthreads();
-        if (threadIdx.x < nr) rowbits[r0 + threadIdx.x] = rmax[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rm = max(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+        if (rowbits && lane == 0 && r < R && rm) atomicMax(rowbits + r, rm);
+    }
+    if (!colbits) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cmax[warp][4 * lane + e] = cm[e];
+    __syncthreads();
+    if (threadIdx.x < kAmCols) {
+        uint32_t m = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m = max(m, cmax[w][threadIdx.x]);
+        const int64_t c = (int64_t)blockIdx.y * kAmCols + threadIdx.x;
+        if (c < C && m) atomicMax(colbits + c, m);
     }
 }
 
@@ -428,9 +545,16 @@ static Plan pick_plan(int64_t M, int64_t N, int64_t K) {
             if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = S; }
         }
     }
+#ifdef HVAE_EXPERIMENT
+    if (getenv("HVAE_X2_BN")) best.bn = atoi(getenv("HVAE_X2_BN"));
+    if (getenv("HVAE_X2_SPLITS")) best.splits = atoi(getenv("HVAE_X2_SPLITS"));
+#endif
     const uint32_t stage = 2u * TILE_A + 2u * (uint32_t)best.bn * (BK * 2);
     int nst = (int)((SMEM_LIMIT - 1024u - BAR_BYTES) / stage);
     best.nst = nst > MAX_STAGES ? MAX_STAGES : nst;
+#ifdef HVAE_EXPERIMENT
+    if (getenv("HVAE_X2_NST") && atoi(getenv("HVAE_X2_NST")) < best.nst) best.nst = atoi(getenv("HVAE_X2_NST"));
+#endif
     return best;
 }
 
@@ -438,6 +562,12 @@ static Plan pick_plan(int64_t M, int64_t N, int64_t K) {
 }  // namespace hvae
 
 using namespace hvae;
+
+#ifdef HVAE_EXPERIMENT
+static long long* g_x2_ts = nullptr;
+// experiment build: a device buffer of 192 int64 that CTA 0 of every following k_x2_gemm launch stamps with clock64
+extern "C" void hvae_exp_x2_timestamps(long long* dev_buf) { g_x2_ts = dev_buf; }
+#endif
 
 extern "C" size_t hvae_split2h_bytes(int64_t rows, int64_t cols) {
     if (rows <= 0 || cols <= 0) return 0;
@@ -474,8 +604,11 @@ extern "C" int hvae_split2h_both_f32(const float* src, void* dst_rows, float* in
     cudaStream_t s = (cudaStream_t)stream;
     uint32_t* colbits = (uint32_t*)workspace;
     uint32_t* rowbits = colbits + cols;
-    if (cudaMemsetAsync(colbits, 0, (size_t)cols * 4, s) != cudaSuccess) return HVAE_ELAUNCH;
-    x2::k_absmax_rc<<<(unsigned)((rows + x2::kAbsmaxRows - 1) / x2::kAbsmaxRows), 256, 0, s>>>(src, dst_rows ? rowbits : nullptr, colbits, rows, cols);
+    if (cudaMemsetAsync(colbits, 0, (size_t)(cols + rows) * 4, s) != cudaSuccess) return HVAE_ELAUNCH;
+    {
+        dim3 grid((unsigned)((rows + x2::kAmRows - 1) / x2::kAmRows), (unsigned)((cols + x2::kAmCols - 1) / x2::kAmCols));
+        x2::k_absmax_rc<<<grid, 256, 0, s>>>(src, dst_rows ? rowbits : nullptr, colbits, rows, cols);
+    }
     dim3 grid((unsigned)(Rp / 64), (unsigned)(Cp / 64));
     x2::k_split2h_both<<<grid, 256, 0, s>>>(src, rowbits, colbits, (__half*)dst_rows, inv_rows, (__half*)dst_t, inv_cols, rows, cols, Cp, Rp);
     return check_launch();
@@ -514,10 +647,16 @@ extern "C" int hvae_gemm_x2s_f32(const void* As, const float* inv_a, const void*
     if (!tc::make_map(&ma, As, M, 2 * Kp, x2::BM) || !tc::make_map(&mb, Bs, N, 2 * Kp, pl.bn)) return HVAE_ELAUNCH;
     x2::Params prm{};
     prm.M = M; prm.N = N; prm.kpos = (int)(Kp / x2::BK); prm.bn = pl.bn; prm.splits = pl.splits; prm.nst = pl.nst; prm.hand = 2;
+#ifdef HVAE_EXPERIMENT
+    if (getenv("HVAE_X2_HAND")) prm.hand = atoi(getenv("HVAE_X2_HAND"));
+    prm.ts = g_x2_ts;
+    prm.dbg = getenv("HVAE_X2_DBG") ? atoi(getenv("HVAE_X2_DBG")) : 0;
+#endif
     prm.a_lo = (int)Kp; prm.b_lo = (int)Kp; prm.sa = inv_a; prm.sb = inv_b;
     const uint32_t smem = (uint32_t)pl.nst * (2u * x2::TILE_A + 2u * (uint32_t)pl.bn * (x2::BK * 2)) + 1024u + x2::BAR_BYTES;
     cudaFuncSetAttribute(x2::k_x2_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x2::SMEM_LIMIT);
     const int64_t units = ((M + x2::BM - 1) / x2::BM) * ((N + pl.bn - 1) / pl.bn) * pl.splits;
+    if (units > 0x7fffffffLL || N > 0x3ffffffLL) return HVAE_ESHAPE;   // 32-bit unit / in-tile offset arithmetic in the kernel
     const unsigned grid = (unsigned)(units < kNumSMs ? units : kNumSMs);
     if (pl.splits == 1) {
         prm.D = C; prm.bias = bias; prm.relu = relu;
