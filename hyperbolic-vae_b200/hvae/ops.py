@@ -467,18 +467,82 @@ def _gy_backward(ctx, g):
 gyroplane_fwd.register_autograd(_gy_backward, setup_context=_gy_setup)
 
 
+@_op("hvae::gyroplane_tc32_fwd", mutates_args=())
+def gyroplane_tc32_fwd(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], c: float, flags: int) -> Tensor:
+    """K2 at fp32 accuracy for any latent dim and any (a, p): tensor-core GEMMs on the three-way split for the inner
+    products and the gradient contractions, the pair function elementwise (csrc/gyro_tc32.cu):
+    x (B,D); p (P,D); a (P,D) or None (= p); bias (P,) or None -> (B,P)."""
+    C.require_cuda(x, p, a, bias)
+    B, D = x.shape
+    P = p.shape[0]
+    out = x.new_empty(B, P)
+    ws = _workspace(C.lib().hvae_gyroplane_tc32_fwd_workspace_bytes(B, D, P, int(a is not None)), x.device)
+    C.call("hvae_gyroplane_tc32_fwd_f32", C.ptr(x), C.ptr(p), C.ptr(a) if a is not None else None, C.ptr(bias), C.ptr(out), B, D, P, c,
+           flags, C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += 7 + (2 if a is not None else 0)
+    return out
+
+
+@gyroplane_tc32_fwd.register_fake
+def _(x, p, a, bias, c, flags):
+    return x.new_empty(x.shape[0], p.shape[0])
+
+
+@_op("hvae::gyroplane_tc32_bwd", mutates_args=())
+def gyroplane_tc32_bwd(x: Tensor, p: Tensor, a: Optional[Tensor], g: Tensor, c: float, flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    C.require_cuda(x, p, a, g)
+    B, D = x.shape
+    P = p.shape[0]
+    gx, gp = torch.empty_like(x), torch.empty_like(p)
+    ga = torch.empty_like(a) if a is not None else x.new_empty(0)
+    ws = _workspace(C.lib().hvae_gyroplane_tc32_bwd_workspace_bytes(B, D, P, int(a is not None)), x.device)
+    C.call("hvae_gyroplane_tc32_bwd_f32", C.ptr(x), C.ptr(p), C.ptr(a) if a is not None else None, C.ptr(g), C.ptr(gx), C.ptr(gp),
+           C.ptr(ga) if a is not None else None, B, D, P, c, flags, C.ptr(ws), ws.numel(), C.stream())
+    C.launch_count += 19 + (10 if a is not None else 0)
+    return gx, gp, ga
+
+
+@gyroplane_tc32_bwd.register_fake
+def _(x, p, a, g, c, flags):
+    return torch.empty_like(x), torch.empty_like(p), torch.empty_like(a) if a is not None else x.new_empty(0)
+
+
+def _gytc32_setup(ctx, inputs, output):
+    x, p, a, bias, c, flags = inputs
+    ctx.save_for_backward(x, p, a if a is not None else p)
+    ctx.has_a, ctx.has_bias, ctx.c, ctx.flags = a is not None, bias is not None, c, flags
+
+
+def _gytc32_backward(ctx, g):
+    x, p, a = ctx.saved_tensors
+    g = _c(g)
+    gx, gp, ga = gyroplane_tc32_bwd(x, p, a if ctx.has_a else None, g, ctx.c, ctx.flags)
+    gb = colsum(g) if ctx.has_bias else None
+    return gx, gp, (ga if ctx.has_a else None), gb, None, None
+
+
+gyroplane_tc32_fwd.register_autograd(_gytc32_backward, setup_context=_gytc32_setup)
+
+GYRO_SIMT_MAX_D = 64   # the SIMT kernels (csrc/gyroplane.cu) keep a row of x in registers
+
+
 def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], c: float, flags: int) -> Tensor:
-    """Signed hyperplane distances of every row of x (..., D) to every plane -> (..., P)."""
+    """Signed hyperplane distances of every row of x (..., D) to every plane -> (..., P).
+    bf16 GEMM mode: the fused tcgen05 kernels (a == p forward + backward; a != p forward under no_grad).  fp32 mode: the
+    SIMT kernels up to D = 64, beyond that - and for the a != p backward at any GEMM-sized D - the fp32-accurate
+    tensor-core path (split-operand GEMMs + the elementwise pair function)."""
     lead = x.shape[:-1]
     xr = _rows(x)
     a_arg = None if (a is None or a is p) else _c(a)
+    b_arg = None if bias is None else _c(bias)
     if a_arg is None and _tc_eligible(xr.shape[0], xr.shape[1], p.shape[0]):
-        out = gyroplane_tc_fwd(xr, _c(p), None if bias is None else _c(bias), c, int(flags))
+        out = gyroplane_tc_fwd(xr, _c(p), b_arg, c, int(flags))
     elif a_arg is not None and _tc_eligible(xr.shape[0], xr.shape[1], p.shape[0]) and not torch.is_grad_enabled():
-        # a != p (GeodesicLayer): tensor-core forward (inference / evaluation; the a != p backward is the fp32 kernels')
-        out = geodesic_tc_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
+        out = geodesic_tc_fwd(xr, _c(p), a_arg, b_arg, c, int(flags))
+    elif xr.shape[1] > GYRO_SIMT_MAX_D:
+        out = gyroplane_tc32_fwd(xr, _c(p), a_arg, b_arg, c, int(flags))
     else:
-        out = gyroplane_fwd(xr, _c(p), a_arg, None if bias is None else _c(bias), c, int(flags))
+        out = gyroplane_fwd(xr, _c(p), a_arg, b_arg, c, int(flags))
     return out.view(*lead, p.shape[0])
 
 

@@ -314,6 +314,21 @@ int hvae_gemm_x2s_plan(int64_t M, int64_t N, int64_t K, int* bn, int* splits, in
 int hvae_gemm_x2s_f32(const void* As, const float* inv_a, const void* Bs, const float* inv_b, const float* bias, int relu,
                       float* C, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K2 at fp32 accuracy for GEMM-sized latent dims (D > 64: beyond the SIMT kernels) and ANY (a, p): a == p
+ * (layers.py:193-210, geoopt Distance2StereographicHyperplanes) and GeodesicLayer / normdist2plane (layers.py:96-121 ->
+ * manifolds.py:41-65, HVAE_GYRO_PVAE), forward and backward.  <x,p> and <x,a> come from the three-way split GEMM above
+ * (2^-24 per term), the pair function and its gradient are applied elementwise, the parameter / input gradients are four more GEMMs
+ * (hyperbolic-vae_b200/csrc/gyro_tc32.cu).  Same arguments as hvae_gyroplane_{fwd,bwd}_f32; a == NULL or a == p: a aliases p
+ * (`two` = 0 in the workspace queries) and ga must be NULL. */
+size_t hvae_gyroplane_tc32_fwd_workspace_bytes(int64_t B, int64_t D, int64_t P, int two);
+size_t hvae_gyroplane_tc32_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P, int two);
+int hvae_gyroplane_tc32_fwd_f32(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B,
+                              int64_t D, int64_t P, float c, uint32_t flags, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int hvae_gyroplane_tc32_bwd_f32(const float* x, const float* p, const float* a, const float* gout, float* gx, float* gp,
+                              float* ga, int64_t B, int64_t D, int64_t P, float c, uint32_t flags, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
