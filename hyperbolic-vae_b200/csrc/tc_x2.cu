@@ -41,6 +41,7 @@ constexpr int CG = 4, EPI_WARPS = 4 * CG, THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2, ACC_COLS = 256;            // two accumulator stages of up to 256 columns: all of tensor memory
 constexpr uint32_t TILE_A = BM * BK * 2;                 // 16 KB
 constexpr uint32_t SMEM_LIMIT = 232448, BAR_BYTES = 256;
+constexpr uint32_t STG_WARP = 16 * 128, STG_BYTES = EPI_WARPS * STG_WARP;   // 16 rows x 32 fp32 per epilogue warp
 constexpr int MAX_STAGES = 4, MAX_SPLITS = 8;
 
 // 16 lanes x (4 repeats of 256 bits) -> 16 registers, complete on return
@@ -95,7 +96,8 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const uint32_t tile_b = (uint32_t)prm.bn * (BK * 2);
     const uint32_t stage_bytes = 2u * TILE_A + 2u * tile_b;
     const int NST = prm.nst;
-    const uint32_t bars = base + (uint32_t)NST * stage_bytes;
+    const uint32_t stg_base = base + (uint32_t)NST * stage_bytes;          // per-warp staging boxes of the finish
+    const uint32_t bars = stg_base + STG_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
@@ -236,7 +238,6 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int lr = lane >> 2, lc = (lane & 3) * 2;
         const int nchunks = prm.bn >> 5;
         const bool two = cg + CG < nchunks;   // (warp-uniform) this warp owns a second chunk
-        const bool n_even = (prm.N & 1) == 0;
         int as = 0;
         uint32_t aphase = 0;
         [[maybe_unused]] const int tsb = 128;
@@ -252,18 +253,9 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[j][0][i] = acc[j][1][i] = 0.0f;
-            // row / column constants of the finish, fetched while the first chunk is still being multiplied: lane l holds the
-            // inverse scale (and bias) of column l of each of the warp's chunks (shuffled to its users below) and the
-            // inverse scales of the thread's four rows
+            // inverse scales of the thread's four rows (fragment layout), fetched while the first chunk is still being multiplied
             const bool fin = S == 1;
-            float sbl[2], bl[2], sar[4];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t col = (int64_t)nt * prm.bn + (cg + CG * j) * 32 + lane;
-                const bool in = (j == 0 || two) && col < prm.N;
-                sbl[j] = in ? __ldg(prm.sb + col) : 0.0f;
-                bl[j] = (in && fin && prm.bias) ? __ldg(prm.bias + col) : 0.0f;
-            }
+            float sar[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int64_t row = (int64_t)mt * BM + q * 32 + 16 * (k >> 1) + 8 * (k & 1) + lr;
@@ -291,43 +283,72 @@ k_x2_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1u; }
             }
             // finish: undo the operand scales, bias, ReLU, store.  element (k = 2h + g, i, e): acc[j][h][4i + 2g + e]  <->
-            // row 16h + 8g + lr of the warp's 32, column 8i + lc + e of chunk j
-            // (one 64-bit base per thread - row lr of the warp's quarter, first column of the tile - and 32-bit offsets)
-            const int N32 = (int)prm.N;
-            const int64_t row0 = (int64_t)mt * BM + q * 32 + lr, col0 = (int64_t)nt * prm.bn;
-            float* __restrict__ Dt = prm.D + (int64_t)sp * prm.M * prm.N + row0 * prm.N + col0;
-            const bool interior = n_even && (int64_t)mt * BM + BM <= prm.M && col0 + prm.bn <= prm.N;   // (uniform) nothing to clip
+            // row 16h + 8g + lr of the warp's 32, column 8i + lc + e of chunk j.  Each 16-row half of a chunk is scaled by its
+            // rows' factors, goes through the warp's 2 KB staging box (16 rows x 128 B, 16-byte chunk c of row r at position
+            // c ^ (r % 8): conflict-free both ways) and is read back with a lane owning 4 consecutive columns of one row: the
+            // column factors and the bias are one float4 each per lane and chunk, the stores full 128-byte row segments.
+            const int64_t col0 = (int64_t)nt * prm.bn, rowq = (int64_t)mt * BM + q * 32;
+            float* __restrict__ Dp = prm.D + (int64_t)sp * prm.M * prm.N;
+            // (uniform) nothing to clip and every float4 access 16-byte aligned
+            const bool fast = (prm.N & 3) == 0 && (int64_t)mt * BM + BM <= prm.M && col0 + prm.bn <= prm.N &&
+                              ((reinterpret_cast<uintptr_t>(prm.D) | reinterpret_cast<uintptr_t>(prm.sb) | reinterpret_cast<uintptr_t>(prm.bias)) & 15) == 0;
+            uint8_t* stg_ptr = smem_raw + (stg_base - raw) + (uint32_t)(warp - 2) * STG_WARP;
+            const int c4 = (lane & 7) * 4;     // read-back: this lane's first column inside the chunk
             X2_STAMP(tsn++);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (j == 1 && !two) break;
-                const int cj = (cg + CG * j) * 32 + lc;   // this thread's first column of chunk j, relative to the tile
-                X2_STAMP(tsn++);
+                const int64_t n0 = col0 + (cg + CG * j) * 32;
+                float4 s4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b4 = s4;
+                if (fast) {
+                    s4 = __ldg(reinterpret_cast<const float4*>(prm.sb + n0 + c4));
+                    if (fin && prm.bias) b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + c4));
+                } else {
+                    float* sv = &s4.x;
+                    float* bv = &b4.x;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float s0 = __shfl_sync(0xffffffffu, sbl[j], 8 * i + lc), s1 = __shfl_sync(0xffffffffu, sbl[j], 8 * i + lc + 1);
-                    const float b0 = __shfl_sync(0xffffffffu, bl[j], 8 * i + lc), b1 = __shfl_sync(0xffffffffu, bl[j], 8 * i + lc + 1);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float t0 = fmaf(acc[j][k >> 1][4 * i + 2 * (k & 1)], sar[k] * s0, b0);
-                        float t1 = fmaf(acc[j][k >> 1][4 * i + 2 * (k & 1) + 1], sar[k] * s1, b1);
-                        if (fin && prm.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
-                        const int off = (16 * (k >> 1) + 8 * (k & 1)) * N32 + cj + 8 * i;
-#ifdef HVAE_EXPERIMENT
-                        if (prm.dbg & 1) { if (t0 == 123.456f) Dt[0] = t1; continue; }
-#endif
-                        if (interior) {
-                            *reinterpret_cast<float2*>(Dt + off) = make_float2(t0, t1);
-                        } else if (row0 + 16 * (k >> 1) + 8 * (k & 1) < prm.M) {
-                            const int64_t col = col0 + cj + 8 * i;
-                            if (n_even && col + 2 <= prm.N) {
-                                *reinterpret_cast<float2*>(Dt + off) = make_float2(t0, t1);
-                            } else {
-                                if (col < prm.N) Dt[off] = t0;
-                                if (col + 1 < prm.N) Dt[off + 1] = t1;
-                            }
+                    for (int e = 0; e < 4; ++e) {
+                        if (n0 + c4 + e < prm.N) {
+                            sv[e] = __ldg(prm.sb + n0 + c4 + e);
+                            if (fin && prm.bias) bv[e] = __ldg(prm.bias + n0 + c4 + e);
                         }
                     }
+                }
+                X2_STAMP(tsn++);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const float rsc = sar[2 * h + g];
+                            // (plain shared-memory accesses, not asm volatile: the compiler schedules them freely between the
+                            //  __syncwarp barriers)
+                            *reinterpret_cast<float2*>(stg_ptr + (8 * g + lr) * 128 + (((2 * i + (lc >> 2)) ^ lr) << 4) + (lc & 3) * 4) =
+                                make_float2(acc[j][h][4 * i + 2 * g] * rsc, acc[j][h][4 * i + 2 * g + 1] * rsc);
+                        }
+                    __syncwarp();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int rr = 4 * kk + (lane >> 3), c = lane & 7;
+                        float4 o = *reinterpret_cast<const float4*>(stg_ptr + rr * 128 + ((c ^ (rr & 7)) << 4));
+                        o.x = fmaf(o.x, s4.x, b4.x); o.y = fmaf(o.y, s4.y, b4.y); o.z = fmaf(o.z, s4.z, b4.z); o.w = fmaf(o.w, s4.w, b4.w);
+                        if (fin && prm.relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                        const int64_t row = rowq + 16 * h + rr, col = n0 + c4;
+#ifdef HVAE_EXPERIMENT
+                        if (prm.dbg & 1) { if (o.x == 123.456f) Dp[0] = o.y; continue; }
+#endif
+                        float* dst = Dp + row * prm.N + col;
+                        if (fast) {
+                            *reinterpret_cast<float4*>(dst) = o;
+                        } else if (row < prm.M) {
+                            if (col < prm.N) dst[0] = o.x;
+                            if (col + 1 < prm.N) dst[1] = o.y;
+                            if (col + 2 < prm.N) dst[2] = o.z;
+                            if (col + 3 < prm.N) dst[3] = o.w;
+                        }
+                    }
+                    __syncwarp();   // the box is rewritten by the next half
                 }
             }
             X2_STAMP(tsn++);
@@ -550,7 +571,7 @@ static Plan pick_plan(int64_t M, int64_t N, int64_t K) {
     if (getenv("HVAE_X2_SPLITS")) best.splits = atoi(getenv("HVAE_X2_SPLITS"));
 #endif
     const uint32_t stage = 2u * TILE_A + 2u * (uint32_t)best.bn * (BK * 2);
-    int nst = (int)((SMEM_LIMIT - 1024u - BAR_BYTES) / stage);
+    int nst = (int)((SMEM_LIMIT - 1024u - BAR_BYTES - STG_BYTES) / stage);
     best.nst = nst > MAX_STAGES ? MAX_STAGES : nst;
 #ifdef HVAE_EXPERIMENT
     if (getenv("HVAE_X2_NST") && atoi(getenv("HVAE_X2_NST")) < best.nst) best.nst = atoi(getenv("HVAE_X2_NST"));
@@ -653,7 +674,7 @@ extern "C" int hvae_gemm_x2s_f32(const void* As, const float* inv_a, const void*
     prm.dbg = getenv("HVAE_X2_DBG") ? atoi(getenv("HVAE_X2_DBG")) : 0;
 #endif
     prm.a_lo = (int)Kp; prm.b_lo = (int)Kp; prm.sa = inv_a; prm.sb = inv_b;
-    const uint32_t smem = (uint32_t)pl.nst * (2u * x2::TILE_A + 2u * (uint32_t)pl.bn * (x2::BK * 2)) + 1024u + x2::BAR_BYTES;
+    const uint32_t smem = (uint32_t)pl.nst * (2u * x2::TILE_A + 2u * (uint32_t)pl.bn * (x2::BK * 2)) + x2::STG_BYTES + 1024u + x2::BAR_BYTES;
     cudaFuncSetAttribute(x2::k_x2_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x2::SMEM_LIMIT);
     const int64_t units = ((M + x2::BM - 1) / x2::BM) * ((N + pl.bn - 1) / pl.bn) * pl.splits;
     if (units > 0x7fffffffLL || N > 0x3ffffffLL) return HVAE_ESHAPE;   // 32-bit unit / in-tile offset arithmetic in the kernel
