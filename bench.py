@@ -290,9 +290,16 @@ def trunk_roofline(gemms, device, pk, pk_kind, flush):
     t_g, t_c = _time_flushed(run_x2, flush), _time_flushed(run_cublas, flush)
     fl = sum(2.0 * m_ * n_ * k_ for (m_, n_, k_) in gemms)
     n_g = sum(C.lib().hvae_gemm_x2s_num_launches(m_, n_, k_) for (m_, n_, k_) in gemms)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r2b_x2_traffic.json")   # ncu --set full capture of these five launches (committed)
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["traffic_bytes_per_launch_mean"], "profiles/r2b_x2_traffic.json (ncu capture, not this run)"
     return {"bound": "tensor", "kernel": "k_x2_gemm (trunk dense layers: fp32-accurate two-piece fp16 tcgen05 GEMM, power-of-two row scales)",
             "achieved": fl / t_g / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t_g / 1e12 / pk["bf16_tflops"],
-            "traffic": None, "peak_source": pk_kind, "launch_us": t_g / len(gemms) * 1e6, "launches_per_step": n_g,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": sum((m_ + n_) * 2 * ((k_ + 63) // 64 * 64) * 2 + 4 * m_ * n_ for (m_, n_, k_) in gemms) / len(gemms),
+            "peak_source": pk_kind, "launch_us": t_g / len(gemms) * 1e6, "launches_per_step": n_g,
             "algorithmic_flops_per_step": fl, "executed_tflops": 3.0 * fl / t_g / 1e12,
             "executed_frac": 3.0 * fl / t_g / 1e12 / pk["bf16_tflops"],
             "cublas_fp32_same_shapes": {"us": t_c * 1e6, "tflops": fl / t_c / 1e12, "ours_over_cublas_time": t_g / t_c,
@@ -361,7 +368,7 @@ def cfg2_kernels(wl, device, pk, flush):
         "mobius_matvec_fwd": (lambda: ops.mobius_matvec_fwd(x, M, c), 4 * (B * F + D * F + 2 * B * D)),
         "mobius_matvec_bwd": (lambda: ops.mobius_matvec_bwd(x, M, mx, gy, c), 4 * (2 * B * F + 2 * D * F + 3 * B * D)),
         "gyroplane_fwd": (lambda: ops.gyroplane_fwd(z, Mg, bpt, None, c, FL), 4 * (B * D + 2 * H * D + B * H)),
-        "gyroplane_bwd": (lambda: ops.gyroplane_bwd(z, Mg, bpt, gout, c, FL, False), 4 * (B * H + 2 * B * D + 4 * H * D)),
+        "gyroplane_bwd": (lambda: ops.gyroplane_bwd(z, Mg, bpt, None, gout, c, FL, False), 4 * (B * H + 2 * B * D + 4 * H * D)),
     }
     res = {}
     for name, (fn, nbytes) in cases.items():

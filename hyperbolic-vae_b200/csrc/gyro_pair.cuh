@@ -94,6 +94,7 @@ __device__ __forceinline__ float gyro_pair_fwd(float px, float xa, float x2, flo
 
 struct GyroPairGrad {
     float dpx, dxa, dx2, dp2, dpa, dan;  // dan: gradient wrt the RAW ||a||
+    float g_used;                        // set by gyro_pair_grad_general only: the upstream gradient after the fused-ReLU mask
 };
 
 __device__ __forceinline__ GyroPairGrad gyro_pair_bwd(float g, float px, float xa, float x2, float p2, float pa,
@@ -141,6 +142,176 @@ __device__ __forceinline__ GyroPairGrad gyro_pair_bwd(float g, float px, float x
     r.dx2 = k.Bc * k.Bc * dN2 + c * dA + c * c * p2 * dden0;
     r.dpx = -2.0f * k.A * k.Bc * dN2 - 2.0f * c * dA - 2.0f * c * dden0;
     r.dan = (pvae && an_raw < kMinNorm) ? 0.0f : gan;
+    return r;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Lean pair path (SIMT kernels).  Two closed forms cover every pair on which no MIN_NORM clamp binds:
+//  * unprojected: da = N1/den, |diff|^2 = N2/den^2, w = (1 - c|diff|^2)|a|, y = 2 sc da / w collapse to ONE division,
+//        y = 2 sc N1 den / (|a| (den^2 - c N2));
+//  * projected (pvae: |(-p)(+)x| > maxnorm, the COMMON case for a 10-d RiemannianNormal posterior, whose radius
+//    concentrates near (D-1) sigma^2 - far beyond the fp32 projection radius): diff is rescaled to norm maxnorm, so
+//    |diff|^2 and w are constants and  y = K_j N1 / sqrt(N2),  K_j = 2 sc maxnorm / ((1 - c maxnorm^2)|a_j|)  (den cancels).
+// Reciprocals are MUFU + one Newton step (~1 ulp, no IEEE slow-path branch); the backward differentiates these forms
+// directly.  gyro_pair_lean_fwd returns GYRO_GENERAL when one of the reference's clamps (den, |diff|^2, w >= MIN_NORM;
+// geoopt's clamp_abs) would change the value or mask a gradient: the caller then takes gyro_pair_fwd / _bwd.
+// ---------------------------------------------------------------------------------------------------
+struct GyroPlaneK {
+    float p2, pa, an_raw, an, ran, Bc, kproj;   // |p|^2, <p,a>, |a|, clamped |a| (pvae), 1/an, 1 - c|p|^2, K_j
+};
+
+__device__ __forceinline__ GyroPlaneK gyro_plane_consts(float p2, float pa, float an_raw, const GyroParams& P) {
+    GyroPlaneK k;
+    k.p2 = p2; k.pa = pa; k.an_raw = an_raw;
+    k.an = (P.flags & HVAE_GYRO_PVAE) ? fmaxf(an_raw, kMinNorm) : an_raw;
+    k.ran = 1.0f / k.an;
+    k.Bc = 1.0f - P.c * p2;
+    const float w = (1.0f - P.c * (P.maxnorm * P.maxnorm)) * k.an;      // w of a projected pair
+    k.kproj = (w >= kMinNorm) ? 2.0f * P.sc * P.maxnorm / w : 0.0f;     // 0: the w clamp binds -> general path
+    return k;
+}
+
+// MUFU wrappers without the denormal pre-/post-scaling the plain intrinsics carry in non-ftz builds: every argument on
+// the lean path is >= 1 (1 + y^2, |y| + sqrt(1 + y^2)) or a checked normal number
+__device__ __forceinline__ float rsqrt_ftz(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float lg2_ftz(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+// asinh_fast with those wrappers (same polynomial / log split, same error bound)
+__device__ __forceinline__ float asinh_lean(float y, float h /* 1 + y^2 */, float rsh /* rsqrt(h) */) {
+    const float ay = fabsf(y);
+    const float y2 = ay * ay;
+    const float poly = ay * fmaf(y2, fmaf(y2, fmaf(y2, fmaf(y2, 105.0f / 3456.0f, -15.0f / 336.0f), 3.0f / 40.0f), -1.0f / 6.0f), 1.0f);
+    const float big = lg2_ftz(fmaf(h, rsh, ay)) * 0.693147180559945309f;
+    return copysignf(ay < 0.25f ? poly : big, y);
+}
+
+__device__ __forceinline__ float rcp_nr(float v) {   // v normal and positive
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return fmaf(r, fmaf(-v, r, 1.0f), r);
+}
+
+enum : int { GYRO_GENERAL = 0, GYRO_UNPROJECTED = 1, GYRO_PROJECTED = 2 };
+
+struct GyroLean {
+    // y = s * t:  unprojected s = +-2 sc N1 den, t = 1/(|a| (den^2 - c N2));  projected s = +-N1, t = K_j rsqrt(N2)
+    float A, N1, N2, den, t, rs, y, rsh, out0, out1;   // rs = rsqrt(N2) (projected), rsh = rsqrt(1 + y^2)
+};
+
+__device__ __forceinline__ int gyro_pair_lean_fwd(const GyroDiff& df, float x2, const GyroPlaneK& pl, const GyroParams& P,
+                                                  GyroLean& L, float& out) {
+    const float c = P.c;
+    const bool pvae = P.flags & HVAE_GYRO_PVAE;
+    const float px = pl.p2 - df.q;
+    const float den = fmaf(c * c * pl.p2, x2, fmaf(-2.0f * c, px, 1.0f));
+    const float ce = c * df.e;
+    L.A = pl.Bc + ce;
+    L.N1 = -fmaf(pl.Bc, df.qa, ce * pl.pa);
+    L.N2 = df.e * fmaf(c * pl.p2, ce, fmaf(2.0f * c * pl.Bc, df.q, pl.Bc * pl.Bc));
+    L.den = den;
+    const float dd = den * den;
+    const float lo = kMinNorm * dd;
+    if (!(den >= kMinNorm) || !(L.N2 >= lo)) return GYRO_GENERAL;
+    int mode;
+    float s;
+    if (pvae && L.N2 > P.maxnorm * P.maxnorm * dd) {
+        if (!(pl.kproj > 0.0f)) return GYRO_GENERAL;
+        mode = GYRO_PROJECTED;
+        L.rs = rsqrt_ftz(L.N2);
+        L.t = pl.kproj * L.rs;
+        s = L.N1;
+    } else {
+        // w = denom/dd above its clamp (geoopt: |w| + MIN_NORM == |w| in fp32)
+        const float denom = pl.an * fmaf(-c, L.N2, dd);
+        if (!(denom >= (pvae ? lo : 1e-6f * dd))) return GYRO_GENERAL;
+        mode = GYRO_UNPROJECTED;
+        L.t = rcp_nr(denom);
+        s = (2.0f * P.sc) * L.N1 * den;
+    }
+    L.y = ((P.flags & HVAE_GYRO_SIGNED) ? s : fabsf(s)) * L.t;
+    const float h = fmaf(L.y, L.y, 1.0f);
+    L.rsh = rsqrt_ftz(h);
+    L.out0 = asinh_lean(L.y, h, L.rsh) * P.rsc;
+    L.out1 = (P.flags & HVAE_GYRO_SCALED) ? L.out0 * pl.an : L.out0;
+    float o = L.out1;
+    if (P.flags & HVAE_GYRO_SQUARED) {
+        const float sg = (o > 0.0f) ? 1.0f : ((o < 0.0f) ? -1.0f : 0.0f);
+        o = (P.flags & HVAE_GYRO_SIGNED) ? o * o * sg : o * o;
+    }
+    out = o;
+    return mode;
+}
+
+__device__ __forceinline__ GyroPairGrad gyro_pair_lean_bwd(int mode, float g, const GyroDiff& df, float x2, const GyroPlaneK& pl,
+                                                           const GyroParams& P, const GyroLean& L) {
+    GyroPairGrad r;
+    const float c = P.c;
+    float g1 = g;
+    if (P.flags & HVAE_GYRO_SQUARED) g1 = (P.flags & HVAE_GYRO_SIGNED) ? g * 2.0f * fabsf(L.out1) : g * 2.0f * L.out1;
+    float gan = 0.0f, g0 = g1;
+    if (P.flags & HVAE_GYRO_SCALED) {
+        gan = g1 * L.out0;
+        g0 = g1 * pl.an;
+    }
+    const float dy = g0 * P.rsc * L.rsh;
+    float u = dy * L.t;                                       // dL/ds up to the sign of s
+    if (!(P.flags & HVAE_GYRO_SIGNED)) u = (L.N1 > 0.0f) ? u : ((L.N1 < 0.0f) ? -u : 0.0f);   // den > 0: sign(s) = sign(N1)
+    const float yv = dy * L.y;
+    gan = fmaf(-yv, pl.ran, gan);
+    float dN1, dN2, dden;
+    if (mode == GYRO_PROJECTED) {
+        dN1 = u;
+        dN2 = -0.5f * yv * L.rs * L.rs;                       // y ~ N2^(-1/2)
+        dden = 0.0f;
+    } else {
+        u *= 2.0f * P.sc;
+        const float v = yv * L.t * pl.an;                     // -dL/d(den^2 - c N2)
+        dN1 = u * L.den;
+        dN2 = c * v;
+        dden = fmaf(u, L.N1, -2.0f * L.den * v);
+    }
+    const float px = pl.p2 - df.q, xa = pl.pa - df.qa;
+    const float A = L.A, Bc = pl.Bc;
+    const float dA = fmaf(-pl.pa, dN1, 2.0f * (A * pl.p2 - Bc * px) * dN2);
+    const float dBc = fmaf(xa, dN1, 2.0f * (Bc * x2 - A * px) * dN2);
+    r.dpa = -A * dN1;
+    r.dxa = Bc * dN1;
+    r.dp2 = fmaf(A * A, dN2, fmaf(c * c * x2, dden, -c * dBc));
+    r.dx2 = fmaf(Bc * Bc, dN2, fmaf(c * c * pl.p2, dden, c * dA));
+    r.dpx = -2.0f * fmaf(A * Bc, dN2, c * (dA + dden));
+    r.dan = ((P.flags & HVAE_GYRO_PVAE) && pl.an_raw < kMinNorm) ? 0.0f : gan;
+    return r;
+}
+
+// the general path out of line: it runs for a handful of pairs (if any), and inlining it next to the lean path in an
+// 8-row unrolled loop would multiply the kernel's code size for nothing
+static __device__ __noinline__ float gyro_pair_fwd_general(float e, float q, float qa, float x2, float p2, float pa, float an_raw,
+                                                    GyroParams P) {
+    GyroPairCtx k;
+    GyroDiff df;
+    df.e = e; df.q = q; df.qa = qa;
+    return gyro_pair_fwd(p2 - q, pa - qa, x2, p2, pa, an_raw, P, k, &df);
+}
+
+static __device__ __noinline__ GyroPairGrad gyro_pair_grad_general(float g, float e, float q, float qa, float x2, float p2, float pa,
+                                                            float an_raw, GyroParams P, float bias) {
+    GyroPairCtx k;
+    GyroDiff df;
+    df.e = e; df.q = q; df.qa = qa;
+    const float px = p2 - q, xa = pa - qa;
+    const float o = gyro_pair_fwd(px, xa, x2, p2, pa, an_raw, P, k, &df);
+    if ((P.flags & HVAE_GYRO_RELU) && !(o + bias > 0.0f)) g = 0.0f;
+
+    GyroPairGrad r = gyro_pair_bwd(g, px, xa, x2, p2, pa, an_raw, P, k);
+    r.g_used = g;
     return r;
 }
 

@@ -24,10 +24,14 @@ namespace hvae {
 constexpr int kGyroThreads = 128;
 constexpr int kGyroRB = 8;    // rows per register block
 
-template <int D4, bool kAliased, int kGyroTB /* rows per CTA */>
+// FL >= 0: the flag word as a compile-time constant (the two combinations the layers use: GeodesicLayer's
+// PVAE|SIGNED with a != p, Distance2PoincareHyperplanes' SIGNED with a == p); FL < 0: flags read from prm at run time.
+template <int D4, bool kAliased, int FL>
 __global__ void __launch_bounds__(kGyroThreads)
 k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
-           const float* __restrict__ bias, float* __restrict__ out, int B, int D, int P_, GyroParams prm) {
+           const float* __restrict__ bias, float* __restrict__ out, int B, int D, int P_, int kGyroTB /* rows per CTA */,
+           GyroParams prm) {
+    if (FL >= 0) prm.flags = (uint32_t)FL;
     constexpr int TJ = kGyroThreads;
     extern __shared__ float smem[];
     float* xs = smem;                       // [TB][D4]
@@ -66,6 +70,7 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
         a2 = fmaf(av, av, a2);
     }
     const float an_raw = sqrtf(a2);
+    const GyroPlaneK pl = gyro_plane_consts(p2, pa, an_raw, prm);
     const float bj = (bias != nullptr && j < P_) ? __ldg(bias + j) : 0.0f;
     __syncthreads();
     for (int r0 = 0; r0 < kGyroTB; r0 += kGyroRB) {
@@ -92,17 +97,21 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
             }
         }
         if (j < P_) {
+            float* op = out + (int64_t)(b0 + r0) * P_ + j;
+            const int nr = min(kGyroRB, B - b0 - r0);
 #pragma unroll
             for (int r = 0; r < kGyroRB; ++r) {
-                const int b = b0 + r0 + r;
-                if (b < B) {
-                    GyroPairCtx k;
+                if (r < nr) {
                     GyroDiff df;
                     df.e = ee[r]; df.q = qq[r]; df.qa = kAliased ? qq[r] : qa[r];
-                    const float px = p2 - qq[r];
-                    const float xa = kAliased ? px : pa - qa[r];
-                    const float o = gyro_pair_fwd(px, xa, xs2[r0 + r], p2, pa, an_raw, prm, k, &df);
-                    out[(int64_t)b * P_ + j] = o + bj;
+                    GyroLean L;
+                    float o;
+                    if (gyro_pair_lean_fwd(df, xs2[r0 + r], pl, prm, L, o) == GYRO_GENERAL)
+                        o = gyro_pair_fwd_general(df.e, df.q, df.qa, xs2[r0 + r], p2, pa, an_raw, prm);
+                    o += bj;
+                    if (prm.flags & HVAE_GYRO_RELU) o = fmaxf(o, 0.0f);
+                    *op = o;
+                    op += P_;
                 }
             }
         }
@@ -116,29 +125,33 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
 //                            CP[b][j] = dL/d<p_j,x_b> (+ dL/d<a_j,x_b> when a aliases p),  CA[b][j] = dL/d<a_j,x_b>
 //                          and per-(row-block, plane) sums of the scalar terms (d|p|^2, d<p,a>, d|a|, g).
 //   G2  k_gyro_bwd_planes: thread = one plane; gp_j = sum_b CP[b][j] x_b + (scalar terms) — a skinny GEMM over a
-//                          slab of rows, partials per slab, then k_gyro_reduce_slabs (deterministic, no atomics).
+//                          slab of rows, partials per slab, then k_gyro_reduce_all (one launch for gx, gp, ga, gbias; deterministic, no atomics).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGyroBxThreads = 128;  // rows per CTA
 constexpr int kGyroBxTJ = 32;        // planes per smem stage
 
 // small D: cap registers so 5 CTAs fit an SM (the static smem allows 5): 115 -> 89 registers at D4 = 12, no spills
-template <int D4, bool kAliased>
+template <int D4, bool kAliased, int FL>
 __global__ void __launch_bounds__(kGyroBxThreads, (D4 <= 16 ? 5 : 1))
 k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const float* __restrict__ a,
-                 const float* __restrict__ gout, float* __restrict__ gx, float* __restrict__ CP, float* __restrict__ CA,
+                 const float* __restrict__ bias /* forward bias, read only with HVAE_GYRO_RELU */, const float* __restrict__ gout, float* __restrict__ gx, float* __restrict__ CP, float* __restrict__ CA,
                  float* __restrict__ wsum /* [rowblocks][P][4] */, int B, int D, int P_, int planes_per_chunk,
                  GyroParams prm) {
     constexpr int TJ = (D4 >= 64) ? 16 : kGyroBxTJ;  // keep the static smem under 48 KB at D4 = 64
     __shared__ float ps[TJ][D4];
     __shared__ float as[kAliased ? 1 : TJ][D4];
-    __shared__ float pst[TJ][4];                      // p2, pa, an_raw
+    __shared__ __align__(16) float pst[TJ][8];        // GyroPlaneK of the staged planes
     __shared__ float gs[kGyroBxThreads][TJ + 1];      // upstream grad tile [row][plane]; reused for CP
     __shared__ float cs[kAliased ? 1 : kGyroBxThreads][TJ + 1];  // CA tile
     __shared__ float psum[4][TJ][4];                  // per-warp partial sums of the scalar terms
+    if (FL >= 0) prm.flags = (uint32_t)FL;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * kGyroBxThreads;
     const int b = b0 + tid;
+    float* const grow = &gs[tid][0];                         // this thread's row of the gradient / CP tile
+    float* const crow = &cs[kAliased ? 0 : tid][0];
+    float* const prow = &psum[warp][0][(lane >> 3) & 3];    // lane 8q publishes sum q
     float xr[D4], acc[D4];
     float x2 = 0.0f, sdx2 = 0.0f;
 #pragma unroll
@@ -172,7 +185,10 @@ k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const
                 pa = fmaf(pv, av, pa);
                 a2 = fmaf(av, av, a2);
             }
-            pst[tid][0] = p2; pst[tid][1] = pa; pst[tid][2] = sqrtf(a2);
+            const GyroPlaneK pk = gyro_plane_consts(p2, pa, sqrtf(a2), prm);
+            *reinterpret_cast<float4*>(&pst[tid][0]) = make_float4(pk.p2, pk.pa, pk.an_raw, pk.an);
+            const float bj = (bias != nullptr && (j0 + tid) < jhi) ? __ldg(bias + j0 + tid) : 0.0f;
+            *reinterpret_cast<float4*>(&pst[tid][4]) = make_float4(pk.ran, pk.Bc, pk.kproj, bj);
         }
         __syncthreads();
         const int jn = min(TJ, jhi - j0);
@@ -191,14 +207,24 @@ k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const
                 }
             }
             if (kAliased) df.qa = df.q;
-            const float p2 = pst[jj][0], pa = pst[jj][1], an_raw = pst[jj][2];
-            const float px = p2 - df.q;
-            const float xa = kAliased ? px : pa - df.qa;
-            const float g = gs[tid][jj];
-            GyroPairCtx k;
-            gyro_pair_fwd(px, xa, x2, p2, pa, an_raw, prm, k, &df);
-            GyroPairGrad gr = gyro_pair_bwd(g, px, xa, x2, p2, pa, an_raw, prm, k);
-            if (b >= B) { gr.dpx = gr.dxa = gr.dx2 = gr.dp2 = gr.dpa = gr.dan = 0.0f; }
+            GyroPlaneK pl;
+            {
+                const float4 c0 = *reinterpret_cast<const float4*>(&pst[jj][0]);
+                const float4 c1 = *reinterpret_cast<const float4*>(&pst[jj][4]);
+                pl.p2 = c0.x; pl.pa = c0.y; pl.an_raw = c0.z; pl.an = c0.w; pl.ran = c1.x; pl.Bc = c1.y; pl.kproj = c1.z;
+            }
+            float g = grow[jj];   // zero for rows past B: every gradient term below is linear in g
+            GyroPairGrad gr;
+            GyroLean L;
+            float o;
+            const int mode = gyro_pair_lean_fwd(df, x2, pl, prm, L, o);
+            if (mode != GYRO_GENERAL) {
+                if ((prm.flags & HVAE_GYRO_RELU) && !(o + pst[jj][7] > 0.0f)) g = 0.0f;   // fused ReLU: mask by the recomputed sign
+                gr = gyro_pair_lean_bwd(mode, g, df, x2, pl, prm, L);
+            } else {
+                gr = gyro_pair_grad_general(g, df.e, df.q, df.qa, x2, pl.p2, pl.pa, pl.an_raw, prm, pst[jj][7]);
+                g = gr.g_used;
+            }
             sdx2 += gr.dx2;
             const float cp = kAliased ? gr.dpx + gr.dxa : gr.dpx;
 #pragma unroll
@@ -212,18 +238,25 @@ k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const
                     acc[d + 2] = fmaf(gr.dxa, av.z, acc[d + 2]); acc[d + 3] = fmaf(gr.dxa, av.w, acc[d + 3]);
                 }
             }
-            gs[tid][jj] = cp;                       // own element: no hazard
-            if (!kAliased) cs[tid][jj] = gr.dxa;
+            grow[jj] = cp;                          // own element: no hazard
+            if (!kAliased) crow[jj] = gr.dxa;
             // per-plane sums over this warp's 32 rows
-            float s0 = gr.dp2, s1 = gr.dpa, s2 = gr.dan, s3 = (b < B) ? g : 0.0f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+            // four sums over the warp by a transposing butterfly (6 shuffles instead of 20): the halves of the warp
+            // swap two of the four values, then the quarters one, then three plain steps; lane 8q ends with sum q
+            {
+                const bool h16 = lane & 16, h8 = lane & 8;
+                float k0 = h16 ? gr.dan : gr.dp2, k1 = h16 ? g : gr.dpa;
+                const float t0 = h16 ? gr.dp2 : gr.dan, t1 = h16 ? gr.dpa : g;
+                k0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+                k1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+                float k = h8 ? k1 : k0;
+                const float t = h8 ? k0 : k1;
+                k += __shfl_xor_sync(0xffffffffu, t, 8);
+                k += __shfl_xor_sync(0xffffffffu, k, 4);
+                k += __shfl_xor_sync(0xffffffffu, k, 2);
+                k += __shfl_xor_sync(0xffffffffu, k, 1);
+                if ((lane & 7) == 0) prow[jj * 4] = k;
             }
-            if (lane == 0) { psum[warp][jj][0] = s0; psum[warp][jj][1] = s1; psum[warp][jj][2] = s2; psum[warp][jj][3] = s3; }
         }
         __syncthreads();
         // coalesced write-out of the coefficient tiles and the per-row-block sums
@@ -278,18 +311,30 @@ k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, cons
         __syncthreads();
         const int bn = min(kGyroBpTB, be - b0);
         if (j < P_) {
-#pragma unroll 4
-            for (int bb = 0; bb < bn; ++bb) {
-                const float cp = __ldg(CP + (int64_t)(b0 + bb) * P_ + j);  // coalesced across the CTA's planes
-                const float ca = kAliased ? 0.0f : __ldg(CA + (int64_t)(b0 + bb) * P_ + j);
+            // the kernel is latency-bound (a few warps per SM, each load a trip to L2): issue the coefficient loads of
+            // 8 rows before the first FMA (rows past bn read as zero: they add nothing)
+            constexpr int U = 8;
+            static_assert(kGyroBpTB % U == 0, "row stage must be a multiple of the load batch");
+            for (int bb = 0; bb < bn; bb += U) {
+                float cpv[U], cav[U];
 #pragma unroll
-                for (int d = 0; d < D4; d += 4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][d]);
-                    accp[d] = fmaf(cp, xv.x, accp[d]); accp[d + 1] = fmaf(cp, xv.y, accp[d + 1]);
-                    accp[d + 2] = fmaf(cp, xv.z, accp[d + 2]); accp[d + 3] = fmaf(cp, xv.w, accp[d + 3]);
-                    if (!kAliased) {
-                        acca[d] = fmaf(ca, xv.x, acca[d]); acca[d + 1] = fmaf(ca, xv.y, acca[d + 1]);
-                        acca[d + 2] = fmaf(ca, xv.z, acca[d + 2]); acca[d + 3] = fmaf(ca, xv.w, acca[d + 3]);
+                for (int u = 0; u < U; ++u) {
+                    const bool ok = bb + u < bn;
+                    cpv[u] = ok ? __ldg(CP + (int64_t)(b0 + bb + u) * P_ + j) : 0.0f;  // coalesced across the CTA's planes
+                    cav[u] = (!kAliased && ok) ? __ldg(CA + (int64_t)(b0 + bb + u) * P_ + j) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float cp = cpv[u], ca = cav[u];
+#pragma unroll
+                    for (int d = 0; d < D4; d += 4) {
+                        const float4 xv = *reinterpret_cast<const float4*>(&xs[bb + u][d]);
+                        accp[d] = fmaf(cp, xv.x, accp[d]); accp[d + 1] = fmaf(cp, xv.y, accp[d + 1]);
+                        accp[d + 2] = fmaf(cp, xv.z, accp[d + 2]); accp[d + 3] = fmaf(cp, xv.w, accp[d + 3]);
+                        if (!kAliased) {
+                            acca[d] = fmaf(ca, xv.x, acca[d]); acca[d + 1] = fmaf(ca, xv.y, acca[d + 1]);
+                            acca[d + 2] = fmaf(ca, xv.z, acca[d + 2]); acca[d + 3] = fmaf(ca, xv.w, acca[d + 3]);
+                        }
                     }
                 }
             }
@@ -329,12 +374,40 @@ k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, cons
     }
 }
 
-__global__ void k_gyro_reduce_slabs(const float* __restrict__ w, float* __restrict__ out, int64_t n, int slabs) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.0f;
-    for (int k = 0; k < slabs; ++k) s += w[(int64_t)k * n + i];
-    out[i] = s;
+// all slab reductions of one backward (gx over plane chunks; gp, ga, gbias over row slabs) in ONE launch:
+// blockIdx.y selects the segment
+struct GyroReduceSeg {
+    const float* w;
+    float* out;
+    int64_t n;
+    int slabs;
+};
+struct GyroReduceArgs {
+    GyroReduceSeg seg[4];
+};
+// block = 32 consecutive elements x 8 slab lanes: lane group s sums slabs s, s + 8, ... (coalesced 128-byte loads, 8
+// independent chains per element instead of one serial walk over up to 64 slabs), then a fixed-order sum of the 8 partials
+__global__ void __launch_bounds__(256) k_gyro_reduce_all(GyroReduceArgs a) {
+    __shared__ float part[8][33];
+    const GyroReduceSeg sg = a.seg[blockIdx.y];
+    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < sg.n; i0 += (int64_t)gridDim.x * 32) {
+        const int64_t i = i0 + e;
+        float s = 0.0f;
+        if (i < sg.n) {
+#pragma unroll 4
+            for (int k = sl; k < sg.slabs; k += 8) s += sg.w[(int64_t)k * sg.n + i];
+        }
+        part[sl][e] = s;
+        __syncthreads();
+        if (sl == 0 && i < sg.n) {
+            float t = part[0][e];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) t += part[q][e];
+            sg.out[i] = t;
+        }
+        __syncthreads();
+    }
 }
 
 // G2 slabs of rows (multiples of the 128-row blocks of G1)
@@ -347,15 +420,23 @@ inline int gyro_slabs(int64_t B, int64_t P) {
     return (int)want;
 }
 
-// G1: how many plane-chunks (gridDim.y) so that ~4 CTAs/SM are in flight
-constexpr int kGyroChunkGran = 8;  // plane-chunk granularity (a stage holds up to 32 planes, a chunk may be shorter)
-inline int gyro_x_chunks(int64_t B, int64_t P) {
+// G1: planes per chunk (gridDim.y chunks).  The pair math is a long dependent chain, so the grid wants several CTAs per SM
+// - but in WHOLE waves of the resident-CTA slots (5 per SM at D <= 16 by launch bounds, 2 assumed beyond): at 4096 x 600
+// the old "about 8 CTAs per SM" rule made 800 CTAs of 24 planes on 740 slots, i.e. a second wave 8 % full.
+// cost = waves x (planes per chunk + ~3 planes' worth of per-CTA prologue / epilogue); ties go to fewer chunks.
+inline void gyro_x_plan(int64_t B, int64_t P, int64_t D, int* ppc_out, int* nch_out) {
     const int64_t rb = (B + kGyroBxThreads - 1) / kGyroBxThreads;
-    int64_t want = (8 * kNumSMs + rb - 1) / rb;   // the pair math is a long dependent chain: aim for ~8 CTAs per SM
-    const int64_t maxc = (P + kGyroChunkGran - 1) / kGyroChunkGran;
-    if (want > maxc) want = maxc;
-    if (want < 1) want = 1;
-    return (int)want;
+    const int64_t slots = (int64_t)kNumSMs * (D <= 16 ? 5 : 2);
+    int64_t best_ppc = P, best_cost = -1;
+    const int64_t max_ch = P < 512 ? P : 512;
+    for (int64_t nch = 1; nch <= max_ch; ++nch) {
+        const int64_t ppc = (P + nch - 1) / nch;
+        const int64_t n = (P + ppc - 1) / ppc;
+        const int64_t cost = ((rb * n + slots - 1) / slots) * (ppc + 3);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ppc = ppc; }
+    }
+    *ppc_out = (int)best_ppc;
+    *nch_out = (int)((P + best_ppc - 1) / best_ppc);
 }
 
 struct GyroWs {
@@ -365,7 +446,9 @@ struct GyroWs {
 inline GyroWs gyro_ws_layout(int64_t B, int64_t D, int64_t P) {
     GyroWs w;
     const size_t rbs = (size_t)((B + kGyroBxThreads - 1) / kGyroBxThreads);
-    const size_t slabs = (size_t)gyro_slabs(B, P), chunks = (size_t)gyro_x_chunks(B, P);
+    int ppc_, nch_;
+    gyro_x_plan(B, P, D, &ppc_, &nch_);
+    const size_t slabs = (size_t)gyro_slabs(B, P), chunks = (size_t)nch_;
     size_t o = 0;
     auto take = [&](size_t n) { const size_t at = o; o += (n + 3) / 4 * 4; return at; };
     w.cp = take((size_t)B * P);
@@ -386,48 +469,74 @@ inline GyroParams make_gyro_params(float c, uint32_t flags) {
     return p;
 }
 
-template <int D4, bool kAliased, int TB>
-int gyro_fwd_launch_tb(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B, int64_t D,
-                       int64_t P, const GyroParams& prm, cudaStream_t s) {
-    dim3 grid((unsigned)((P + kGyroThreads - 1) / kGyroThreads), (unsigned)((B + TB - 1) / TB));
-    const size_t smem = sizeof(float) * ((size_t)TB * D4 + TB + (size_t)D4 * kGyroThreads * (kAliased ? 1 : 2));
-    auto kern = k_gyro_fwd<D4, kAliased, TB>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kGyroThreads, smem, s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, prm);
+// rows per CTA of the forward kernel: the grid should fill the resident-CTA slots of the 148 SMs in whole waves (a
+// 4096 x 600 problem at 16 rows per CTA was 1280 CTAs on ~1036 slots: a second wave a quarter full).  cost = waves x
+// (rows + ~4 rows' worth of staging the 128 planes)
+inline int gyro_fwd_rows_per_cta(int64_t B, int64_t P, int ctas_per_sm) {
+    const int64_t jb = (P + kGyroThreads - 1) / kGyroThreads;
+    const int64_t slots = (int64_t)kNumSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    int best = kGyroRB;
+    int64_t best_cost = -1;
+    for (int tb = kGyroRB; tb <= 128; tb += kGyroRB) {
+        const int64_t ctas = jb * ((B + tb - 1) / tb);
+        const int64_t cost = ((ctas + slots - 1) / slots) * (tb + 4);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tb; }
+    }
+    return best;
+}
+
+template <int D4, bool kAliased>
+int gyro_fwd_launch_a(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B, int64_t D,
+                      int64_t P, const GyroParams& prm, cudaStream_t s) {
+    constexpr uint32_t kLayerFlags = kAliased ? HVAE_GYRO_SIGNED : (HVAE_GYRO_PVAE | HVAE_GYRO_SIGNED);
+    auto kern = (prm.flags == kLayerFlags) ? k_gyro_fwd<D4, kAliased, (int)kLayerFlags>
+              : (!kAliased && prm.flags == (kLayerFlags | HVAE_GYRO_RELU)) ? k_gyro_fwd<D4, kAliased, (int)(kLayerFlags | HVAE_GYRO_RELU)>
+                                                                           : k_gyro_fwd<D4, kAliased, -1>;
+    auto smem_for = [](int tb) { return sizeof(float) * ((size_t)tb * D4 + tb + (size_t)D4 * kGyroThreads * (kAliased ? 1 : 2)); };
+    if (smem_for(128) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(128));
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGyroThreads, smem_for(32)) != cudaSuccess || occ < 1) occ = 4;
+    const int tb = gyro_fwd_rows_per_cta(B, P, occ);
+    dim3 grid((unsigned)((P + kGyroThreads - 1) / kGyroThreads), (unsigned)((B + tb - 1) / tb));
+    kern<<<grid, kGyroThreads, smem_for(tb), s>>>(x, p, a, bias, out, (int)B, (int)D, (int)P, tb, prm);
     return check_launch();
 }
 
 template <int D4>
 int gyro_fwd_launch(const float* x, const float* p, const float* a, const float* bias, float* out, int64_t B, int64_t D,
                     int64_t P, const GyroParams& prm, cudaStream_t s) {
-    const bool aliased = (a == p);
-    // rows per CTA: 64 when that already gives >= 4 waves of CTAs, else 16 (the epilogue is a long dependent
-    // chain of div/sqrt/log: small problems need many resident warps, not big tiles)
-    const int64_t ctas64 = ((P + kGyroThreads - 1) / kGyroThreads) * ((B + 63) / 64);
-    const bool big = ctas64 >= 4 * (int64_t)kNumSMs * 4;
-    if (aliased) return big ? gyro_fwd_launch_tb<D4, true, 64>(x, p, a, bias, out, B, D, P, prm, s)
-                            : gyro_fwd_launch_tb<D4, true, 16>(x, p, a, bias, out, B, D, P, prm, s);
-    return big ? gyro_fwd_launch_tb<D4, false, 64>(x, p, a, bias, out, B, D, P, prm, s)
-               : gyro_fwd_launch_tb<D4, false, 16>(x, p, a, bias, out, B, D, P, prm, s);
+    if (a == p) return gyro_fwd_launch_a<D4, true>(x, p, a, bias, out, B, D, P, prm, s);
+    return gyro_fwd_launch_a<D4, false>(x, p, a, bias, out, B, D, P, prm, s);
 }
 
 template <int D4>
-int gyro_bwd_launch(const float* x, const float* p, const float* a, const float* gout, float* gx, float* gp, float* ga,
+int gyro_bwd_launch(const float* x, const float* p, const float* a, const float* bias, const float* gout, float* gx, float* gp, float* ga,
                     float* gbias, int64_t B, int64_t D, int64_t P, const GyroParams& prm, float* ws, cudaStream_t s) {
     const bool aliased = (a == p);
     const GyroWs L = gyro_ws_layout(B, D, P);
     float *CP = ws + L.cp, *CA = ws + L.ca, *wsum = ws + L.wsum, *wx = ws + L.wx, *wp = ws + L.wp, *wa = ws + L.wa,
           *wb = ws + L.wb;
-    const int chunks = gyro_x_chunks(B, P);
-    const int ppc = (int)((((P + chunks - 1) / chunks) + kGyroChunkGran - 1) / kGyroChunkGran * kGyroChunkGran);
-    const int nch = (int)((P + ppc - 1) / ppc);
+    int ppc, nch;
+    gyro_x_plan(B, P, D, &ppc, &nch);
     float* dst = nch == 1 ? gx : wx;
     {
         dim3 grid((unsigned)((B + kGyroBxThreads - 1) / kGyroBxThreads), (unsigned)nch);
-        if (aliased) k_gyro_bwd_pairs<D4, true><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, CP, CA, wsum, (int)B, (int)D, (int)P, ppc, prm);
-        else         k_gyro_bwd_pairs<D4, false><<<grid, kGyroBxThreads, 0, s>>>(x, p, a, gout, dst, CP, CA, wsum, (int)B, (int)D, (int)P, ppc, prm);
-        if (nch > 1) k_gyro_reduce_slabs<<<(unsigned)((B * D + 255) / 256), 256, 0, s>>>(wx, gx, B * D, nch);
+        constexpr uint32_t kGeo = HVAE_GYRO_PVAE | HVAE_GYRO_SIGNED;
+        auto kern = aliased ? (prm.flags == HVAE_GYRO_SIGNED ? k_gyro_bwd_pairs<D4, true, (int)HVAE_GYRO_SIGNED> : k_gyro_bwd_pairs<D4, true, -1>)
+                            : (prm.flags == kGeo ? k_gyro_bwd_pairs<D4, false, (int)kGeo>
+                               : prm.flags == (kGeo | HVAE_GYRO_RELU) ? k_gyro_bwd_pairs<D4, false, (int)(kGeo | HVAE_GYRO_RELU)>
+                                                                      : k_gyro_bwd_pairs<D4, false, -1>);
+        kern<<<grid, kGyroBxThreads, 0, s>>>(x, p, a, bias, gout, dst, CP, CA, wsum, (int)B, (int)D, (int)P, ppc, prm);
     }
+    GyroReduceArgs ra;
+    int nseg = 0;
+    int64_t nmax = 0;
+    auto add_seg = [&](const float* w, float* out, int64_t n, int slabs) {
+        ra.seg[nseg].w = w; ra.seg[nseg].out = out; ra.seg[nseg].n = n; ra.seg[nseg].slabs = slabs;
+        ++nseg;
+        if (n > nmax) nmax = n;
+    };
+    if (nch > 1) add_seg(wx, gx, B * D, nch);
     if (gp || ga || gbias) {
         const int slabs = gyro_slabs(B, P);
         const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBpSlabGran - 1) / kGyroBpSlabGran * kGyroBpSlabGran);
@@ -436,9 +545,14 @@ int gyro_bwd_launch(const float* x, const float* p, const float* a, const float*
         if (aliased) k_gyro_bwd_planes<D4, true><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);
         else         k_gyro_bwd_planes<D4, false><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);
         const int64_t n = P * D;
-        if (gp) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wp, gp, n, nsl);
-        if (ga && !aliased) k_gyro_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wa, ga, n, nsl);
-        if (gbias) k_gyro_reduce_slabs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(wb, gbias, P, nsl);
+        if (gp) add_seg(wp, gp, n, nsl);
+        if (ga && !aliased) add_seg(wa, ga, n, nsl);
+        if (gbias) add_seg(wb, gbias, P, nsl);
+    }
+    if (nseg > 0) {
+        const int64_t bx = (nmax + 31) / 32;
+        dim3 grid((unsigned)(bx < 8 * kNumSMs ? bx : 8 * kNumSMs), (unsigned)nseg);
+        k_gyro_reduce_all<<<grid, 256, 0, s>>>(ra);
     }
     return check_launch();
 }
@@ -469,9 +583,9 @@ extern "C" size_t hvae_gyroplane_bwd_workspace_bytes(int64_t B, int64_t D, int64
     return sizeof(float) * gyro_ws_layout(B, D, P).total;
 }
 
-extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout, float* gx,
-                                      float* gp, float* ga, float* gbias, int64_t B, int64_t D, int64_t P, float c,
-                                      uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int hvae_gyroplane_relu_bwd_f32(const float* x, const float* p, const float* a, const float* bias, const float* gout,
+                                           float* gx, float* gp, float* ga, float* gbias, int64_t B, int64_t D, int64_t P,
+                                           float c, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
     if (B < 0 || P < 0 || D <= 0 || D > kGyroMaxD) return HVAE_ESHAPE;
     if (B == 0 || P == 0) return HVAE_OK;
     if (!x || !p || !a || !gout) return HVAE_EARG;
@@ -481,10 +595,16 @@ extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const floa
     const GyroParams prm = make_gyro_params(c, flags);
     cudaStream_t s = (cudaStream_t)stream;
     float* ws = (float*)workspace;
-    if (D <= 4) return gyro_bwd_launch<4>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
-    if (D <= 8) return gyro_bwd_launch<8>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
-    if (D <= 12) return gyro_bwd_launch<12>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
-    if (D <= 16) return gyro_bwd_launch<16>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
-    if (D <= 32) return gyro_bwd_launch<32>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
-    return gyro_bwd_launch<64>(x, p, a, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 4) return gyro_bwd_launch<4>(x, p, a, bias, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 8) return gyro_bwd_launch<8>(x, p, a, bias, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 12) return gyro_bwd_launch<12>(x, p, a, bias, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 16) return gyro_bwd_launch<16>(x, p, a, bias, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    if (D <= 32) return gyro_bwd_launch<32>(x, p, a, bias, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+    return gyro_bwd_launch<64>(x, p, a, bias, gout, gx, gp, ga, gbias, B, D, P, prm, ws, s);
+}
+
+extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout, float* gx,
+                                      float* gp, float* ga, float* gbias, int64_t B, int64_t D, int64_t P, float c,
+                                      uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+    return hvae_gyroplane_relu_bwd_f32(x, p, a, nullptr, gout, gx, gp, ga, gbias, B, D, P, c, flags, workspace, workspace_bytes, stream);
 }

@@ -68,7 +68,9 @@ class HyperbolicRadius(torch.distributions.Distribution):
         self.c_value = float(c) if not torch.is_tensor(c) else float(c)
         self.scale = scale
         self.device = scale.device
-        self.log_normalizer = ops.hradius_lognorm(scale, self.dim, self.c_value)
+        # (logZ, dlogZ/dsigma) from one kernel; the derivative is also what the fused head's backward consumes
+        lz, dlz = ops.hradius_lognorm_fwd(ops._c(scale).view(-1), self.dim, self.c_value)
+        self.log_normalizer, self._dlogz = lz.view(scale.shape), dlz
         super().__init__(self.scale.size(), validate_args=False)
 
     philox_counter: Tensor = None  # optional override of the per-device noise counter (ops.philox_counter)
@@ -138,6 +140,27 @@ class RiemannianNormal(torch.distributions.Distribution):
             return ops.expmap_polar(self.loc, alpha.reshape(self.loc.shape), radius.reshape(*self.loc.shape[:-1], 1),
                                     self.manifold.c_value)
         return ops.expmap_polar(self.loc, alpha, radius, self.manifold.c_value)
+
+    def rsample_kl(self, prior: "RiemannianNormal", alpha: Tensor = None, r: Tensor = None):
+        """One sample z (1, B, D) and its Monte-Carlo KL term log q(z) - log p(z) (1, B) against an origin-centred prior
+        with scalar sigma - rsample() followed by kl_mc(), as ONE kernel per direction (ops.rn_head): the backward
+        delivers the total gradients of loc and scale (KL terms, the sample's path through expmap_polar, the implicit
+        reparameterisation dr/dsigma and the normaliser's dlogZ/dsigma) without any autograd glue kernels."""
+        B, D = self.loc.shape[-2], self.loc.shape[-1]
+        c = self.manifold.c_value
+        mu = ops._c(self.loc).view(B, D)
+        sig = ops._c(self.scale).view(B)
+        if alpha is None:
+            alpha = self.direction.sample(torch.Size([1, B]))
+        if r is None:
+            r = self.radius.sample(torch.Size([1]))
+        alpha = ops._c(alpha.detach()).view(B, D)
+        r = ops._c(r.detach()).view(1, B)
+        dr = ops.hradius_rgrad(r, sig.detach(), D, c)
+        z, kl = ops.rn_head_fwd(mu, sig, self.radius.log_normalizer.detach().view(B), self.radius._dlogz.detach().view(B), alpha,
+                                r.view(B), dr.view(B), ops._c(prior.scale).detach().view(1),
+                                ops._c(prior.radius.log_normalizer).detach().view(1), c)
+        return z.view(1, B, D), kl.view(1, B)
 
     def kl_mc(self, z: Tensor, prior: "RiemannianNormal") -> Tensor:
         """Monte-Carlo KL term log q(z) - log p(z) for z (S, B, D), q = self with per-row sigma (B,1) and an

@@ -82,10 +82,11 @@ class GeodesicLayer(RiemannianLayer):
     def __init__(self, in_features, out_features, manifold, over_param=False, weight_norm=False):
         super().__init__(in_features, out_features, manifold, over_param, weight_norm)
 
-    def forward(self, input: Tensor) -> Tensor:
+    def forward(self, input: Tensor, relu: bool = False) -> Tensor:
+        """relu=True (not in the reference's signature): return relu(layer(input)) with the activation fused into the kernels."""
         bpt, w = self._prep()
         flags = ops.GYRO_PVAE | ops.GYRO_SIGNED | (ops.GYRO_SCALED if self.weight_norm else 0)
-        return ops.gyroplane(input, w, bpt, None, self.manifold.c_value, flags)
+        return ops.gyroplane(input, w, bpt, None, self.manifold.c_value, flags, relu=relu)
 
 
 GyroplaneLayer = GeodesicLayer  # the name BASELINE.json uses; a commented-out stub in the reference (layers.py:16-32)

@@ -318,6 +318,8 @@ class PvaeMnist(nn.Module):
         return mu, F.softplus(h) + 1e-5
 
     def decode(self, z):
+        if self.fused and z.is_cuda:
+            return self.fc31(self.dec0(z, relu=True))   # the ReLU runs inside the gyroplane kernels
         return self.fc31(F.relu(self.dec0(z)))
 
     def loss(self, x, alpha=None, r=None):
@@ -326,12 +328,17 @@ class PvaeMnist(nn.Module):
         B = x.shape[0]
         mu, sigma = self.encode(x, clamp_sigma=self.fused)
         q = RiemannianNormal(mu, sigma, self.manifold, scale_is_clamped=self.fused and sigma.is_cuda)
-        zs = q.rsample(torch.Size([1]), alpha=alpha, r=r)  # (1,B,D)
-        logits = self.decode(zs)
         p = self._prior()
+        head = self.fused and mu.is_cuda and not (p.scale.requires_grad or p.loc.requires_grad)
+        if head:
+            zs, kld = q.rsample_kl(p, alpha=alpha, r=r)   # sample + both log-densities: one kernel per direction
+        else:
+            zs = q.rsample(torch.Size([1]), alpha=alpha, r=r)  # (1,B,D)
+        logits = self.decode(zs)
         if self.fused:
             nll = ops.bernoulli_nll_rows(logits, x.view(B, -1))  # one row kernel per direction
-            kld = q.kl_mc(zs, p)  # one kernel: both log-densities and their difference
+            if not head:
+                kld = q.kl_mc(zs, p)  # one kernel: both log-densities and their difference
             total, recon, kl = ops.pvae_loss(nll, kld, self.beta)   # the three scalars in one launch (double accumulation)
             return dict(loss_total=total, recon_loss=recon, kl_loss=kl)
         lpx_z = -F.binary_cross_entropy_with_logits(logits, x.view(1, B, -1).expand_as(logits), reduction="none").sum(-1)

@@ -381,6 +381,7 @@ def latent_head(mu: Tensor, sigma: Tensor, eps: Tensor, prior_scale: float, c: f
 # flags shared with include/hvae_b200.h
 # ---------------------------------------------------------------------------------------------------
 GYRO_SIGNED, GYRO_SQUARED, GYRO_SCALED, GYRO_PVAE = 1, 2, 4, 8
+GYRO_RELU = 16   # SIMT kernels only: the ReLU that follows the layer, fused (forward clamp, backward mask by the recomputed sign)
 
 
 def log_sinhc(x: Tensor) -> Tensor:
@@ -429,9 +430,10 @@ def _(x, p, a, bias, c, flags):
 
 
 @_op("hvae::gyroplane_bwd", mutates_args=())
-def gyroplane_bwd(x: Tensor, p: Tensor, a: Optional[Tensor], g: Tensor, c: float, flags: int,
+def gyroplane_bwd(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], g: Tensor, c: float, flags: int,
                   need_bias: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    C.require_cuda(x, p, a, g)
+    """bias: the forward's bias, read only with GYRO_RELU (the mask is the sign of the recomputed out + bias)."""
+    C.require_cuda(x, p, a, g, bias)
     B, D = x.shape
     P = p.shape[0]
     gx, gp = torch.empty_like(x), torch.empty_like(p)
@@ -439,28 +441,30 @@ def gyroplane_bwd(x: Tensor, p: Tensor, a: Optional[Tensor], g: Tensor, c: float
     gb = x.new_empty(P) if need_bias else x.new_empty(0)
     nbytes = C.lib().hvae_gyroplane_bwd_workspace_bytes(B, D, P)
     ws = _workspace(nbytes, x.device)
-    C.call("hvae_gyroplane_bwd_f32", C.ptr(x), C.ptr(p), C.ptr(p if a is None else a), C.ptr(g), C.ptr(gx), C.ptr(gp),
+    C.call("hvae_gyroplane_relu_bwd_f32", C.ptr(x), C.ptr(p), C.ptr(p if a is None else a), C.ptr(bias), C.ptr(g), C.ptr(gx), C.ptr(gp),
            C.ptr(ga) if a is not None else None, C.ptr(gb) if need_bias else None, B, D, P, c, flags, C.ptr(ws),
            ws.numel(), C.stream())
-    C.launch_count += 2 + (1 if a is not None else 0) + (1 if need_bias else 0)
+    C.launch_count += 3   # pair kernel, plane kernel, one slab reduction for gx / gp / ga / gbias
     return gx, gp, ga, gb
 
 
 @gyroplane_bwd.register_fake
-def _(x, p, a, g, c, flags, need_bias):
+def _(x, p, a, bias, g, c, flags, need_bias):
     return (torch.empty_like(x), torch.empty_like(p), torch.empty_like(a) if a is not None else x.new_empty(0),
             x.new_empty(p.shape[0]) if need_bias else x.new_empty(0))
 
 
 def _gy_setup(ctx, inputs, output):
     x, p, a, bias, c, flags = inputs
-    ctx.save_for_backward(x, p, a if a is not None else p)
+    relu_bias = bias is not None and bool(flags & GYRO_RELU)
+    ctx.save_for_backward(x, p, a if a is not None else p, *([bias] if relu_bias else []))
     ctx.has_a, ctx.has_bias, ctx.c, ctx.flags = a is not None, bias is not None, c, flags
 
 
 def _gy_backward(ctx, g):
-    x, p, a = ctx.saved_tensors
-    gx, gp, ga, gb = gyroplane_bwd(x, p, a if ctx.has_a else None, _c(g), ctx.c, ctx.flags, ctx.has_bias)
+    x, p, a = ctx.saved_tensors[:3]
+    bias = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
+    gx, gp, ga, gb = gyroplane_bwd(x, p, a if ctx.has_a else None, bias, _c(g), ctx.c, ctx.flags, ctx.has_bias)
     return gx, gp, (ga if ctx.has_a else None), (gb if ctx.has_bias else None), None, None
 
 
@@ -526,8 +530,9 @@ gyroplane_tc32_fwd.register_autograd(_gytc32_backward, setup_context=_gytc32_set
 GYRO_SIMT_MAX_D = 64   # the SIMT kernels (csrc/gyroplane.cu) keep a row of x in registers
 
 
-def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], c: float, flags: int) -> Tensor:
+def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor], c: float, flags: int, relu: bool = False) -> Tensor:
     """Signed hyperplane distances of every row of x (..., D) to every plane -> (..., P).
+    relu=True applies the ReLU that follows the layer: inside the SIMT kernels (GYRO_RELU), as a torch op on the other paths.
     bf16 GEMM mode: the fused tcgen05 kernels (a == p forward + backward; a != p forward under no_grad).  fp32 mode: the
     SIMT kernels up to D = 64, beyond that - and for the a != p backward at any GEMM-sized D - the fp32-accurate
     tensor-core path (split-operand GEMMs + the elementwise pair function)."""
@@ -542,7 +547,10 @@ def gyroplane(x: Tensor, p: Tensor, a: Optional[Tensor], bias: Optional[Tensor],
     elif xr.shape[1] > GYRO_SIMT_MAX_D:
         out = gyroplane_tc32_fwd(xr, _c(p), a_arg, b_arg, c, int(flags))
     else:
-        out = gyroplane_fwd(xr, _c(p), a_arg, b_arg, c, int(flags))
+        out = gyroplane_fwd(xr, _c(p), a_arg, b_arg, c, int(flags) | (GYRO_RELU if relu else 0))
+        relu = False
+    if relu:
+        out = torch.relu(out)
     return out.view(*lead, p.shape[0])
 
 
@@ -1115,7 +1123,7 @@ def _gtc_backward(ctx, g):
         return gx, gp, gb, None, None
     if D > 64:
         raise NotImplementedError("gyroplane backward for D > 64 needs B, D, P to be multiples of 8 (tensor-core path)")
-    gx, gp, _, gb = gyroplane_bwd(x, p, None, g, ctx.c, ctx.flags, ctx.has_bias)
+    gx, gp, _, gb = gyroplane_bwd(x, p, None, None, g, ctx.c, ctx.flags, ctx.has_bias)
     return gx, gp, (gb if ctx.has_bias else None), None, None
 
 
@@ -1169,6 +1177,70 @@ def _rk_backward(ctx, g):
 
 
 rn_kl_fwd.register_autograd(_rk_backward, setup_context=_rk_setup)
+
+
+# ---- the RiemannianNormal head fused with the sample (S = 1): csrc/riemannian_kl.cu k_rn_head_{fwd,bwd} ----
+@_op("hvae::rn_head", mutates_args=())
+def rn_head_fwd(mu: Tensor, sigma_q: Tensor, logz_q: Tensor, dlogz: Tensor, alpha: Tensor, r: Tensor, dr: Tensor,
+                sigma_p: Tensor, logz_p: Tensor, c: float) -> Tuple[Tensor, Tensor]:
+    """z = expmap_polar(mu, alpha, r) (B,D) and kl = log q(z) - log p(z) (B,) in one kernel.  sigma_q, logz_q, dlogz
+    (= dlogZ/dsigma), r, dr (= dr/dsigma, implicit reparameterisation): (B,); sigma_p, logz_p: device scalars.  Only mu
+    and sigma_q are differentiable inputs: the backward returns their TOTAL gradients (KL + sample path + normaliser)."""
+    C.require_cuda(mu, sigma_q, logz_q, dlogz, alpha, r, dr, sigma_p, logz_p)
+    B, D = mu.shape
+    z, kl = torch.empty_like(mu), mu.new_empty(B)
+    C.call("hvae_rn_head_fwd_f32", C.ptr(mu), C.ptr(alpha), C.ptr(r), C.ptr(sigma_q), C.ptr(logz_q), C.ptr(sigma_p), C.ptr(logz_p),
+           C.ptr(z), C.ptr(kl), B, D, c, C.stream())
+    return z, kl
+
+
+@rn_head_fwd.register_fake
+def _(mu, sigma_q, logz_q, dlogz, alpha, r, dr, sigma_p, logz_p, c):
+    return torch.empty_like(mu), mu.new_empty(mu.shape[0])
+
+
+@_op("hvae::rn_head_bwd", mutates_args=())
+def rn_head_bwd(mu: Tensor, sigma_q: Tensor, dlogz: Tensor, alpha: Tensor, r: Tensor, dr: Tensor, sigma_p: Tensor, z: Tensor,
+                gz: Optional[Tensor], gkl: Optional[Tensor], c: float) -> Tuple[Tensor, Tensor]:
+    C.require_cuda(mu, sigma_q, dlogz, alpha, r, dr, sigma_p, z, gz, gkl)
+    B, D = mu.shape
+    gmu, gs = torch.empty_like(mu), torch.empty_like(sigma_q)
+    C.call("hvae_rn_head_bwd_f32", C.ptr(mu), C.ptr(alpha), C.ptr(r), C.ptr(sigma_q), C.ptr(sigma_p), C.ptr(z), C.ptr(dr), C.ptr(dlogz),
+           C.ptr(gz), C.ptr(gkl), C.ptr(gmu), C.ptr(gs), B, D, c, C.stream())
+    return gmu, gs
+
+
+@rn_head_bwd.register_fake
+def _(mu, sigma_q, dlogz, alpha, r, dr, sigma_p, z, gz, gkl, c):
+    return torch.empty_like(mu), torch.empty_like(sigma_q)
+
+
+def _rnh_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    mu, sigma_q, logz_q, dlogz, alpha, r, dr, sigma_p, logz_p, c = inputs
+    ctx.save_for_backward(mu, sigma_q, dlogz, alpha, r, dr, sigma_p, output[0])
+    ctx.c = c
+
+
+def _rnh_backward(ctx, gz, gkl):
+    if gz is None and gkl is None:
+        return (None,) * 10
+    mu, sigma_q, dlogz, alpha, r, dr, sigma_p, z = ctx.saved_tensors
+    gmu, gs = rn_head_bwd(mu, sigma_q, dlogz, alpha, r, dr, sigma_p, z, None if gz is None else _c(gz),
+                          None if gkl is None else _c(gkl), ctx.c)
+    return gmu, gs, None, None, None, None, None, None, None, None
+
+
+rn_head_fwd.register_autograd(_rnh_backward, setup_context=_rnh_setup)
+
+
+def hradius_rgrad(r: Tensor, sigma: Tensor, dim: int, c: float) -> Tensor:
+    """dr/dsigma of the implicit reparameterisation for given radii r (S,B), sigma (B,) (no autograd)."""
+    C.require_cuda(r, sigma)
+    S, B = r.shape
+    dr = torch.empty_like(r)
+    C.call("hvae_hradius_rgrad_f32", C.ptr(sigma), C.ptr(r), C.ptr(dr), None, S, B, dim, c, C.stream())
+    return dr
 
 
 # ---------------------------------------------------------------------------------------------------

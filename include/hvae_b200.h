@@ -41,6 +41,8 @@ extern "C" {
 #define HVAE_GYRO_SQUARED 2u  /* d^2 (times sign(d) if signed)       layers.py:203-207        */
 #define HVAE_GYRO_SCALED 4u   /* multiply by ||a||  (geoopt `scaled`, pvae `norm`)            */
 #define HVAE_GYRO_PVAE 8u     /* normdist2plane clamps + projected (-p)(+)x  manifolds.py:41-65 */
+#define HVAE_GYRO_RELU 16u    /* SIMT path only: out = max(out + bias, 0) - the ReLU that follows the decoder's gyroplane
+                                 layer (scripts/_9_pvae_replicate.py Dec: relu(GeodesicLayer(z))) fused into the kernel */
 
 int hvae_version(void);
 const char* hvae_strerror(int code);
@@ -103,11 +105,17 @@ int hvae_latent_head_bwd_f32(const float* mu, const float* sigma, const float* e
 int hvae_gyroplane_fwd_f32(const float* x, const float* p, const float* a, const float* bias, float* out,
                            int64_t B, int64_t D, int64_t P, float c, uint32_t flags, void* stream);
 size_t hvae_gyroplane_bwd_workspace_bytes(int64_t B, int64_t D, int64_t P);
-/* gp/ga: (P,D) (ga may be NULL when a aliases p: its gradient is added into gp); gbias: (P,) or NULL */
+/* gp/ga: (P,D) (ga may be NULL when a aliases p: its gradient is added into gp); gbias: (P,) or NULL.
+ * With HVAE_GYRO_RELU in flags, gout is the gradient of the ACTIVATED output: the backward recomputes the pre-activation
+ * sign and masks it; use hvae_gyroplane_relu_bwd_f32 to pass the forward's bias (the plain entry assumes bias = NULL). */
 int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const float* gout,
                            float* gx, float* gp, float* ga, float* gbias,
                            int64_t B, int64_t D, int64_t P, float c, uint32_t flags,
                            void* workspace, size_t workspace_bytes, void* stream);
+int hvae_gyroplane_relu_bwd_f32(const float* x, const float* p, const float* a, const float* bias, const float* gout,
+                                float* gx, float* gp, float* ga, float* gbias,
+                                int64_t B, int64_t D, int64_t P, float c, uint32_t flags,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K1b: Riemannian layer weight prep  (layers.py:58-67) ------------------------------------------------
  * W: (P,F) `_weight`; beta: (P,) `_bias` (over_param=False) -> bpt = expmap0(W*beta) (P,F),
@@ -158,6 +166,19 @@ int hvae_rn_kl_fwd_f32(const float* mu, const float* sigma_q, const float* logz_
 int hvae_rn_kl_bwd_f32(const float* mu, const float* sigma_q, const float* z, const float* sigma_p, const float* gkl,
                        float* gmu, float* gsigma_q, float* glogz_q, float* gz, int64_t S, int64_t B, int64_t D,
                        float c, void* stream);
+
+/* ---- the same head fused with the sample (S = 1): z = expmap_polar(mu, alpha, r) and kl in ONE kernel; the backward
+ * takes the decoder's gradient of z (B,D; may be NULL) and of kl (B,; may be NULL) and returns the TOTAL gradients of mu
+ * and sigma_q: KL terms + the sample's path through expmap_polar + g_r * dr/dsigma (implicit reparameterisation,
+ * dr_dsigma from hvae_hradius_rgrad_f32) - gkl * dlogZ/dsigma (dlogz_dsigma from hvae_hradius_lognorm_fwd_f32).
+ * Replaces old_pvae_riemannian_normal.py:12-52 rsample + 2x log_prob and their ~10 autograd kernels. */
+int hvae_rn_head_fwd_f32(const float* mu, const float* alpha, const float* r, const float* sigma_q,
+                         const float* logz_q, const float* sigma_p, const float* logz_p, float* z, float* kl,
+                         int64_t B, int64_t D, float c, void* stream);
+int hvae_rn_head_bwd_f32(const float* mu, const float* alpha, const float* r, const float* sigma_q,
+                         const float* sigma_p, const float* z, const float* dr_dsigma, const float* dlogz_dsigma,
+                         const float* gz, const float* gkl, float* gmu, float* gsigma, int64_t B, int64_t D,
+                         float c, void* stream);
 
 /* ---- K1-TC / K2-TC: tcgen05 (bf16 operands, fp32 accumulate) forward paths for GEMM-sized shapes --------------
  * Same math as hvae_mobius_matvec_fwd_f32 / hvae_gyroplane_fwd_f32 (a == p), operands rounded to bf16: the

@@ -19,6 +19,6 @@ FL = ops.GYRO_PVAE | ops.GYRO_SIGNED
 for _ in range(3):
     out = ops.gyroplane_fwd(z, Mg, bpt, None, c, FL)
     gout = torch.randn_like(out)
-    r = ops.gyroplane_bwd(z, Mg, bpt, gout, c, FL, False)
+    r = ops.gyroplane_bwd(z, Mg, bpt, None, gout, c, FL, False)
 torch.cuda.synchronize()
 print("ok", float(out.abs().mean()))

@@ -137,6 +137,66 @@ def test_riemannian_normal_injected_noise(D, c):
     assert_parity(sg.grad, o32[3], o64[3], what="RN gsigma", rtol=rtol_grad(kap, 5e-5), atol=2e-5, row_relative=False, slack_mult=2.0)
 
 
+@pytest.mark.parametrize("D,c,B", [(2, 1.0, 200), (5, 0.5, 129), (10, 1.0, 4096)])
+def test_riemannian_head_fused_sample_and_kl(D, c, B):
+    """RiemannianNormal.rsample_kl (ops.rn_head: one kernel per direction) against (a) the oracle's rsample +
+    log_prob(q) - log_prob(p) with injected (alpha, r) in float32 / float64 and (b) this repo's unfused graph
+    (rsample + kl_mc + autograd's adds), which runs the same row arithmetic."""
+    import hvae
+    from hvae.distributions import RiemannianNormal
+    from oracle import ref_port as R
+    from oracle.geoopt_min.manifolds.stereographic import math as gmath
+
+    torch.manual_seed(D + B)
+    ob32 = _oracle_pball(D, c, torch.float32)
+    mu0 = ob32.expmap0(torch.randn(B, D) * 0.6 / D ** 0.5).detach()
+    sg0 = torch.rand(B, 1) * 1.5 + 0.3
+    sp0 = torch.tensor([[1.3]])
+    alpha = torch.randn(1, B, D)
+    alpha = alpha / alpha.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        r0 = R.RiemannianNormal(mu0, sg0, ob32).radius.sample(torch.Size([1]))
+    gz, gkl = torch.randn(1, B, D), torch.randn(1, B)
+
+    def oracle(dtype):
+        ball = _oracle_pball(D, c, dtype)
+        mu = mu0.clone().to(dtype).requires_grad_(True)
+        sg = sg0.clone().to(dtype).requires_grad_(True)
+        with gmath.fp32_semantics(dtype == torch.float64):
+            q = R.RiemannianNormal(mu, sg, ball)
+            p = R.RiemannianNormal(torch.zeros(1, D, dtype=dtype), sp0.to(dtype), ball)
+            z = q.rsample(torch.Size([1]), alpha=alpha.to(dtype), r=r0.to(dtype))
+            kl = q.log_prob(z).sum(-1) - p.log_prob(z).sum(-1)
+            ((z * gz.to(dtype)).sum() + (kl * gkl.to(dtype)).sum()).backward()
+        return z.detach(), kl.detach(), mu.grad, sg.grad
+
+    def ours(fused):
+        ball = hvae.PoincareBall(c)
+        mu = mu0.cuda().requires_grad_(True)
+        sg = sg0.cuda().requires_grad_(True)
+        q = RiemannianNormal(mu, sg, ball)
+        p = RiemannianNormal(torch.zeros(1, D, device="cuda"), sp0.cuda(), ball)
+        if fused:
+            z, kl = q.rsample_kl(p, alpha=alpha.cuda(), r=r0.cuda())
+        else:
+            z = q.rsample(torch.Size([1]), alpha=alpha.cuda(), r=r0.cuda())
+            kl = q.kl_mc(z, p)
+        ((z * gz.cuda()).sum() + (kl * gkl.cuda()).sum()).backward()
+        return z.detach(), kl.detach(), mu.grad, sg.grad
+
+    fu, un = ours(True), ours(False)
+    for name, a_, b_ in zip(("z", "kl", "gmu", "gsigma"), fu, un):
+        sc = float(b_.abs().max())
+        assert float((a_ - b_).abs().max()) <= 2e-6 * sc, (name, float((a_ - b_).abs().max()), sc)
+    if B <= 512:   # the oracle's ARS and float64 series are slow; the big case is covered by the config-2 step test
+        o32, o64 = oracle(torch.float32), oracle(torch.float64)
+        kap = kappa(c, o64[0], mu0)
+        assert_parity(fu[0], o32[0], o64[0], what="RN head z", rtol=rtol_val(kap, 2e-5).view(1, -1, 1), atol=2e-6)
+        assert_parity(fu[1], o32[1], o64[1], what="RN head kl", rtol=rtol_val(kap, 2e-5).view(1, -1), atol=2e-5, row_relative=False, slack_mult=2.0)
+        assert_parity(fu[2], o32[2], o64[2], what="RN head gmu", rtol=rtol_grad(kap, 5e-5), atol=2e-5, slack_mult=2.0)
+        assert_parity(fu[3], o32[3], o64[3], what="RN head gsigma", rtol=rtol_grad(kap, 5e-5), atol=2e-5, row_relative=False, slack_mult=2.0)
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_pvae_mnist_step_matches_oracle(fused):
     """Config 2 at reduced width: same weights, same data, same injected (alpha, r)."""

@@ -152,6 +152,80 @@ def test_gyroplane_seeded(kind, D, P, B):
     _check("%s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64, pk=pk, squared=(kind == "squared"), fk=fk)
 
 
+@pytest.mark.parametrize("kind", ["geodesic", "geodesic_wn"])
+@pytest.mark.parametrize("D,P,B", [(2, 40, 200), (10, 600, 260), (16, 130, 129)])
+def test_geodesic_projected_pairs(kind, D, P, B):
+    """pvae's mobius_add projects (-p)(+)x back into the ball: for latent points far out (a 10-d RiemannianNormal puts
+    nearly all of its mass beyond the fp32 projection radius) that is the COMMON case - the lean projected branch of the
+    SIMT kernels (y = K_j N1 / sqrt(N2)).  Rows: a third far out, a third at moderate radius, a third near the origin."""
+    c = 1.0 if D != 16 else 0.7
+    torch.manual_seed(D * 77 + P)
+    layer, make_o, names = _gyro_layers(kind, D, P, c)
+    ob = _oball(c)
+    scale = torch.ones(B, 1)
+    scale[: B // 3] = 6.0
+    scale[B // 3: 2 * B // 3] = 1.5
+    scale[2 * B // 3:] = 0.2
+    x = ob.expmap0(torch.randn(B, D) / D ** 0.5 * scale).detach()
+    params = {k: getattr(layer, k).detach().clone() for k in names}
+    gout = torch.randn(B, P)
+    cu = _cuda_layer_run(layer, params, x, gout)
+    o32 = _oracle_layer_run(make_o, params, x, gout, torch.float32)
+    o64 = _oracle_layer_run(make_o, params, x, gout, torch.float64)
+    from oracle import ref_port as R
+    lay = R.GeodesicLayer(D, P, _oball(c))
+    with torch.no_grad():
+        lay._weight.copy_(params["_weight"]); lay._bias.copy_(params["_bias"])
+        pk = pair_kappa(float(_oball(c).c), x, lay.weight)
+        fk = full_kappa(float(_oball(c).c), x, lay.weight)
+    _check("projected %s D=%d P=%d B=%d" % (kind, D, P, B), cu, o32, o64, pk=pk, fk=fk)
+
+
+@pytest.mark.parametrize("kind", ["geodesic", "geodesic_wn", "bias", "squared"])
+@pytest.mark.parametrize("D,P,B", [(10, 600, 260), (3, 33, 129)])
+def test_gyroplane_fused_relu_equals_unfused(kind, D, P, B):
+    """HVAE_GYRO_RELU (the decoder's ReLU inside the SIMT kernels: forward clamp, backward mask by the sign of the
+    recomputed pre-activation) against relu() applied to the unfused kernels' output: the pair math is the same code, so
+    the two agree to rounding (1e-6 of the tensor's scale)."""
+    import hvae
+    from hvae import ops
+
+    c = 1.0
+    torch.manual_seed(D * 5 + P)
+    layer, _, names = _gyro_layers(kind, D, P, c)
+    layer = layer.cuda()
+    ob = _oball(c)
+    scale = torch.ones(B, 1)
+    scale[: B // 2] = 5.0
+    x0 = ob.expmap0(torch.randn(B, D) / D ** 0.5 * scale).detach().cuda()
+    gout = torch.randn(B, P).cuda()
+    if kind.startswith("geodesic"):
+        bpt, w = layer._prep()
+        pl, al, bias = w.detach(), bpt.detach(), None
+        flags = ops.GYRO_PVAE | ops.GYRO_SIGNED | (ops.GYRO_SCALED if kind == "geodesic_wn" else 0)
+    else:
+        pl, al, bias = layer.points.detach(), None, (layer.bias.detach() if getattr(layer, "bias", None) is not None else None)
+        flags = ops.GYRO_SIGNED | (ops.GYRO_SQUARED if kind == "squared" else 0)
+
+    def run(fused):
+        xx = x0.clone().requires_grad_(True)
+        pp = pl.clone().requires_grad_(True)
+        aa = None if al is None else al.clone().requires_grad_(True)
+        bb = None if bias is None else bias.clone().requires_grad_(True)
+        if fused:
+            out = ops.gyroplane(xx, pp, aa, bb, layer.manifold.c_value if hasattr(layer, "manifold") else layer.ball.c_value, flags, relu=True)
+        else:
+            out = torch.relu(ops.gyroplane(xx, pp, aa, bb, layer.manifold.c_value if hasattr(layer, "manifold") else layer.ball.c_value, flags))
+        out.backward(gout)
+        return [out.detach(), xx.grad, pp.grad] + ([] if aa is None else [aa.grad]) + ([] if bb is None else [bb.grad])
+
+    fu, un = run(True), run(False)
+    assert float((fu[0] > 0).float().mean()) > 0.02 and float((fu[0] == 0).float().mean()) > 0.02   # both signs occur
+    for i, (a_, b_) in enumerate(zip(fu, un)):
+        sc = float(b_.abs().max())
+        assert float((a_ - b_).abs().max()) <= 1e-6 * sc, (kind, i, float((a_ - b_).abs().max()), sc)
+
+
 def _oracle_layer_run_chunked(make_layer, params, x, gout, dtype, rows=256):
     """_oracle_layer_run in row chunks (the oracle broadcasts to (rows, D, P)); parameter gradients accumulate."""
     from oracle.geoopt_min.manifolds.stereographic import math as gmath

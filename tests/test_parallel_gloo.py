@@ -37,7 +37,7 @@ def _worker(rank, world, port, reduction, out_q):
         bucket.all_reduce_segment("early", average=False)
         bucket.all_reduce_segment("late", average=False)
         flat = torch.cat([torch.cat([p.grad.flatten(), torch.zeros((-p.numel()) % 32)]) for p in params])
-        out_q.put((rank, flat))
+        out_q.put((rank, flat.tolist()))   # plain floats: a tensor would travel as a shared-memory fd the exiting child may close first
         dist.barrier()
         dist.destroy_process_group()
         return
@@ -47,7 +47,7 @@ def _worker(rank, world, port, reduction, out_q):
         # per-shard means with unequal shard sizes: weight by the shard's share of the global batch
         bucket.buffer.mul_((hi - lo) * world / 10.0)
         bucket.all_reduce(average=True)
-    out_q.put((rank, bucket.buffer.clone()))
+    out_q.put((rank, bucket.buffer.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,7 +76,7 @@ def _run(reduction, port=None):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, reduction, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(2))
+    res = {k: torch.tensor(v) for k, v in (q.get(timeout=300) for _ in range(2))}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
