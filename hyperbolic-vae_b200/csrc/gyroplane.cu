@@ -125,7 +125,7 @@ k_gyro_fwd(const float* __restrict__ x, const float* __restrict__ p, const float
 //                            CP[b][j] = dL/d<p_j,x_b> (+ dL/d<a_j,x_b> when a aliases p),  CA[b][j] = dL/d<a_j,x_b>
 //                          and per-(row-block, plane) sums of the scalar terms (d|p|^2, d<p,a>, d|a|, g).
 //   G2  k_gyro_bwd_planes: thread = one plane; gp_j = sum_b CP[b][j] x_b + (scalar terms) — a skinny GEMM over a
-//                          slab of rows, partials per slab, then k_gyro_reduce_all (one launch for gx, gp, ga, gbias; deterministic, no atomics).
+//                          slab of rows, partials per slab, then k_reduce_slabs (one launch for gx, gp, ga, gbias; deterministic, no atomics).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kGyroBxThreads = 128;  // rows per CTA
 constexpr int kGyroBxTJ = 32;        // planes per smem stage
@@ -280,7 +280,7 @@ k_gyro_bwd_pairs(const float* __restrict__ x, const float* __restrict__ p, const
 }
 
 constexpr int kGyroBpThreads = 64;
-constexpr int kGyroBpTB = 32;  // rows per smem stage
+constexpr int kGyroBpTB = 64;  // rows per smem stage
 constexpr int kGyroBpSlabGran = 64;  // slab granularity in rows (finer than G1's 128-row blocks: more CTAs in flight)
 
 template <int D4, bool kAliased>
@@ -312,8 +312,8 @@ k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, cons
         const int bn = min(kGyroBpTB, be - b0);
         if (j < P_) {
             // the kernel is latency-bound (a few warps per SM, each load a trip to L2): issue the coefficient loads of
-            // 8 rows before the first FMA (rows past bn read as zero: they add nothing)
-            constexpr int U = 8;
+            // 16 rows before the first FMA (rows past bn read as zero: they add nothing)
+            constexpr int U = 16;
             static_assert(kGyroBpTB % U == 0, "row stage must be a multiple of the load batch");
             for (int bb = 0; bb < bn; bb += U) {
                 float cpv[U], cav[U];
@@ -371,42 +371,6 @@ k_gyro_bwd_planes(const float* __restrict__ x, const float* __restrict__ p, cons
             }
         }
         wb[(int64_t)slab * P_ + j] = sg;
-    }
-}
-
-// all slab reductions of one backward (gx over plane chunks; gp, ga, gbias over row slabs) in ONE launch:
-// blockIdx.y selects the segment
-struct GyroReduceSeg {
-    const float* w;
-    float* out;
-    int64_t n;
-    int slabs;
-};
-struct GyroReduceArgs {
-    GyroReduceSeg seg[4];
-};
-// block = 32 consecutive elements x 8 slab lanes: lane group s sums slabs s, s + 8, ... (coalesced 128-byte loads, 8
-// independent chains per element instead of one serial walk over up to 64 slabs), then a fixed-order sum of the 8 partials
-__global__ void __launch_bounds__(256) k_gyro_reduce_all(GyroReduceArgs a) {
-    __shared__ float part[8][33];
-    const GyroReduceSeg sg = a.seg[blockIdx.y];
-    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < sg.n; i0 += (int64_t)gridDim.x * 32) {
-        const int64_t i = i0 + e;
-        float s = 0.0f;
-        if (i < sg.n) {
-#pragma unroll 4
-            for (int k = sl; k < sg.slabs; k += 8) s += sg.w[(int64_t)k * sg.n + i];
-        }
-        part[sl][e] = s;
-        __syncthreads();
-        if (sl == 0 && i < sg.n) {
-            float t = part[0][e];
-#pragma unroll
-            for (int q = 1; q < 8; ++q) t += part[q][e];
-            sg.out[i] = t;
-        }
-        __syncthreads();
     }
 }
 
@@ -528,15 +492,8 @@ int gyro_bwd_launch(const float* x, const float* p, const float* a, const float*
                                                                       : k_gyro_bwd_pairs<D4, false, -1>);
         kern<<<grid, kGyroBxThreads, 0, s>>>(x, p, a, bias, gout, dst, CP, CA, wsum, (int)B, (int)D, (int)P, ppc, prm);
     }
-    GyroReduceArgs ra;
-    int nseg = 0;
-    int64_t nmax = 0;
-    auto add_seg = [&](const float* w, float* out, int64_t n, int slabs) {
-        ra.seg[nseg].w = w; ra.seg[nseg].out = out; ra.seg[nseg].n = n; ra.seg[nseg].slabs = slabs;
-        ++nseg;
-        if (n > nmax) nmax = n;
-    };
-    if (nch > 1) add_seg(wx, gx, B * D, nch);
+    SlabReducer red;   // gx over plane chunks, gp / ga / gbias over row slabs: one launch (hvae_common.cuh)
+    if (nch > 1) red.add(wx, gx, B * D, nch);
     if (gp || ga || gbias) {
         const int slabs = gyro_slabs(B, P);
         const int rows_per_slab = (int)(((B + slabs - 1) / slabs + kGyroBpSlabGran - 1) / kGyroBpSlabGran * kGyroBpSlabGran);
@@ -545,15 +502,11 @@ int gyro_bwd_launch(const float* x, const float* p, const float* a, const float*
         if (aliased) k_gyro_bwd_planes<D4, true><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);
         else         k_gyro_bwd_planes<D4, false><<<grid, kGyroBpThreads, 0, s>>>(x, p, a, CP, CA, wsum, wp, wa, wb, (int)B, (int)D, (int)P, rows_per_slab);
         const int64_t n = P * D;
-        if (gp) add_seg(wp, gp, n, nsl);
-        if (ga && !aliased) add_seg(wa, ga, n, nsl);
-        if (gbias) add_seg(wb, gbias, P, nsl);
+        if (gp) red.add(wp, gp, n, nsl);
+        if (ga && !aliased) red.add(wa, ga, n, nsl);
+        if (gbias) red.add(wb, gbias, P, nsl);
     }
-    if (nseg > 0) {
-        const int64_t bx = (nmax + 31) / 32;
-        dim3 grid((unsigned)(bx < 8 * kNumSMs ? bx : 8 * kNumSMs), (unsigned)nseg);
-        k_gyro_reduce_all<<<grid, 256, 0, s>>>(ra);
-    }
+    red.launch(s);
     return check_launch();
 }
 

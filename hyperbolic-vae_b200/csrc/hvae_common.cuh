@@ -315,4 +315,80 @@ constexpr int kMaxRowDim = 1024;
     constexpr int RPW = 32 / (G);                                             \
     const int sub = lane / (G);
 
+
+// ---------------------------------------------------------------------------------------------------
+// Deterministic slab reduction  out[i] = sum_k w[k][i]  for up to four (w, out, n, slabs) segments in ONE launch
+// (blockIdx.y = segment): the partial-sum buffers of the skinny gradient GEMMs (gyroplane gx / gp / ga / gbias, Mobius
+// gM).  A block is 32 float4 columns x 8 slab lanes: lane group s walks slabs s, s + 8, ... with up to 8 independent
+// 16-byte loads in flight per thread (coalesced 512-byte rows), then the 8 partials are summed in a fixed order.
+// (A thread per element walking all slabs serially is a chain of up to 64 dependent L2 round trips: 7-14 us for 3 MB.)
+// ---------------------------------------------------------------------------------------------------
+struct SlabSeg {
+    const float* w;
+    float* out;
+    int64_t n;
+    int slabs;
+    int vec;   // n % 4 == 0 and both pointers 16-byte aligned: float4 columns
+};
+struct SlabReduceArgs {
+    SlabSeg seg[4];
+};
+
+static __global__ void __launch_bounds__(256) k_reduce_slabs(SlabReduceArgs a) {
+    __shared__ float4 part[8][32];
+    const SlabSeg sg = a.seg[blockIdx.y];
+    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int64_t units = sg.vec ? (sg.n >> 2) : sg.n;
+    for (int64_t u0 = (int64_t)blockIdx.x * 32; u0 < units; u0 += (int64_t)gridDim.x * 32) {
+        const int64_t u = u0 + e;
+        float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (u < units) {
+            if (sg.vec) {
+                const float4* w4 = reinterpret_cast<const float4*>(sg.w);
+#pragma unroll 8
+                for (int k = sl; k < sg.slabs; k += 8) {
+                    const float4 v = __ldg(w4 + (int64_t)k * units + u);
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+            } else {
+#pragma unroll 8
+                for (int k = sl; k < sg.slabs; k += 8) s.x += __ldg(sg.w + (int64_t)k * sg.n + u);
+            }
+        }
+        part[sl][e] = s;
+        __syncthreads();
+        if (sl == 0 && u < units) {
+            float4 t = part[0][e];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                const float4 v = part[q][e];
+                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+            }
+            if (sg.vec) reinterpret_cast<float4*>(sg.out)[u] = t;
+            else sg.out[u] = t.x;
+        }
+        __syncthreads();
+    }
+}
+
+struct SlabReducer {
+    SlabReduceArgs args;
+    int nseg = 0;
+    int64_t max_units = 0;
+    void add(const float* w, float* out, int64_t n, int slabs) {
+        if (n <= 0 || nseg >= 4) return;
+        SlabSeg& g = args.seg[nseg++];
+        g.w = w; g.out = out; g.n = n; g.slabs = slabs;
+        g.vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+        const int64_t units = g.vec ? n / 4 : n;
+        if (units > max_units) max_units = units;
+    }
+    void launch(cudaStream_t s) const {
+        if (nseg == 0) return;
+        const int64_t bx = (max_units + 31) / 32;
+        dim3 grid((unsigned)(bx < 4 * kNumSMs ? bx : 4 * kNumSMs), (unsigned)nseg);
+        k_reduce_slabs<<<grid, 256, 0, s>>>(args);
+    }
+};
+
 }  // namespace hvae

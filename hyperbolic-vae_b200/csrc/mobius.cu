@@ -318,13 +318,21 @@ k_mobius_bwd_m(const float* __restrict__ x, const float* __restrict__ gmx, float
         __syncthreads();
         const int bn = (int)min((int64_t)kMobGmTB, be - b0);
         if (f < F) {
-            for (int bb = 0; bb < bn; ++bb) {
-                const float xv = __ldg(x + (b0 + bb) * F + f);
+            // latency-bound (a few warps per SM, every x load a trip to L2): 16 row loads in flight before the FMAs
+            constexpr int U = 16;
+            static_assert(kMobGmTB % U == 0, "row stage must be a multiple of the load batch");
+            for (int bb = 0; bb < bn; bb += U) {
+                float xv[U];
 #pragma unroll
-                for (int j = 0; j < PC; j += 4) {
-                    const float4 g4 = *reinterpret_cast<const float4*>(&gs[bb][j]);
-                    acc[j] = fmaf(g4.x, xv, acc[j]); acc[j + 1] = fmaf(g4.y, xv, acc[j + 1]);
-                    acc[j + 2] = fmaf(g4.z, xv, acc[j + 2]); acc[j + 3] = fmaf(g4.w, xv, acc[j + 3]);
+                for (int u = 0; u < U; ++u) xv[u] = (bb + u < bn) ? __ldg(x + (b0 + bb + u) * F + f) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int j = 0; j < PC; j += 4) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(&gs[bb + u][j]);
+                        acc[j] = fmaf(g4.x, xv[u], acc[j]); acc[j + 1] = fmaf(g4.y, xv[u], acc[j + 1]);
+                        acc[j + 2] = fmaf(g4.z, xv[u], acc[j + 2]); acc[j + 3] = fmaf(g4.w, xv[u], acc[j + 3]);
+                    }
                 }
             }
         }
@@ -334,14 +342,6 @@ k_mobius_bwd_m(const float* __restrict__ x, const float* __restrict__ gmx, float
         for (int j = 0; j < PC; ++j)
             if (j < jn) wM[((int64_t)slab * P + j0 + j) * F + f] = acc[j];
     }
-}
-
-__global__ void k_mob_reduce_slabs(const float* __restrict__ w, float* __restrict__ out, int64_t n, int slabs) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.0f;
-    for (int k = 0; k < slabs; ++k) s += w[(int64_t)k * n + i];
-    out[i] = s;
 }
 
 inline int mob_pc(int64_t P) { return P <= 8 ? 8 : (P <= 16 ? 16 : 32); }
@@ -391,8 +391,9 @@ int mob_bwd_launch(const float* x, const float* M, const float* mx, const float*
         if (pc == 8)       k_mobius_bwd_m<8><<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
         else if (pc == 16) k_mobius_bwd_m<16><<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
         else               k_mobius_bwd_m<32><<<grid, kMobGmThreads, 0, s>>>(x, gmx, wM, B, (int)F, (int)P, rows_per_slab);
-        const int64_t n = P * F;
-        k_mob_reduce_slabs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wM, gM, n, slabs);
+        SlabReducer red;   // hvae_common.cuh: slab-parallel, coalesced, fixed summation order
+        red.add(wM, gM, P * F, slabs);
+        red.launch(s);
     }
     return check_launch();
 }

@@ -415,10 +415,15 @@ __global__ void __launch_bounds__(256) k_split2h_rows(const float* __restrict__ 
 // largest magnitude (as float bits) of every row and every column of an (R, C) matrix: a block owns a 32-row x 128-column
 // tile (8 warps x 4 rows each, a lane reads 4 consecutive columns), row maxima by warp shuffle, column maxima through
 // shared memory, then one atomicMax per row / column and block (rowbits and colbits zeroed by the caller)
+// mask (optional, same shape): elements whose mask value is not > 0 count as zero (the ReLU backward of a fused
+// Linear + ReLU layer).  colpart (optional): the block's column sums of its 32 rows -> colpart[blockIdx.x][C] (the bias
+// gradient = their sum over the row blocks, hvae_common.cuh k_reduce_slabs; fixed order, no atomics).
 constexpr int kAmRows = 32, kAmCols = 128;
-__global__ void __launch_bounds__(256) k_absmax_rc(const float* __restrict__ in, uint32_t* __restrict__ rowbits,
-                                                   uint32_t* __restrict__ colbits, int64_t R, int64_t C) {
+__global__ void __launch_bounds__(256) k_absmax_rc(const float* __restrict__ in, const float* __restrict__ mask,
+                                                   uint32_t* __restrict__ rowbits, uint32_t* __restrict__ colbits,
+                                                   float* __restrict__ colpart, int64_t R, int64_t C) {
     __shared__ uint32_t cmax[8][kAmCols];
+    float csum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * kAmRows, c0 = (int64_t)blockIdx.y * kAmCols + 4 * lane;
     const bool vec = (C & 3) == 0;
@@ -431,15 +436,26 @@ __global__ void __launch_bounds__(256) k_absmax_rc(const float* __restrict__ in,
             if (vec && c0 + 4 <= C) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * C + c0));
                 b[0] = __float_as_uint(v.x); b[1] = __float_as_uint(v.y); b[2] = __float_as_uint(v.z); b[3] = __float_as_uint(v.w);
+                if (mask) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(mask + r * C + c0));
+                    if (!(m.x > 0.0f)) b[0] = 0u;
+                    if (!(m.y > 0.0f)) b[1] = 0u;
+                    if (!(m.z > 0.0f)) b[2] = 0u;
+                    if (!(m.w > 0.0f)) b[3] = 0u;
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (c0 + e < C) b[e] = __float_as_uint(__ldg(in + r * C + c0 + e));
+                    if (c0 + e < C) {
+                        b[e] = __float_as_uint(__ldg(in + r * C + c0 + e));
+                        if (mask && !(__ldg(mask + r * C + c0 + e) > 0.0f)) b[e] = 0u;
+                    }
             }
         }
         uint32_t rm = 0u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+            csum[e] += __uint_as_float(b[e]);
             b[e] &= 0x7fffffffu;
             cm[e] = max(cm[e], b[e]);
             rm = max(rm, b[e]);
@@ -448,22 +464,39 @@ __global__ void __launch_bounds__(256) k_absmax_rc(const float* __restrict__ in,
         for (int o = 16; o > 0; o >>= 1) rm = max(rm, __shfl_xor_sync(0xffffffffu, rm, o));
         if (rowbits && lane == 0 && r < R && rm) atomicMax(rowbits + r, rm);
     }
-    if (!colbits) return;
+    if (!colbits && !colpart) return;
+    if (colbits) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) cmax[warp][4 * lane + e] = cm[e];
-    __syncthreads();
-    if (threadIdx.x < kAmCols) {
-        uint32_t m = 0u;
+        for (int e = 0; e < 4; ++e) cmax[warp][4 * lane + e] = cm[e];
+        __syncthreads();
+        if (threadIdx.x < kAmCols) {
+            uint32_t m = 0u;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) m = max(m, cmax[w][threadIdx.x]);
-        const int64_t c = (int64_t)blockIdx.y * kAmCols + threadIdx.x;
-        if (c < C && m) atomicMax(colbits + c, m);
+            for (int w = 0; w < 8; ++w) m = max(m, cmax[w][threadIdx.x]);
+            const int64_t c = (int64_t)blockIdx.y * kAmCols + threadIdx.x;
+            if (c < C && m) atomicMax(colbits + c, m);
+        }
+    }
+    if (colpart) {
+        float* fsum = reinterpret_cast<float*>(&cmax[0][0]);   // reuse the staging array
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fsum[warp * kAmCols + 4 * lane + e] = csum[e];
+        __syncthreads();
+        if (threadIdx.x < kAmCols) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += fsum[w * kAmCols + threadIdx.x];
+            const int64_t c = (int64_t)blockIdx.y * kAmCols + threadIdx.x;
+            if (c < C) colpart[(int64_t)blockIdx.x * C + c] = t;
+        }
     }
 }
 
 // Both layouts from one read: (R, C) fp32 -> rows split (R, 2*Cp) scaled per row AND transposed split (C, 2*Rp) scaled per
 // column (either may be NULL); the inverse scales go to inv_r (R,) / inv_c (C,).  64 x 64 tiles through shared memory.
-__global__ void __launch_bounds__(256) k_split2h_both(const float* __restrict__ in, const uint32_t* __restrict__ rowbits,
+__global__ void __launch_bounds__(256) k_split2h_both(const float* __restrict__ in, const float* __restrict__ mask,
+                                                      const uint32_t* __restrict__ rowbits,
                                                       const uint32_t* __restrict__ colbits, __half* __restrict__ out_r,
                                                       float* __restrict__ inv_r, __half* __restrict__ out_t, float* __restrict__ inv_c,
                                                       int64_t R, int64_t C, int64_t Cp, int64_t Rp) {
@@ -500,6 +533,10 @@ __global__ void __launch_bounds__(256) k_split2h_both(const float* __restrict__ 
             } else {
                 if (c < C) v0 = __ldg(in + r * C + c);
                 if (c + 1 < C) v1 = __ldg(in + r * C + c + 1);
+            }
+            if (mask) {
+                if (c < C && !(__ldg(mask + r * C + c) > 0.0f)) v0 = 0.0f;
+                if (c + 1 < C && !(__ldg(mask + r * C + c + 1) > 0.0f)) v1 = 0.0f;
             }
         }
         tile[i][2 * tx] = v0;
@@ -614,12 +651,55 @@ extern "C" int hvae_split2h_rows_f32(const float* src, void* dst, float* inv_sca
 // Both layouts of src (rows, cols): dst_rows (rows, 2*Cp) scaled per row with inv_rows (rows,), and dst_t (cols, 2*Rp)
 // - the split of src^T - scaled per COLUMN of src with inv_cols (cols,).  Either layout may be NULL.  workspace:
 // hvae_split2h_workspace_bytes.  (A maximum pass, then the split pass.)
+extern "C" size_t hvae_split2h_ex_workspace_bytes(int64_t rows, int64_t cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const size_t row_blocks = (size_t)((rows + x2::kAmRows - 1) / x2::kAmRows);
+    return ((size_t)(rows + cols) * 4 + 255) / 256 * 256 + row_blocks * (size_t)cols * 4 + 256;
+}
+
+// The general form: src optionally masked (elements where mask <= 0 count as zero: the ReLU backward folded into the
+// operand split of the gradient), either layout optional, and optionally the column sums of the (masked) src (the bias
+// gradient, out of the maximum pass's read).  workspace: hvae_split2h_ex_workspace_bytes.
+extern "C" int hvae_split2h_both_ex_f32(const float* src, const float* mask, void* dst_rows, float* inv_rows, void* dst_t,
+                                        float* inv_cols, float* colsum, int64_t rows, int64_t cols, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    if (rows <= 0 || cols <= 0) return HVAE_ESHAPE;
+    if (!src || (!dst_rows && !dst_t && !colsum) || (dst_rows && !inv_rows) || (dst_t && !inv_cols)) return HVAE_EARG;
+    if (!dst_t && !mask && !colsum) return hvae_split2h_rows_f32(src, dst_rows, inv_rows, rows, cols, stream);
+    if (!workspace || workspace_bytes < hvae_split2h_ex_workspace_bytes(rows, cols)) return HVAE_EARG;
+    const int64_t Cp = x2::kp_of(cols), Rp = x2::kp_of(rows);
+    if (Cp / 64 > 65535) return HVAE_ESHAPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t* colbits = (uint32_t*)workspace;
+    uint32_t* rowbits = colbits + cols;
+    float* colpart = (float*)((char*)workspace + ((size_t)(rows + cols) * 4 + 255) / 256 * 256);
+    if (cudaMemsetAsync(colbits, 0, (size_t)(cols + rows) * 4, s) != cudaSuccess) return HVAE_ELAUNCH;
+    const int64_t row_blocks = (rows + x2::kAmRows - 1) / x2::kAmRows;
+    {
+        dim3 grid((unsigned)row_blocks, (unsigned)((cols + x2::kAmCols - 1) / x2::kAmCols));
+        x2::k_absmax_rc<<<grid, 256, 0, s>>>(src, mask, dst_rows ? rowbits : nullptr, dst_t ? colbits : nullptr,
+                                             colsum ? colpart : nullptr, rows, cols);
+    }
+    if (colsum) {
+        SlabReducer red;
+        red.add(colpart, colsum, cols, (int)row_blocks);
+        red.launch(s);
+    }
+    if (dst_rows || dst_t) {
+        dim3 grid((unsigned)(Rp / 64), (unsigned)(Cp / 64));
+        x2::k_split2h_both<<<grid, 256, 0, s>>>(src, mask, rowbits, colbits, (__half*)dst_rows, inv_rows, (__half*)dst_t, inv_cols, rows,
+                                                cols, Cp, Rp);
+    }
+    return check_launch();
+}
+
 extern "C" int hvae_split2h_both_f32(const float* src, void* dst_rows, float* inv_rows, void* dst_t, float* inv_cols, int64_t rows,
                                      int64_t cols, void* workspace, size_t workspace_bytes, void* stream) {
     if (rows <= 0 || cols <= 0) return HVAE_ESHAPE;
     if (!src || (!dst_rows && !dst_t) || (dst_rows && !inv_rows) || (dst_t && !inv_cols)) return HVAE_EARG;
     if (!dst_t) return hvae_split2h_rows_f32(src, dst_rows, inv_rows, rows, cols, stream);
     if (!workspace || workspace_bytes < hvae_split2h_workspace_bytes(rows, cols)) return HVAE_EARG;
+    // the plain form needs only the row / column maxima: the first (rows + cols) words of the workspace
     const int64_t Cp = x2::kp_of(cols), Rp = x2::kp_of(rows);
     if (Cp / 64 > 65535) return HVAE_ESHAPE;
     cudaStream_t s = (cudaStream_t)stream;
@@ -628,10 +708,11 @@ extern "C" int hvae_split2h_both_f32(const float* src, void* dst_rows, float* in
     if (cudaMemsetAsync(colbits, 0, (size_t)(cols + rows) * 4, s) != cudaSuccess) return HVAE_ELAUNCH;
     {
         dim3 grid((unsigned)((rows + x2::kAmRows - 1) / x2::kAmRows), (unsigned)((cols + x2::kAmCols - 1) / x2::kAmCols));
-        x2::k_absmax_rc<<<grid, 256, 0, s>>>(src, dst_rows ? rowbits : nullptr, colbits, rows, cols);
+        x2::k_absmax_rc<<<grid, 256, 0, s>>>(src, nullptr, dst_rows ? rowbits : nullptr, colbits, nullptr, rows, cols);
     }
     dim3 grid((unsigned)(Rp / 64), (unsigned)(Cp / 64));
-    x2::k_split2h_both<<<grid, 256, 0, s>>>(src, rowbits, colbits, (__half*)dst_rows, inv_rows, (__half*)dst_t, inv_cols, rows, cols, Cp, Rp);
+    x2::k_split2h_both<<<grid, 256, 0, s>>>(src, nullptr, rowbits, colbits, (__half*)dst_rows, inv_rows, (__half*)dst_t, inv_cols, rows, cols,
+                                            Cp, Rp);
     return check_launch();
 }
 

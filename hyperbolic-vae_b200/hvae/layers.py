@@ -157,5 +157,6 @@ class Linear(nn.Linear):
     fp32-accurate GEMM (ops.linear); everything else defers to torch.  reference: the nn.Linear trunk layers of
     hyperbolic_vae/models/*.py and pvae's Enc/Dec."""
 
-    def forward(self, input):
-        return ops.linear(input, self.weight, self.bias)
+    def forward(self, input, relu: bool = False):
+        """relu=True (extension): relu(linear(input)) with the activation fused into the GEMM epilogue / gradient split."""
+        return ops.linear(input, self.weight, self.bias, relu=relu)

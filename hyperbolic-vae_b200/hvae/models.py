@@ -310,7 +310,10 @@ class PvaeMnist(nn.Module):
 
     def encode(self, x, clamp_sigma=False):
         """clamp_sigma: return sigma already clamped to RiemannianNormal's [0.1, 7] (one fused kernel with the softplus)."""
-        e = self.enc(x.view(x.shape[0], -1))
+        if self.fused and x.is_cuda:
+            e = self.enc[0](x.view(x.shape[0], -1), relu=True)   # Linear + ReLU: one GEMM, the mask inside the gradient split
+        else:
+            e = self.enc(x.view(x.shape[0], -1))
         mu = self.manifold.expmap0(self.fc21(e))
         h = self.fc22(e)
         if clamp_sigma and h.is_cuda:

@@ -1458,6 +1458,40 @@ def _(x, want_rows, want_t):
             torch.empty(cols if want_t else 0, dtype=torch.float32, device=dev))
 
 
+@_op("hvae::split2h_both_ex", mutates_args=())
+def split2h_both_ex(x: Tensor, mask: Optional[Tensor], want_rows: bool, want_t: bool, want_colsum: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """split2h_both of x with (optionally) the elements where mask <= 0 zeroed - the ReLU backward folded into the
+    gradient's operand split - and (optionally) the column sums of that masked x (the bias gradient) from the same pass:
+    -> (rows split, its scales, transposed split, its scales, colsum (cols,)); unwanted outputs come back empty."""
+    C.require_cuda(x, mask)
+    rows, cols = x.shape
+    dev = x.device
+    r = torch.empty((rows, 2 * _cp64(cols)) if want_rows else (0,), dtype=torch.float16, device=dev)
+    ri = torch.empty(rows if want_rows else 0, dtype=torch.float32, device=dev)
+    t = torch.empty((cols, 2 * _cp64(rows)) if want_t else (0,), dtype=torch.float16, device=dev)
+    ti = torch.empty(cols if want_t else 0, dtype=torch.float32, device=dev)
+    cs = torch.empty(cols if want_colsum else 0, dtype=torch.float32, device=dev)
+    if want_rows or want_t or want_colsum:
+        ws = _workspace(C.lib().hvae_split2h_ex_workspace_bytes(rows, cols), dev)
+        C.call("hvae_split2h_both_ex_f32", C.ptr(x), C.ptr(mask), C.ptr(r) if want_rows else None, C.ptr(ri) if want_rows else None,
+               C.ptr(t) if want_t else None, C.ptr(ti) if want_t else None, C.ptr(cs) if want_colsum else None, rows, cols,
+               C.ptr(ws), ws.numel(), C.stream())
+        general = want_t or want_colsum or mask is not None
+        C.launch_count += ((1 + (1 if want_colsum else 0) + (1 if (want_rows or want_t) else 0)) if general else 1) - 1
+    return r, ri, t, ti, cs
+
+
+@split2h_both_ex.register_fake
+def _(x, mask, want_rows, want_t, want_colsum):
+    rows, cols = x.shape
+    dev = x.device
+    return (torch.empty((rows, 2 * _cp64(cols)) if want_rows else (0,), dtype=torch.float16, device=dev),
+            torch.empty(rows if want_rows else 0, dtype=torch.float32, device=dev),
+            torch.empty((cols, 2 * _cp64(rows)) if want_t else (0,), dtype=torch.float16, device=dev),
+            torch.empty(cols if want_t else 0, dtype=torch.float32, device=dev),
+            torch.empty(cols if want_colsum else 0, dtype=torch.float32, device=dev))
+
+
 @_op("hvae::gemm_x2s", mutates_args=())
 def gemm_x2s(As: Tensor, inv_a: Tensor, Bs: Tensor, inv_b: Tensor, bias: Optional[Tensor], relu: bool, M: int, N: int,
              K: int) -> Tensor:
@@ -1481,16 +1515,18 @@ def _(As, inv_a, Bs, inv_b, bias, relu, M, N, K):
 
 
 @_op("hvae::linear_x2", mutates_args=())
-def linear_x2_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], need_gx: bool, need_gw: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """-> (y, split of x^T + its scales, split of W^T + its scales): as linear_x3, on the fp16 two-piece path."""
+def linear_x2_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], need_gx: bool, need_gw: bool, relu: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (y, split of x^T + its scales, split of W^T + its scales): as linear_x3, on the fp16 two-piece path.
+    relu: y = relu(x W^T + b) in the GEMM epilogue; the backward masks the upstream gradient by y > 0 inside its operand
+    split (no separate activation kernels in either direction)."""
     xs, xi, xts, xti = split2h_both(x, True, need_gw)
     ws, wi, wts, wti = split2h_both(weight, True, need_gx)
-    y = gemm_x2s(xs, xi, ws, wi, bias, False, x.shape[0], weight.shape[0], x.shape[1])
+    y = gemm_x2s(xs, xi, ws, wi, bias, relu, x.shape[0], weight.shape[0], x.shape[1])
     return y, xts, xti, wts, wti
 
 
 @linear_x2_fwd.register_fake
-def _(x, weight, bias, need_gx, need_gw):
+def _(x, weight, bias, need_gx, need_gw, relu):
     M, K = x.shape
     N = weight.shape[0]
     dev = x.device
@@ -1503,45 +1539,52 @@ def _(x, weight, bias, need_gx, need_gw):
 
 def _lx2_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)
-    x, weight, bias, need_gx, need_gw = inputs
-    ctx.save_for_backward(output[1], output[2], output[3], output[4])
+    x, weight, bias, need_gx, need_gw, relu = inputs
+    ctx.save_for_backward(output[1], output[2], output[3], output[4], *([output[0]] if relu else []))
     ctx.dims = (x.shape[0], weight.shape[0], x.shape[1])  # rows, out, in
     ctx.has_bias = bias is not None
     ctx.need = (need_gx, need_gw)
+    ctx.relu = relu
 
 
 def _lx2_backward(ctx, gy, *_unused):
     if gy is None:
-        return None, None, None, None, None
-    xts, xti, wts, wti = ctx.saved_tensors
+        return None, None, None, None, None, None
+    xts, xti, wts, wti = ctx.saved_tensors[:4]
+    y_act = ctx.saved_tensors[4] if ctx.relu else None
     M, n_out, n_in = ctx.dims
     need_gx, need_gw = ctx.need
     gy = _c(gy)
     gx = gw = gb = None
     want_gx = ctx.needs_input_grad[0] and need_gx
     want_gw = ctx.needs_input_grad[1] and need_gw
-    if want_gx or want_gw:
-        gs, gi, gts, gti = split2h_both(gy, want_gx, want_gw)
+    want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+    if want_gx or want_gw or want_gb:
+        # one pass for the row / column maxima, the ReLU mask and the bias gradient; one for the split(s)
+        gs, gi, gts, gti, cs = split2h_both_ex(gy, y_act, want_gx, want_gw, want_gb)
         if want_gx:
             gx = gemm_x2s(gs, gi, wts, wti, None, False, M, n_in, n_out)      # gy (M,out) . W (out,in)
         if want_gw:
             gw = gemm_x2s(gts, gti, xts, xti, None, False, n_out, n_in, M)    # gy^T (out,M) . x (M,in)
-    if ctx.has_bias and ctx.needs_input_grad[2]:
-        gb = colsum(gy)
-    return gx, gw, gb, None, None
+        if want_gb:
+            gb = cs
+    return gx, gw, gb, None, None, None
 
 
 linear_x2_fwd.register_autograd(_lx2_backward, setup_context=_lx2_setup)
 
 
-def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
-    """torch.nn.functional.linear semantics; the tensor-core fp32 path for GEMM-sized CUDA inputs."""
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], relu: bool = False) -> Tensor:
+    """torch.nn.functional.linear semantics (relu=True: followed by ReLU); the tensor-core fp32 path for GEMM-sized CUDA
+    inputs - there the activation runs in the GEMM epilogue and its backward inside the gradient's operand split."""
     if trunk_x3_eligible(x, weight) and _trunk_mode == "x2":
         lead = x.shape[:-1]
         grad_on = torch.is_grad_enabled()
         y = linear_x2_fwd(_rows(x), _c(weight), None if bias is None else _c(bias), grad_on and x.requires_grad,
-                          grad_on and weight.requires_grad)[0]
+                          grad_on and weight.requires_grad, relu)[0]
         return y.view(*lead, weight.shape[0])
+    if relu:
+        return torch.relu(linear(x, weight, bias))
     if trunk_x3_eligible(x, weight):
         lead = x.shape[:-1]
         grad_on = torch.is_grad_enabled()

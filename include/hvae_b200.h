@@ -326,6 +326,13 @@ int hvae_gemm_x3_f32(const float* A, int a_trans, const float* B, int b_trans, c
  *   hvae_gemm_x2s_plan: the tile width (128..256), split-K factor and TMA ring depth chosen for a problem. */
 size_t hvae_split2h_bytes(int64_t rows, int64_t cols);
 size_t hvae_split2h_workspace_bytes(int64_t rows, int64_t cols);
+/* general form: optional mask (same shape; elements where mask <= 0 count as zero - the ReLU backward of a fused
+ * Linear + ReLU layer folded into the gradient's operand split), either layout optional, optional colsum (cols,) = column
+ * sums of the (masked) src - the bias gradient, taken from the maximum pass's read. */
+size_t hvae_split2h_ex_workspace_bytes(int64_t rows, int64_t cols);
+int hvae_split2h_both_ex_f32(const float* src, const float* mask, void* dst_rows, float* inv_rows, void* dst_t,
+                             float* inv_cols, float* colsum, int64_t rows, int64_t cols, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int hvae_split2h_rows_f32(const float* src, void* dst, float* inv_scale, int64_t rows, int64_t cols, void* stream);
 int hvae_split2h_both_f32(const float* src, void* dst_rows, float* inv_rows, void* dst_t, float* inv_cols, int64_t rows,
                           int64_t cols, void* workspace, size_t workspace_bytes, void* stream);

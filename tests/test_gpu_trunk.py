@@ -226,6 +226,56 @@ def _linear_layer_forward_backward(mode):
     assert torch.equal(small(xs), torch.nn.functional.linear(xs, small.weight, small.bias))
 
 
+@pytest.mark.parametrize("rows,n_in,n_out,need_gx", [(4096, 784, 600, False), (4096, 600, 784, True), (1000, 333, 601, True), (130, 257, 77, True)])
+def test_linear_relu_fused_forward_backward(rows, n_in, n_out, need_gx):
+    """Linear(relu=True): ReLU in the GEMM epilogue, its backward mask inside the gradient's operand split, the bias
+    gradient out of the same maximum pass - against float64 relu(linear(x)) and its autograd."""
+    from hvae import layers, ops
+
+    torch.manual_seed(rows + n_in)
+    lin = layers.Linear(n_in, n_out).cuda()
+    x = torch.randn(rows, n_in, device="cuda", requires_grad=need_gx)
+    gy = torch.randn(rows, n_out, device="cuda")
+    assert ops.trunk_x3_eligible(x, lin.weight) and ops.get_trunk_mode() == "x2"
+    y = lin(x, relu=True)
+    y.backward(gy)
+    xd = x.detach().double().requires_grad_(True)
+    Wd, bd = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    zd = torch.nn.functional.linear(xd, Wd, bd)
+    # pre-activations within fp32 rounding of zero may land on either side of the kink: take the mask the kernel used
+    mask = (y.detach() > 0).double()
+    assert float(((zd.detach() > 0).double() - mask).abs().sum()) <= 1e-4 * mask.numel()
+    yd = zd * mask
+    yd.backward(gy.double())
+    pairs = [(y, yd), (lin.weight.grad, Wd.grad), (lin.bias.grad, bd.grad)] + ([(x.grad, xd.grad)] if need_gx else [])
+    for got, ref in pairs:
+        assert _rel(got, ref.detach()) < 2e-6
+    assert float((y < 0).sum()) == 0 and 0.3 < float((y == 0).float().mean()) < 0.7
+
+
+@pytest.mark.parametrize("R,C", [(4096, 784), (1000, 77), (5, 3), (33, 600), (64, 130)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_split2h_both_ex_mask_and_colsum(R, C, masked):
+    """The general operand split: masked input == the plain split of the masked tensor (bit for bit), column sums == a
+    float64 sum of the masked tensor."""
+    from hvae import ops
+
+    torch.manual_seed(R * 3 + C)
+    x = torch.randn(R, C, device="cuda") * torch.rand(R, 1, device="cuda").mul(3).exp()
+    m = torch.randn(R, C, device="cuda") if masked else None
+    xm = x * (m > 0) if masked else x
+    r, ri, t, ti, cs = ops.split2h_both_ex(x, m, True, True, True)
+    r0, ri0, t0, ti0 = ops.split2h_both(xm.contiguous(), True, True)
+    assert torch.equal(r, r0) and torch.equal(ri, ri0) and torch.equal(t, t0) and torch.equal(ti, ti0)
+    ref = xm.double().sum(0)
+    assert float((cs.double() - ref).abs().max()) < 1e-5 * float(xm.double().abs().sum(0).max() + 1e-30)
+    # column sums alone / transposed layout alone
+    _, _, _, _, cs2 = ops.split2h_both_ex(x, m, False, False, True)
+    assert torch.equal(cs, cs2)
+    _, _, t3, ti3, _ = ops.split2h_both_ex(x, m, False, True, False)
+    assert torch.equal(t3, t0) and torch.equal(ti3, ti0)
+
+
 @pytest.mark.parametrize("S,B,N", [(1, 4096, 784), (3, 17, 10), (2, 5, 1)])
 def test_bernoulli_nll_rows(S, B, N):
     from hvae import ops
