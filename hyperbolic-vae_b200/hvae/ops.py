@@ -1263,10 +1263,25 @@ def get_trunk_mode() -> str:
     return _trunk_mode
 
 
+# Below this many flops (2MNK) a dense layer stays on cuBLAS fp32: the tensor-core path is a pipeline of 5-7 launches per
+# direction (operand maxima, splits, GEMM, reductions) - ~15 us of fixed cost that only pays off once the GEMM itself is
+# worth that much (measured cross-over ~0.5 GFLOP: config 1's 128 x 784 x 64 layers were 16 % slower on it).
+_trunk_min_flops = 2.5e8
+
+
+def set_trunk_min_flops(flops: float) -> float:
+    """Smallest 2MNK routed to the tensor-core trunk path; returns the previous value (tests pass 0 to force the path)."""
+    global _trunk_min_flops
+    old, _trunk_min_flops = _trunk_min_flops, float(flops)
+    return old
+
+
 def trunk_x3_eligible(x: Tensor, weight: Tensor) -> bool:
     """GEMM-sized fp32 CUDA problem and a tensor-core trunk mode ('x2' or 'x3')."""
+    rows = x.numel() // x.shape[-1]
     return (_trunk_mode in ("x2", "x3") and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
-            and x.numel() // x.shape[-1] >= 128 and weight.shape[0] >= 64 and weight.shape[1] >= 64)
+            and rows >= 128 and weight.shape[0] >= 64 and weight.shape[1] >= 64
+            and 2.0 * rows * weight.shape[0] * weight.shape[1] >= _trunk_min_flops)
 
 
 @_op("hvae::gemm_x3", mutates_args=())

@@ -220,10 +220,15 @@ def _linear_layer_forward_backward(mode):
         ops.set_trunk_mode(mode)
     assert torch.allclose(y_t, ref_lin(x))
     assert _rel(y, y_t.detach().double()) < 2e-6
-    # small shapes defer to torch
+    # small shapes defer to torch (too narrow, or too few flops to pay for the operand-split pipeline)
     small = layers.Linear(16, 8).cuda()
     xs = torch.randn(4, 16, device="cuda")
     assert torch.equal(small(xs), torch.nn.functional.linear(xs, small.weight, small.bias))
+    tiny = layers.Linear(784, 64).cuda()
+    xt = torch.randn(128, 784, device="cuda")
+    assert not ops.trunk_x3_eligible(xt, tiny.weight)
+    assert torch.equal(tiny(xt), torch.nn.functional.linear(xt, tiny.weight, tiny.bias))
+    assert torch.equal(tiny(xt, relu=True), torch.relu(torch.nn.functional.linear(xt, tiny.weight, tiny.bias)))
 
 
 @pytest.mark.parametrize("rows,n_in,n_out,need_gx", [(4096, 784, 600, False), (4096, 600, 784, True), (1000, 333, 601, True), (130, 257, 77, True)])
@@ -236,9 +241,13 @@ def test_linear_relu_fused_forward_backward(rows, n_in, n_out, need_gx):
     lin = layers.Linear(n_in, n_out).cuda()
     x = torch.randn(rows, n_in, device="cuda", requires_grad=need_gx)
     gy = torch.randn(rows, n_out, device="cuda")
-    assert ops.trunk_x3_eligible(x, lin.weight) and ops.get_trunk_mode() == "x2"
-    y = lin(x, relu=True)
-    y.backward(gy)
+    old_min = ops.set_trunk_min_flops(0.0)   # the small shapes too: the tensor-core path, not the cuBLAS route for tiny layers
+    try:
+        assert ops.trunk_x3_eligible(x, lin.weight) and ops.get_trunk_mode() == "x2"
+        y = lin(x, relu=True)
+        y.backward(gy)
+    finally:
+        ops.set_trunk_min_flops(old_min)
     xd = x.detach().double().requires_grad_(True)
     Wd, bd = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
     zd = torch.nn.functional.linear(xd, Wd, bd)
