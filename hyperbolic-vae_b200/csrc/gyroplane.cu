@@ -561,3 +561,14 @@ extern "C" int hvae_gyroplane_bwd_f32(const float* x, const float* p, const floa
                                       uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
     return hvae_gyroplane_relu_bwd_f32(x, p, a, nullptr, gout, gx, gp, ga, gbias, B, D, P, c, flags, workspace, workspace_bytes, stream);
 }
+
+// the grid the backward's pair kernel runs for a problem (host-only; bench.py / tests report it)
+extern "C" int hvae_gyroplane_bwd_plan(int64_t B, int64_t D, int64_t P, int* planes_per_chunk, int* chunks, int* ctas) {
+    if (B <= 0 || P <= 0 || D <= 0 || D > kGyroMaxD) return HVAE_ESHAPE;
+    int ppc = 0, nch = 0;
+    gyro_x_plan(B, P, D, &ppc, &nch);
+    if (planes_per_chunk) *planes_per_chunk = ppc;
+    if (chunks) *chunks = nch;
+    if (ctas) *ctas = (int)(((B + kGyroBxThreads - 1) / kGyroBxThreads) * nch);
+    return HVAE_OK;
+}

@@ -112,6 +112,9 @@ int hvae_gyroplane_bwd_f32(const float* x, const float* p, const float* a, const
                            float* gx, float* gp, float* ga, float* gbias,
                            int64_t B, int64_t D, int64_t P, float c, uint32_t flags,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* host-only: the grid of the backward's pair kernel for a problem - plane chunks sized so that the CTAs fill the resident
+ * slots of the 148 SMs in whole waves (config 2: 23 chunks x 27 planes, 736 CTAs on 740 slots) */
+int hvae_gyroplane_bwd_plan(int64_t B, int64_t D, int64_t P, int* planes_per_chunk, int* chunks, int* ctas);
 int hvae_gyroplane_relu_bwd_f32(const float* x, const float* p, const float* a, const float* bias, const float* gout,
                                 float* gx, float* gp, float* ga, float* gbias,
                                 int64_t B, int64_t D, int64_t P, float c, uint32_t flags,
