@@ -11,7 +11,13 @@
 //   <diff,a> = (-A<p,a> + Bc<x,a>)/den,   |diff|^2 = (A^2|p|^2 - 2 A Bc <p,x> + Bc^2|x|^2)/den^2
 // so one pass over D per (row, plane) pair gives <p,x> (and <a,x>), and the rest is a scalar epilogue.
 // Memory is O(B*P) for the output only.  Algorithmic bytes: fwd 4(BD + 2PD + BP), bwd 4(BP + 2BD + 4PD).
-// At D <= 64 the kernel is bound by the B*P output write / epilogue math, not by the FMA count.
+// At D <= 64 the kernels are bound by the pair function's instructions and by latency, not by bytes or FMAs:
+//  * the pair function has two lean closed forms (gyro_pair.cuh: unprojected - one division; projected - the common
+//    case for latent points beyond the fp32 projection radius - one rsqrt) and falls back to the general clamp-by-clamp
+//    form only where a clamp binds;
+//  * the flag word is a template constant for the two combinations the layers use;
+//  * grids are sized in whole waves of the resident-CTA slots (gyro_fwd_rows_per_cta, gyro_x_plan);
+//  * HVAE_GYRO_RELU fuses the decoder's ReLU (forward clamp, backward mask from the recomputed sign).
 #include "hvae_common.cuh"
 #include "gyro_pair.cuh"
 
