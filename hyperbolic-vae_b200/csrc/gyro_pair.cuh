@@ -293,6 +293,7 @@ __device__ __forceinline__ GyroPairGrad gyro_pair_lean_bwd(int mode, float g, co
 
 // the general path out of line: it runs for a handful of pairs (if any), and inlining it next to the lean path in an
 // 8-row unrolled loop would multiply the kernel's code size for nothing
+#pragma nv_diag_suppress 177   // used by the SIMT kernels only; the tensor-core translation units include this header too
 static __device__ __noinline__ float gyro_pair_fwd_general(float e, float q, float qa, float x2, float p2, float pa, float an_raw,
                                                     GyroParams P) {
     GyroPairCtx k;
@@ -314,5 +315,7 @@ static __device__ __noinline__ GyroPairGrad gyro_pair_grad_general(float g, floa
     r.g_used = g;
     return r;
 }
+
+#pragma nv_diag_default 177
 
 }  // namespace hvae
