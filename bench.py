@@ -522,7 +522,11 @@ def run_step(args, name, wl):
             evs.append((s, e))
         barrier()
         t_wall = time.perf_counter() - t_wall0
-        dev_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+        per_ms = sorted(s.elapsed_time(e) for s, e in evs)
+        dev_s = sum(per_ms) * 1e-3
+        # median and p10 / p90 of the per-step device times (this rank's)
+        step_pct = {"p10": per_ms[int(0.10 * (len(per_ms) - 1))], "p50": per_ms[int(0.50 * (len(per_ms) - 1))],
+                    "p90": per_ms[int(0.90 * (len(per_ms) - 1))]}
         # ---- e2e: host batch -> pinned H2D -> TrainStep (public API) -> D2H loss, every step; the H2D of step i+1 is
         # prefetched on a copy stream under step i, the host waits for every step's loss
         for _ in range(3):
@@ -591,6 +595,7 @@ def run_step(args, name, wl):
                     "note": "at this workload's sizes every own kernel moves < 1 MB: the step is launch/latency-bound (graph replay); "
                             "the HBM fraction is the same kernel at large row counts"}
         line["roofline"] = roof
+        line["ms_per_step_percentiles"] = step_pct
         line["kernel_rooflines"] = big
         if world == 1 and name == "cfg2" and not args.no_tc_rooflines:
             line["tc_rooflines"] = tc_rooflines(device, pk, args.tc_logB)
