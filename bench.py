@@ -562,7 +562,7 @@ def run_step(args, name, wl):
                               "none (the metric is fwd+bwd; --optimizer adds the fused Riemannian Adam step)",
                  "l2": "256 MiB buffer written between timed steps (L2 flush)",
                  "trunk": "hvae.layers.Linear -> tcgen05 two-piece fp16 GEMM with power-of-two row scales (fp32-accurate, own kernel) for GEMM-sized layers; "
-                          "small layers and the conv stack of model B run on cuBLAS / cuDNN with TF32 off"}
+                          "layers narrower than 64 or below 0.25 GFLOP (2MNK) and the conv stack of model B run on cuBLAS / cuDNN with TF32 off"}
         line = {
             "metric": "train samples/sec (fwd+bwd)", "value": world * B * args.steps / dev_s, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3,
